@@ -1,0 +1,150 @@
+/* lifusim.h -- C ABI of the B200-native k-space acoustic solver behind
+ * openlifu.sim.run_simulation.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of what the
+ * reference adapter /root/reference/src/openlifu/sim/kwave_if.py does through
+ * k-wave-python 0.4.0 (kWaveGrid / kWaveArray / kWaveMedium / kSensor / kSource /
+ * kspaceFirstOrder3D -> HDF5 -> kspaceFirstOrder-OMP|CUDA subprocess).  The reference
+ * has no FFI of its own (it is pure Python); the binding a
+ * maintainer adds is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *   - every data pointer may be a HOST or a DEVICE pointer (unified virtual addressing
+ *     resolves it; copies use cudaMemcpyDefault on the handle's stream).
+ *   - 3-D arrays are "x fastest" = Fortran order of the reference's (Nx,Ny,Nz) arrays
+ *     = what kwave_if.py:132-141 reshapes with order='F'.
+ *   - every function returns 0 on success or a negative lifu_status; the message of the
+ *     last failure on the calling thread is lifu_last_error().  No exception crosses.
+ *   - a handle is bound to one (device, stream); it is not thread-safe; distinct handles
+ *     may be used concurrently (one per GPU when foci are sharded).
+ *   - the handle never frees or retains caller buffers after the call returns.
+ */
+#ifndef LIFUSIM_H
+#define LIFUSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIFUSIM_ABI_VERSION 1
+
+typedef enum lifu_status {
+  LIFU_OK = 0,
+  LIFU_ERR_INVALID = -1,   /* bad argument */
+  LIFU_ERR_CUDA = -2,      /* CUDA runtime failure */
+  LIFU_ERR_CUFFT = -3,     /* cuFFT failure */
+  LIFU_ERR_STATE = -4,     /* call order violated (e.g. run before set_medium) */
+  LIFU_ERR_NOMEM = -5
+} lifu_status;
+
+/* alpha_mode of kWaveMedium (kwave_if.py:56,62).  The k-Wave binary receives only
+ * alpha_coeff/alpha_power, so LIFU_ALPHA_BINARY (both terms) is what the reference's
+ * OMP path computes (SURVEY.md ledger A7). */
+typedef enum lifu_alpha_mode {
+  LIFU_ALPHA_BINARY = 0,        /* absorption (tau) and dispersion (eta) terms */
+  LIFU_ALPHA_NO_DISPERSION = 1, /* eta = 0 */
+  LIFU_ALPHA_NO_ABSORPTION = 2  /* tau = 0 */
+} lifu_alpha_mode;
+
+typedef enum lifu_source_mode {
+  LIFU_SOURCE_ADDITIVE = 0,               /* k-space corrected additive source (k-Wave default) */
+  LIFU_SOURCE_ADDITIVE_NO_CORRECTION = 1
+} lifu_source_mode;
+
+/* Grid + time axis.  Replaces get_kgrid (kwave_if.py:13-27) and the pml_auto /
+ * pml_inside=False expansion done inside kspaceFirstOrder3D (kwave_if.py:117-122). */
+typedef struct lifu_grid {
+  int32_t n[3];     /* inner grid size Nx,Ny,Nz = len(coords) (kwave_if.py:19) */
+  int32_t pml[3];   /* PML thickness per axis; any entry < 0 -> pml_auto for that axis */
+  double d[3];      /* spacing in metres (kwave_if.py:20) */
+  double dt;        /* time step [s] */
+  int32_t nt;       /* number of time steps */
+  double pml_alpha; /* <= 0 -> 2.0 (k-Wave default) */
+  double c_ref;     /* <= 0 -> max(c0) once the medium is set (k-Wave default) */
+} lifu_grid;
+
+typedef struct lifu_stats {
+  int64_t voxels;          /* expanded grid voxels advanced per step (incl. PML) */
+  int32_t n_exp[3];        /* expanded grid size */
+  int32_t pml[3];
+  int32_t steps;           /* time steps executed */
+  int32_t source_steps;    /* steps on which the source was active */
+  int64_t kernel_launches; /* hand-written kernels launched inside the time loop */
+  int64_t fft_launches;    /* FFT transforms executed inside the time loop */
+  double loop_ms;          /* CUDA-event time of the time loop on the handle's stream */
+  double setup_ms;         /* CUDA-event time of uploads/initialisation in lifu_run */
+  double bytes_per_voxel_step; /* algorithmic bytes model, averaged over steps */
+  int32_t homogeneous;
+  int32_t absorbing;
+} lifu_stats;
+
+typedef struct lifu_sim lifu_sim; /* opaque */
+
+/* ---- pure host helpers (no GPU needed) -------------------------------------------- */
+int lifu_abi_version(void);
+const char* lifu_last_error(void);
+/* kWaveGrid.makeTime(c_ref, cfl) as called at kwave_if.py:22-23; writes nt, dt. */
+int lifu_make_time(const int32_t n[3], const double d[3], double c_ref, double cfl,
+                   int32_t* nt, double* dt);
+/* get_optimal_pml_size for pml_auto=True (kwave_if.py:118): range [10,40]. */
+int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]);
+
+/* ---- lifecycle --------------------------------------------------------------------- */
+int lifu_create(const lifu_grid* grid, int device, void* cuda_stream, lifu_sim** out);
+int lifu_destroy(lifu_sim* sim);
+
+/* Replaces get_medium (kwave_if.py:49-63) + the medium expansion / staggered density /
+ * absorption coefficients derived inside kspaceFirstOrder3D.  Maps are float32 on the
+ * INNER grid, x fastest.  homogeneous != 0: each pointer addresses ONE float. */
+int lifu_set_medium(lifu_sim* sim, const float* c0, const float* rho0, const float* alpha_db,
+                    float alpha_power, int alpha_mode, int homogeneous);
+
+/* Replaces get_karray + get_array_binary_mask + the weight half of
+ * get_distributed_source_signal (kwave_if.py:29-47,75-77): off-grid rectangular elements
+ * spread with the truncated-sinc band-limited interpolant, computed on the GPU.
+ *   pos_m     [n_el*3] element centres in metres in the k-Wave grid frame, i.e. already
+ *             shifted by array_offset = -mean(coords) (kwave_if.py:108)
+ *   size_m    [n_el*2] (width, length)
+ *   angle_deg [n_el*3] (el, az, roll) = rotations about x, y, z (element.py:216-226)
+ * Host pointers (float64).  Returns the number of source points through n_src. */
+int lifu_set_elements(lifu_sim* sim, int32_t n_el, const double* pos_m, const double* size_m,
+                      const double* angle_deg, double bli_tolerance, int32_t upsampling_rate,
+                      int64_t* n_src);
+
+/* Explicit alternative to lifu_set_elements: caller supplies the mask indices (sorted,
+ * x-fastest linear, INNER grid) and the weights as CSR over source points. */
+int lifu_set_source_geometry(lifu_sim* sim, const int64_t* idx, const int32_t* row_ptr,
+                             const int32_t* col_elem, const float* w, int64_t n_src,
+                             int64_t nnz, int32_t n_el);
+
+/* Read back the geometry built by either call above (for parity checks / caching --
+ * the reference's dead grid-weights cache API, db/database.py:41-55).
+ * Any output pointer may be NULL.  Sizes: idx[n_src], row_ptr[n_src+1], col/w[nnz]. */
+int lifu_get_source_sizes(lifu_sim* sim, int64_t* n_src, int64_t* nnz, int32_t* n_el);
+int lifu_get_source_geometry(lifu_sim* sim, int64_t* idx, int32_t* row_ptr, int32_t* col_elem,
+                             float* w);
+
+/* Replaces the drive-signal half: kwave_if.py:101-103 + Transducer.calc_output
+ * (xdc/transducer.py:95-112).  Element e emits gains[e]*base_signal[t - delay_samples[e]].
+ * delay_samples[e] = int(delay_e/dt) is computed by the host (integer, bit-exact). */
+int lifu_set_drive(lifu_sim* sim, const float* base_signal, int32_t n_base,
+                   const int32_t* delay_samples, const float* gains, int32_t n_el,
+                   int source_mode);
+
+/* Replaces kspaceFirstOrder3D(...) with sensor.record=['p_max','p_min'] over the whole
+ * inner grid (kwave_if.py:65-69,124-129).  p_max/p_min: float32[Nx*Ny*Nz] x fastest; p_min is
+ * the raw minimum (the adapter negates it, kwave_if.py:136).  stats may be NULL. */
+int lifu_run(lifu_sim* sim, float* p_max, float* p_min, lifu_stats* stats);
+
+/* Debug / test access to the state after lifu_run: which = 0 p, 1..3 u_x,u_y,u_z,
+ * 4..6 rho_x,rho_y,rho_z; out: float32 on the EXPANDED grid, x fastest. */
+int lifu_get_field(lifu_sim* sim, int which, float* out);
+int lifu_get_info(lifu_sim* sim, lifu_stats* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIFUSIM_H */

@@ -1,0 +1,100 @@
+// common.cuh -- shared declarations of liblifusim (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lifusim.h"
+
+namespace lifu {
+
+void set_error(const char* fmt, ...);
+
+#define LIFU_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      lifu::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call,              \
+                      cudaGetErrorString(e__));                                          \
+      return LIFU_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+#define LIFU_CUFFT(call)                                                                 \
+  do {                                                                                   \
+    cufftResult r__ = (call);                                                            \
+    if (r__ != CUFFT_SUCCESS) {                                                          \
+      lifu::set_error("%s:%d cuFFT error %d in %s", __FILE__, __LINE__, (int)r__, #call); \
+      return LIFU_ERR_CUFFT;                                                             \
+    }                                                                                    \
+  } while (0)
+
+#define LIFU_CHECK(call)          \
+  do {                            \
+    int s__ = (call);             \
+    if (s__ != LIFU_OK) return s__; \
+  } while (0)
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// Device-side view of everything the step kernels need.  Passed by value.
+struct StepParams {
+  int Nx, Ny, Nz, Nxh;        // expanded grid, half-spectrum length along x
+  int nx, ny, nz;             // inner grid
+  int px, py, pz;             // PML thickness
+  long long V;                // Nx*Ny*Nz
+  long long Vh;               // Nxh*Ny*Nz
+  long long RS, CS;           // strides between batched real / complex fields
+  float invN;                 // 1/(Nx*Ny*Nz): cuFFT transforms are unnormalised
+  // 1-D tables
+  const float2 *dpx, *dpy, *dpz;   // i k exp(+i k d/2)
+  const float2 *dnx, *dny, *dnz;   // i k exp(-i k d/2)
+  const float *ax2, *ay2, *az2;    // (c_ref dt k/2)^2 per axis  -> kappa = sinc(sqrt(sum))
+  const float *kx2, *ky2, *kz2;    // k^2 per axis (absorption operators)
+  const float *pmlx, *pmly, *pmlz, *sgx, *sgy, *sgz;
+  // medium
+  int homogeneous;
+  float dt_rho0_sg_s, dt_rho0_s, c2_s, rho0_s, tau_s, eta_s;   // scalars (homogeneous)
+  const float* dt_rho0_sg;    // [3][RS]  dt / rho0 staggered
+  const float* dt_rho0;       // [RS]     dt * rho0
+  const float* rho0;          // [RS]
+  const float* c2;            // [RS]
+  const float* tau;           // [RS]
+  const float* eta;           // [RS]
+  float y_minus2_half, y_minus1_half;  // (y-2)/2 and (y-1)/2 for the fractional Laplacians
+  // state
+  float* p;                   // [RS]
+  float* u;                   // [3][RS]
+  float* rho;                 // [3][RS]
+  float* r3;                  // [3][RS] scratch: pressure gradients, then velocity gradients
+  float* r1;                  // [RS]    scratch
+  float* S;                   // [RS]    sparse source field (zeros off the mask)
+  float* Sf;                  // [RS]    k-space filtered source field
+  float2* c1;                 // [CS]    spectrum scratch
+  float2* c3;                 // [3][CS] spectrum scratch
+  float* pmax;                // inner grid, x fastest
+  float* pmin;
+  int* step;                  // device-side time-step counter
+};
+
+struct SourceParams {
+  long long n_src;
+  const long long* lin_exp;   // expanded-grid linear index per source point
+  const int* row_ptr;
+  const int* col;
+  const float* w;
+  const float* scale;         // 2 dt / (3 c0 dx) per point
+  const float* base;          // base drive signal
+  int n_base;
+  const int* delay;           // per element
+  const float* gain;          // per element
+};
+
+}  // namespace lifu

@@ -1,0 +1,759 @@
+// lifusim.cu -- C ABI (include/lifusim.h) and time-loop orchestration of the B200 k-space solver.
+//
+// Replaces, for the path openlifu.sim.run_simulation drives, what k-wave-python's
+// kspaceFirstOrder3D + the kspaceFirstOrder-OMP/-CUDA binary do
+// (/root/reference/src/openlifu/sim/kwave_if.py:117-129): PML sizing and grid expansion,
+// k-space operators, the time loop and the p_max/p_min sensor reduction.
+#include <cstdarg>
+
+#include "sim.cuh"
+#include "step_kernels.cuh"
+
+namespace lifu {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int dev_alloc(lifu_sim* s, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? LIFU_ERR_NOMEM : LIFU_ERR_CUDA;
+  }
+  s->allocs.push_back(*p);
+  return LIFU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side grid logic
+static int largest_prime_factor(int n) {
+  int best = 1;
+  for (int p = 2; (long long)p * p <= n; ++p)
+    while (n % p == 0) { best = p; n /= p; }
+  if (n > 1) best = n;
+  return best;
+}
+
+static void pml_auto(const int32_t n[3], int32_t out[3]) {
+  for (int a = 0; a < 3; ++a) {
+    int best_p = 10, best_f = INT32_MAX;
+    for (int p = 10; p <= 40; ++p) {
+      int f = largest_prime_factor(n[a] + 2 * p);
+      if (f < best_f) { best_f = f; best_p = p; }   // first minimum wins
+    }
+    out[a] = best_p;
+  }
+}
+
+// kWaveGrid wavenumber of FFT bin i (ifftshifted; Nyquist negative for even N)
+static double k_fft(int N, double d, int i) {
+  int j = i <= (N - 1) / 2 ? i : i - N;   // even N: bin N/2 -> -N/2
+  return (2.0 * M_PI / d) * ((double)j / (double)N);
+}
+
+static void pml_profile(int N, double d, double dt, double c, int size, double alpha, bool sg,
+                        std::vector<float>& out) {
+  out.assign(N, 1.0f);
+  for (int i = 1; i <= size; ++i) {
+    double x = (double)i;
+    double l, r;
+    if (sg) {
+      l = alpha * (c / d) * std::pow(((x + 0.5) - size - 1.0) / (0.0 - size), 4.0);
+      r = alpha * (c / d) * std::pow((x + 0.5) / size, 4.0);
+    } else {
+      l = alpha * (c / d) * std::pow((x - size - 1.0) / (0.0 - size), 4.0);
+      r = alpha * (c / d) * std::pow(x / size, 4.0);
+    }
+    out[i - 1] = (float)std::exp(-l * dt / 2.0);
+    out[N - size + i - 1] = (float)std::exp(-r * dt / 2.0);
+  }
+}
+
+// Build every 1-D table that depends on c_ref; called once c_ref is known.
+static int build_tables(lifu_sim* s) {
+  const int Nx = s->N[0], Ny = s->N[1], Nz = s->N[2], Nxh = s->Nxh;
+  const double* d = s->grid.d;
+  const double dt = s->grid.dt, c = s->c_ref;
+  const double alpha = s->grid.pml_alpha > 0 ? s->grid.pml_alpha : 2.0;
+  std::vector<float> host;
+  auto push = [&](const std::vector<float>& v) {
+    size_t off = host.size();
+    host.insert(host.end(), v.begin(), v.end());
+    while (host.size() % 4) host.push_back(0.f);   // keep every table 16-byte aligned
+    return off;
+  };
+  size_t off_dp[3], off_dn[3], off_a2[3], off_k2[3], off_pml[3], off_sg[3];
+  const int Ns[3] = {Nx, Ny, Nz};
+  for (int a = 0; a < 3; ++a) {
+    int len = a == 0 ? Nxh : Ns[a];
+    std::vector<float> dp(2 * len), dn(2 * len), a2(len), k2(len);
+    for (int i = 0; i < len; ++i) {
+      double k = k_fft(Ns[a], d[a], i);
+      // i k exp(+-i k d/2) = k * (-+sin(k d/2) + i cos(k d/2))
+      double sn = std::sin(k * d[a] / 2.0), cs = std::cos(k * d[a] / 2.0);
+      dp[2 * i] = (float)(-k * sn); dp[2 * i + 1] = (float)(k * cs);
+      dn[2 * i] = (float)(k * sn);  dn[2 * i + 1] = (float)(k * cs);
+      double arg = c * k * dt / 2.0;
+      a2[i] = (float)(arg * arg);
+      k2[i] = (float)(k * k);
+    }
+    off_dp[a] = push(dp); off_dn[a] = push(dn); off_a2[a] = push(a2); off_k2[a] = push(k2);
+    std::vector<float> pm, sg;
+    pml_profile(Ns[a], d[a], dt, c, s->pml[a], alpha, false, pm);
+    pml_profile(Ns[a], d[a], dt, c, s->pml[a], alpha, true, sg);
+    off_pml[a] = push(pm); off_sg[a] = push(sg);
+  }
+  if (!s->d_tables) LIFU_CHECK(dev_alloc(s, (void**)&s->d_tables, host.size() * sizeof(float)));
+  LIFU_CUDA(cudaMemcpyAsync(s->d_tables, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+  LIFU_CUDA(cudaStreamSynchronize(s->stream));
+  StepParams& P = s->P;
+  const float* T = s->d_tables;
+  P.dpx = (const float2*)(T + off_dp[0]); P.dpy = (const float2*)(T + off_dp[1]); P.dpz = (const float2*)(T + off_dp[2]);
+  P.dnx = (const float2*)(T + off_dn[0]); P.dny = (const float2*)(T + off_dn[1]); P.dnz = (const float2*)(T + off_dn[2]);
+  P.ax2 = T + off_a2[0]; P.ay2 = T + off_a2[1]; P.az2 = T + off_a2[2];
+  P.kx2 = T + off_k2[0]; P.ky2 = T + off_k2[1]; P.kz2 = T + off_k2[2];
+  P.pmlx = T + off_pml[0]; P.pmly = T + off_pml[1]; P.pmlz = T + off_pml[2];
+  P.sgx = T + off_sg[0]; P.sgy = T + off_sg[1]; P.sgz = T + off_sg[2];
+  s->tables_ready = true;
+  return LIFU_OK;
+}
+
+static int make_plan(lifu_sim* s, cufftHandle* h, cufftType type, int batch, size_t* ws) {
+  int n[3] = {s->N[2], s->N[1], s->N[0]};
+  int rembed[3] = {s->N[2], s->N[1], s->N[0]};
+  int cembed[3] = {s->N[2], s->N[1], s->Nxh};
+  LIFU_CUFFT(cufftCreate(h));
+  LIFU_CUFFT(cufftSetAutoAllocation(*h, 0));
+  size_t w = 0;
+  if (type == CUFFT_R2C) {
+    LIFU_CUFFT(cufftMakePlanMany(*h, 3, n, rembed, 1, (int)s->RS, cembed, 1, (int)s->CS, CUFFT_R2C, batch, &w));
+  } else {
+    LIFU_CUFFT(cufftMakePlanMany(*h, 3, n, cembed, 1, (int)s->CS, rembed, 1, (int)s->RS, CUFFT_C2R, batch, &w));
+  }
+  LIFU_CUFFT(cufftSetStream(*h, s->stream));
+  if (w > *ws) *ws = w;
+  return LIFU_OK;
+}
+
+static int build_plans(lifu_sim* s) {
+  if (s->plans_ready) return LIFU_OK;
+  if (s->RS >= (1LL << 31)) { set_error("grid too large for a single-GPU cuFFT plan"); return LIFU_ERR_INVALID; }
+  size_t ws = 0;
+  LIFU_CHECK(make_plan(s, &s->r2c1, CUFFT_R2C, 1, &ws));
+  LIFU_CHECK(make_plan(s, &s->r2c3, CUFFT_R2C, 3, &ws));
+  LIFU_CHECK(make_plan(s, &s->c2r1, CUFFT_C2R, 1, &ws));
+  LIFU_CHECK(make_plan(s, &s->c2r3, CUFFT_C2R, 3, &ws));
+  LIFU_CHECK(make_plan(s, &s->r2c2, CUFFT_R2C, 2, &ws));
+  LIFU_CHECK(make_plan(s, &s->c2r2, CUFFT_C2R, 2, &ws));
+  s->work_bytes = ws;
+  LIFU_CHECK(dev_alloc(s, &s->d_work, ws));
+  cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
+  for (cufftHandle h : hs) LIFU_CUFFT(cufftSetWorkArea(h, s->d_work));
+  s->plans_ready = true;
+  return LIFU_OK;
+}
+
+int upload_source_points(lifu_sim* s) {
+  // (re)compute expanded-grid indices and the additive-source scale once both the geometry and
+  // the medium are known
+  if (!s->geometry_set || !s->medium_set) return LIFU_OK;
+  if (s->d_lin_exp) { cudaFree(s->d_lin_exp); s->d_lin_exp = nullptr; }
+  if (s->d_scale) { cudaFree(s->d_scale); s->d_scale = nullptr; }
+  LIFU_CUDA(cudaMalloc(&s->d_lin_exp, sizeof(long long) * std::max<long long>(s->n_src, 1)));
+  LIFU_CUDA(cudaMalloc(&s->d_scale, sizeof(float) * std::max<long long>(s->n_src, 1)));
+  if (s->n_src > 0) {
+    k_source_points<<<grid_blocks(s, s->n_src, 128), 128, 0, s->stream>>>(
+        s->d_idx, s->n_src, s->P, s->homogeneous ? nullptr : s->d_c0e, s->c0_s, s->grid.dt, s->grid.d[0],
+        s->d_lin_exp, s->d_scale);
+    LIFU_CUDA(cudaGetLastError());
+  }
+  return LIFU_OK;
+}
+
+}  // namespace lifu
+
+// ------------------------------------------------------------------------------------------
+// small device reduction used by lifu_set_medium (min and max of a positive field)
+namespace lifu {
+__global__ void k_minmax(const float* __restrict__ a, long long n, float* out /*[2]*/) {
+  float mn = INFINITY, mx = -INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = a[i];
+    mn = fminf(mn, v); mx = fmaxf(mx, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  __shared__ float smn[32], smx[32];
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { smn[w] = mn; smx[w] = mx; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    mn = l < nw ? smn[l] : INFINITY;
+    mx = l < nw ? smx[l] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (l == 0) {
+      // values of interest are finite; order-preserving int trick is valid for non-negative floats,
+      // negative minima are handled through the sign-flipped encoding below
+      auto enc = [](float f) { int i = __float_as_int(f); return i >= 0 ? i : (int)(0x80000000u - (unsigned)i); };
+      atomicMin((int*)out, enc(mn));
+      atomicMax((int*)out + 1, enc(mx));
+    }
+  }
+}
+}  // namespace lifu
+
+namespace lifu {
+int reduce_minmax(lifu_sim* s, const float* a, long long n, float* mn, float* mx) {
+  int* red = s->P.step + 1;
+  int init[2] = {INT32_MAX, INT32_MIN};
+  LIFU_CUDA(cudaMemcpyAsync(red, init, sizeof(init), cudaMemcpyHostToDevice, s->stream));
+  lifu::k_minmax<<<lifu::grid_blocks(s, n, 256, 4), 256, 0, s->stream>>>(a, n, (float*)red);
+  LIFU_CUDA(cudaGetLastError());
+  int h[2];
+  LIFU_CUDA(cudaMemcpyAsync(h, red, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  LIFU_CUDA(cudaStreamSynchronize(s->stream));
+  auto dec = [](int i) { int j = i >= 0 ? i : (int)(0x80000000u - (unsigned)i); float f; memcpy(&f, &j, 4); return f; };
+  *mn = dec(h[0]);
+  *mx = dec(h[1]);
+  return LIFU_OK;
+}
+}  // namespace lifu
+
+using namespace lifu;
+
+// =========================================================================================
+extern "C" {
+
+int lifu_abi_version(void) { return LIFUSIM_ABI_VERSION; }
+
+const char* lifu_last_error(void) { return g_err.c_str(); }
+
+int lifu_make_time(const int32_t n[3], const double d[3], double c_ref, double cfl, int32_t* nt, double* dt) {
+  if (!n || !d || !nt || !dt || c_ref <= 0 || cfl <= 0) { set_error("lifu_make_time: bad argument"); return LIFU_ERR_INVALID; }
+  double s2 = 0, dmin = d[0];
+  for (int a = 0; a < 3; ++a) { double L = (double)n[a] * d[a]; s2 += L * L; dmin = std::min(dmin, d[a]); }
+  double t_end = std::sqrt(s2) / c_ref;
+  double dt_ = cfl * dmin / c_ref;
+  double q = t_end / dt_;
+  int Nt = (int)std::floor(q) + 1;
+  if (std::floor(q) != std::ceil(q) && std::fmod(t_end, dt_) == 0.0) Nt += 1;
+  *nt = Nt;
+  *dt = dt_;
+  return LIFU_OK;
+}
+
+int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]) {
+  if (!n || !pml_out) { set_error("lifu_pml_auto: null argument"); return LIFU_ERR_INVALID; }
+  for (int a = 0; a < 3; ++a)
+    if (n[a] <= 0) { set_error("lifu_pml_auto: grid size must be positive"); return LIFU_ERR_INVALID; }
+  pml_auto(n, pml_out);
+  return LIFU_OK;
+}
+
+int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** out) {
+  if (!g || !out) { set_error("lifu_create: null argument"); return LIFU_ERR_INVALID; }
+  *out = nullptr;
+  for (int a = 0; a < 3; ++a) {
+    if (g->n[a] <= 0 || !(g->d[a] > 0)) { set_error("lifu_create: grid size and spacing must be positive"); return LIFU_ERR_INVALID; }
+  }
+  if (!(g->dt > 0) || g->nt <= 0) { set_error("lifu_create: dt and nt must be positive"); return LIFU_ERR_INVALID; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    set_error("lifu_create: no CUDA device available (%s); this library has no CPU fallback",
+              ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+    return LIFU_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { set_error("lifu_create: device %d out of range [0,%d)", device, ndev); return LIFU_ERR_INVALID; }
+  LIFU_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LIFU_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("lifu_create: device %d is sm_%d%d; liblifusim is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    return LIFU_ERR_CUDA;
+  }
+  lifu_sim* s = new lifu_sim();
+  s->grid = *g;
+  s->device = device;
+  s->stream = (cudaStream_t)cuda_stream;
+  s->n_sm = prop.multiProcessorCount;
+  int32_t pa[3];
+  pml_auto(g->n, pa);
+  for (int a = 0; a < 3; ++a) {
+    s->n[a] = g->n[a];
+    s->pml[a] = g->pml[a] >= 0 ? g->pml[a] : pa[a];
+    s->N[a] = s->n[a] + 2 * s->pml[a];
+    s->grid.pml[a] = s->pml[a];
+  }
+  s->Nxh = s->N[0] / 2 + 1;
+  s->V = (long long)s->N[0] * s->N[1] * s->N[2];
+  s->Vh = (long long)s->Nxh * s->N[1] * s->N[2];
+  s->Vin = (long long)s->n[0] * s->n[1] * s->n[2];
+  s->RS = round_up(s->V, 128);
+  s->CS = round_up(s->Vh, 64);
+  const char* ng = getenv("LIFU_NO_GRAPH");
+  s->use_graph = !(ng && ng[0] == '1');
+
+  StepParams& P = s->P;
+  P.Nx = s->N[0]; P.Ny = s->N[1]; P.Nz = s->N[2]; P.Nxh = s->Nxh;
+  P.nx = s->n[0]; P.ny = s->n[1]; P.nz = s->n[2];
+  P.px = s->pml[0]; P.py = s->pml[1]; P.pz = s->pml[2];
+  P.V = s->V; P.Vh = s->Vh; P.RS = s->RS; P.CS = s->CS;
+  P.invN = (float)(1.0 / (double)s->V);
+
+  int rc = LIFU_OK;
+  auto A = [&](void** p, size_t bytes) { if (rc == LIFU_OK) rc = dev_alloc(s, p, bytes); };
+  const size_t R = sizeof(float) * s->RS, C = sizeof(float2) * s->CS;
+  A((void**)&P.p, R); A((void**)&P.u, 3 * R); A((void**)&P.rho, 3 * R); A((void**)&P.r3, 3 * R);
+  A((void**)&P.r1, R); A((void**)&P.S, R); A((void**)&P.Sf, R);
+  A((void**)&P.c1, C); A((void**)&P.c3, 3 * C);
+  A((void**)&P.pmax, sizeof(float) * s->Vin); A((void**)&P.pmin, sizeof(float) * s->Vin);
+  A((void**)&P.step, sizeof(int) * 4);
+  if (rc == LIFU_OK) for (int i = 0; i < 3 && rc == LIFU_OK; ++i)
+    if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = LIFU_ERR_CUDA; }
+  if (rc != LIFU_OK) { lifu_destroy(s); return rc; }
+  if (g->c_ref > 0) {
+    s->c_ref = g->c_ref;
+    rc = build_tables(s);
+    if (rc != LIFU_OK) { lifu_destroy(s); return rc; }
+  }
+  *out = s;
+  return LIFU_OK;
+}
+
+int lifu_destroy(lifu_sim* s) {
+  if (!s) return LIFU_OK;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
+  cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
+  if (s->plans_ready || s->r2c1) for (cufftHandle h : hs) if (h) cufftDestroy(h);
+  for (void* p : s->allocs) cudaFree(p);
+  cudaFree(s->d_idx); cudaFree(s->d_lin_exp); cudaFree(s->d_row_ptr); cudaFree(s->d_col);
+  cudaFree(s->d_w); cudaFree(s->d_scale); cudaFree(s->d_base); cudaFree(s->d_delay); cudaFree(s->d_gain);
+  for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  delete s;
+  return LIFU_OK;
+}
+
+int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
+                    float alpha_power, int alpha_mode, int homogeneous) {
+  if (!s || !c0 || !rho0) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
+  if (alpha_mode < 0 || alpha_mode > 2) { set_error("lifu_set_medium: alpha_mode %d unknown", alpha_mode); return LIFU_ERR_INVALID; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  StepParams& P = s->P;
+  s->alpha_power = alpha_power;
+  s->alpha_mode = alpha_mode;
+  s->homogeneous = homogeneous != 0;
+  for (int i = 0; i < 2; ++i) if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }
+  const double y = alpha_power;
+  const double np_coef = 100.0 * std::pow(1e-6 / (2.0 * M_PI), y) / (20.0 * std::log10(M_E));
+  const double tan_term = std::tan(M_PI * y / 2.0);
+  P.y_minus2_half = (float)((y - 2.0) / 2.0);
+  P.y_minus1_half = (float)((y - 1.0) / 2.0);
+  double c_max;
+  if (s->homogeneous) {
+    float hc = 0, hr = 0, ha = 0;
+    LIFU_CUDA(cudaMemcpyAsync(&hc, c0, sizeof(float), cudaMemcpyDefault, st));
+    LIFU_CUDA(cudaMemcpyAsync(&hr, rho0, sizeof(float), cudaMemcpyDefault, st));
+    if (alpha_db) LIFU_CUDA(cudaMemcpyAsync(&ha, alpha_db, sizeof(float), cudaMemcpyDefault, st));
+    LIFU_CUDA(cudaStreamSynchronize(st));
+    if (!(hc > 0) || !(hr > 0) || ha < 0) { set_error("lifu_set_medium: need c0 > 0, rho0 > 0, alpha >= 0"); return LIFU_ERR_INVALID; }
+    s->c0_s = hc; s->rho0_s = hr; s->alpha_s = ha;
+    s->absorbing = ha != 0.f;
+    const double dt = s->grid.dt;
+    P.homogeneous = 1;
+    P.dt_rho0_sg_s = (float)(dt / (double)hr);
+    P.dt_rho0_s = (float)(dt * (double)hr);
+    P.c2_s = (float)((double)hc * (double)hc);
+    P.rho0_s = hr;
+    double a_np = np_coef * (double)ha;
+    P.tau_s = (float)(-2.0 * a_np * std::pow((double)hc, y - 1.0));
+    P.eta_s = (float)(2.0 * a_np * std::pow((double)hc, y) * tan_term);
+    c_max = hc;
+  } else {
+    P.homogeneous = 0;
+    const size_t R = sizeof(float) * s->RS;
+    if (!s->d_c0e) {
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_c0e, R));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_rho0e, R));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_alphae, R));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_med, 7 * R));
+    }
+    // stage the inner-grid maps through the (currently idle) scratch field r3
+    float* stage = P.r3;
+    const size_t inb = sizeof(float) * s->Vin;
+    const int gb = grid_blocks(s, s->V, 256);
+    const float* src[3] = {c0, rho0, alpha_db};
+    float* dst[3] = {s->d_c0e, s->d_rho0e, s->d_alphae};
+    for (int m = 0; m < 3; ++m) {
+      if (src[m]) {
+        LIFU_CUDA(cudaMemcpyAsync(stage, src[m], inb, cudaMemcpyDefault, st));
+        k_expand_edge<<<gb, 256, 0, st>>>(stage, dst[m], P);
+      } else {
+        k_fill<<<gb, 256, 0, st>>>(dst[m], s->V, 0.f);
+      }
+    }
+    LIFU_CUDA(cudaGetLastError());
+    float* d_dt_rho0_sg = s->d_med;
+    float* d_dt_rho0 = s->d_med + 3 * s->RS;
+    float* d_c2 = s->d_med + 4 * s->RS;
+    float* d_tau = s->d_med + 5 * s->RS;
+    float* d_eta = s->d_med + 6 * s->RS;
+    k_derive_medium<<<gb, 256, 0, st>>>(s->d_c0e, s->d_rho0e, s->d_alphae, P, (float)s->grid.dt, alpha_power,
+                                        np_coef, tan_term, d_dt_rho0_sg, d_dt_rho0, d_c2, d_tau, d_eta);
+    LIFU_CUDA(cudaGetLastError());
+    P.dt_rho0_sg = d_dt_rho0_sg; P.dt_rho0 = d_dt_rho0; P.c2 = d_c2; P.tau = d_tau; P.eta = d_eta;
+    P.rho0 = s->d_rho0e;
+    // c_ref = max(c0) and absorbing = any(alpha != 0) come from device reductions
+    float cmax = 0, amax = 0, cmin = 0, amin = 0;
+    LIFU_CHECK(reduce_minmax(s, s->d_c0e, s->V, &cmin, &cmax));
+    LIFU_CHECK(reduce_minmax(s, s->d_alphae, s->V, &amin, &amax));
+    if (!(cmin > 0)) { set_error("lifu_set_medium: sound speed must be positive everywhere"); return LIFU_ERR_INVALID; }
+    if (amin < 0) { set_error("lifu_set_medium: attenuation must be non-negative"); return LIFU_ERR_INVALID; }
+    s->absorbing = amax != 0.f;
+    c_max = cmax;
+    s->c0_s = cmax;
+  }
+  if (s->grid.c_ref <= 0) {
+    if (!s->tables_ready || s->c_ref != c_max) { s->c_ref = c_max; LIFU_CHECK(build_tables(s)); }
+  }
+  s->medium_set = true;
+  return upload_source_points(s);
+}
+
+int lifu_set_elements(lifu_sim* s, int32_t n_el, const double* pos_m, const double* size_m,
+                      const double* angle_deg, double bli_tolerance, int32_t upsampling_rate, int64_t* n_src) {
+  if (!s || !pos_m || !size_m || !angle_deg) { set_error("lifu_set_elements: null argument"); return LIFU_ERR_INVALID; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  LIFU_CHECK(bli_build(s, n_el, pos_m, size_m, angle_deg, bli_tolerance, upsampling_rate));
+  if (n_src) *n_src = s->n_src;
+  return LIFU_OK;
+}
+
+int lifu_set_source_geometry(lifu_sim* s, const int64_t* idx, const int32_t* row_ptr, const int32_t* col_elem,
+                             const float* w, int64_t n_src, int64_t nnz, int32_t n_el) {
+  if (!s || n_src < 0 || nnz < 0 || n_el <= 0 || (n_src > 0 && (!idx || !row_ptr)) || (nnz > 0 && (!col_elem || !w))) {
+    set_error("lifu_set_source_geometry: bad argument");
+    return LIFU_ERR_INVALID;
+  }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  s->geometry_set = false;
+  cudaFree(s->d_idx); cudaFree(s->d_row_ptr); cudaFree(s->d_col); cudaFree(s->d_w);
+  s->d_idx = nullptr; s->d_row_ptr = nullptr; s->d_col = nullptr; s->d_w = nullptr;
+  LIFU_CUDA(cudaMalloc(&s->d_idx, sizeof(long long) * std::max<int64_t>(n_src, 1)));
+  LIFU_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(int) * (n_src + 1)));
+  LIFU_CUDA(cudaMalloc(&s->d_col, sizeof(int) * std::max<int64_t>(nnz, 1)));
+  LIFU_CUDA(cudaMalloc(&s->d_w, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  if (n_src > 0) {
+    LIFU_CUDA(cudaMemcpyAsync(s->d_idx, idx, sizeof(long long) * n_src, cudaMemcpyDefault, st));
+    LIFU_CUDA(cudaMemcpyAsync(s->d_row_ptr, row_ptr, sizeof(int) * (n_src + 1), cudaMemcpyDefault, st));
+  } else {
+    LIFU_CUDA(cudaMemsetAsync(s->d_row_ptr, 0, sizeof(int), st));
+  }
+  if (nnz > 0) {
+    LIFU_CUDA(cudaMemcpyAsync(s->d_col, col_elem, sizeof(int) * nnz, cudaMemcpyDefault, st));
+    LIFU_CUDA(cudaMemcpyAsync(s->d_w, w, sizeof(float) * nnz, cudaMemcpyDefault, st));
+  }
+  LIFU_CUDA(cudaStreamSynchronize(st));
+  s->n_src = n_src; s->nnz = nnz; s->n_el = n_el;
+  s->geometry_set = true;
+  return upload_source_points(s);
+}
+
+int lifu_get_source_sizes(lifu_sim* s, int64_t* n_src, int64_t* nnz, int32_t* n_el) {
+  if (!s || !s->geometry_set) { set_error("lifu_get_source_sizes: no source geometry set"); return LIFU_ERR_STATE; }
+  if (n_src) *n_src = s->n_src;
+  if (nnz) *nnz = s->nnz;
+  if (n_el) *n_el = s->n_el;
+  return LIFU_OK;
+}
+
+int lifu_get_source_geometry(lifu_sim* s, int64_t* idx, int32_t* row_ptr, int32_t* col_elem, float* w) {
+  if (!s || !s->geometry_set) { set_error("lifu_get_source_geometry: no source geometry set"); return LIFU_ERR_STATE; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  if (idx && s->n_src) LIFU_CUDA(cudaMemcpyAsync(idx, s->d_idx, sizeof(long long) * s->n_src, cudaMemcpyDefault, st));
+  if (row_ptr) LIFU_CUDA(cudaMemcpyAsync(row_ptr, s->d_row_ptr, sizeof(int) * (s->n_src + 1), cudaMemcpyDefault, st));
+  if (col_elem && s->nnz) LIFU_CUDA(cudaMemcpyAsync(col_elem, s->d_col, sizeof(int) * s->nnz, cudaMemcpyDefault, st));
+  if (w && s->nnz) LIFU_CUDA(cudaMemcpyAsync(w, s->d_w, sizeof(float) * s->nnz, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaStreamSynchronize(st));
+  return LIFU_OK;
+}
+
+int lifu_set_drive(lifu_sim* s, const float* base_signal, int32_t n_base, const int32_t* delay_samples,
+                   const float* gains, int32_t n_el, int source_mode) {
+  if (!s || !base_signal || !delay_samples || !gains || n_base <= 0 || n_el <= 0) {
+    set_error("lifu_set_drive: bad argument");
+    return LIFU_ERR_INVALID;
+  }
+  if (source_mode != LIFU_SOURCE_ADDITIVE && source_mode != LIFU_SOURCE_ADDITIVE_NO_CORRECTION) {
+    set_error("lifu_set_drive: source_mode %d unknown", source_mode);
+    return LIFU_ERR_INVALID;
+  }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  if (n_base != s->n_base || !s->d_base) {
+    cudaFree(s->d_base); s->d_base = nullptr;
+    LIFU_CUDA(cudaMalloc(&s->d_base, sizeof(float) * n_base));
+  }
+  if (n_el != s->drive_n_el || !s->d_delay) {
+    cudaFree(s->d_delay); cudaFree(s->d_gain); s->d_delay = nullptr; s->d_gain = nullptr;
+    LIFU_CUDA(cudaMalloc(&s->d_delay, sizeof(int) * n_el));
+    LIFU_CUDA(cudaMalloc(&s->d_gain, sizeof(float) * n_el));
+  }
+  std::vector<int> hd(n_el);
+  LIFU_CUDA(cudaMemcpyAsync(s->d_base, base_signal, sizeof(float) * n_base, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaMemcpyAsync(s->d_delay, delay_samples, sizeof(int) * n_el, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaMemcpyAsync(s->d_gain, gains, sizeof(float) * n_el, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaMemcpyAsync(hd.data(), s->d_delay, sizeof(int) * n_el, cudaMemcpyDeviceToHost, st));
+  LIFU_CUDA(cudaStreamSynchronize(st));
+  int md = 0;
+  for (int v : hd) {
+    if (v < 0) { set_error("lifu_set_drive: negative delay sample count"); return LIFU_ERR_INVALID; }
+    md = std::max(md, v);
+  }
+  if (source_mode != s->source_mode)
+    for (int i = 0; i < 2; ++i) if (s->graph[i]) { cudaGraphExecDestroy(s->graph[i]); s->graph[i] = nullptr; }
+  s->n_base = n_base; s->drive_n_el = n_el; s->max_delay = md; s->source_mode = source_mode;
+  s->drive_set = true;
+  return LIFU_OK;
+}
+
+}  // extern "C"
+
+
+// =========================================================================================
+// time loop
+namespace lifu {
+
+template <int VEC>
+static void launch_update_u(lifu_sim* s, int gb) {
+  if (s->homogeneous) k_update_u<VEC, true><<<gb, 256, 0, s->stream>>>(s->P);
+  else k_update_u<VEC, false><<<gb, 256, 0, s->stream>>>(s->P);
+}
+
+template <bool HOMOG, int SRC>
+static void launch_rho_p(lifu_sim* s, int gb) {
+  if (s->absorbing) k_update_rho_p<HOMOG, SRC, true><<<gb, 256, 0, s->stream>>>(s->P);
+  else k_update_rho_p<HOMOG, SRC, false><<<gb, 256, 0, s->stream>>>(s->P);
+}
+
+// Enqueue one time step on the handle's stream.  Counts hand-written kernels / FFT executions.
+static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts) {
+  StepParams& P = s->P;
+  cudaStream_t st = s->stream;
+  const int gbh = grid_blocks(s, s->Vh, 256);
+  const int gbr = grid_blocks(s, s->V, 256);
+  int nk = 0, nf = 0;
+  // (1) grad p -> u
+  LIFU_CUFFT(cufftExecR2C(s->r2c1, P.p, (cufftComplex*)P.c1)); nf += 1;
+  k_grad_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+  LIFU_CUFFT(cufftExecC2R(s->c2r3, (cufftComplex*)P.c3, P.r3)); nf += 3;
+  if (s->N[0] % 4 == 0) launch_update_u<4>(s, grid_blocks(s, s->V / 4, 256));
+  else launch_update_u<1>(s, gbr);
+  ++nk;
+  // (2) div u
+  LIFU_CUFFT(cufftExecR2C(s->r2c3, P.u, (cufftComplex*)P.c3)); nf += 3;
+  k_div_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+  LIFU_CUFFT(cufftExecC2R(s->c2r3, (cufftComplex*)P.c3, P.r3)); nf += 3;
+  // (4) source field
+  int src = 0;
+  if (src_active) {
+    k_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(P, s->S); ++nk;
+    if (s->source_mode == LIFU_SOURCE_ADDITIVE) {
+      LIFU_CUFFT(cufftExecR2C(s->r2c1, P.S, (cufftComplex*)P.c1)); nf += 1;
+      k_source_filter<<<gbh, 256, 0, st>>>(P); ++nk;
+      LIFU_CUFFT(cufftExecC2R(s->c2r1, (cufftComplex*)P.c1, P.Sf)); nf += 1;
+      src = 1;
+    } else {
+      src = 2;
+    }
+  }
+  // (3)+(5)+(6) rho update, equation of state, sensor
+  if (s->homogeneous) {
+    if (src == 0) launch_rho_p<true, 0>(s, gbr); else if (src == 1) launch_rho_p<true, 1>(s, gbr); else launch_rho_p<true, 2>(s, gbr);
+  } else {
+    if (src == 0) launch_rho_p<false, 0>(s, gbr); else if (src == 1) launch_rho_p<false, 1>(s, gbr); else launch_rho_p<false, 2>(s, gbr);
+  }
+  ++nk;
+  if (s->absorbing) {
+    LIFU_CUFFT(cufftExecR2C(s->r2c2, P.r3, (cufftComplex*)P.c3)); nf += 2;
+    k_absorb_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+    LIFU_CUFFT(cufftExecC2R(s->c2r2, (cufftComplex*)P.c3, P.r3)); nf += 2;
+    const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
+    if (s->homogeneous) k_pressure_absorb<true><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
+    else k_pressure_absorb<false><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
+    ++nk;
+  }
+  LIFU_CUDA(cudaGetLastError());
+  if (n_kernels) *n_kernels = nk;
+  if (n_ffts) *n_ffts = nf;
+  return LIFU_OK;
+}
+
+static double bytes_model(const lifu_sim* s, bool src_active) {
+  // algorithmic bytes per voxel-step (DESIGN.md section 4 / SURVEY.md 8d)
+  double ffts = 10, k1 = 16, k3 = 24;
+  double k2 = s->homogeneous ? 36 : 48;
+  double k4 = s->homogeneous ? 56 : 64;
+  double b = k1 + k2 + k3 + k4;
+  if (s->absorbing) {
+    if (s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION) { ffts += 2; b += s->homogeneous ? 16 : 20; }
+    if (s->alpha_mode != LIFU_ALPHA_NO_DISPERSION) { ffts += 2; b += 20; }
+  }
+  if (src_active && s->source_mode == LIFU_SOURCE_ADDITIVE) { ffts += 2; b += 8; }
+  return b + 8.0 * ffts;
+}
+
+}  // namespace lifu
+
+extern "C" {
+
+int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
+  if (!s) { set_error("lifu_run: null handle"); return LIFU_ERR_INVALID; }
+  if (!s->medium_set) { set_error("lifu_run: call lifu_set_medium first"); return LIFU_ERR_STATE; }
+  if (!s->geometry_set) { set_error("lifu_run: call lifu_set_elements or lifu_set_source_geometry first"); return LIFU_ERR_STATE; }
+  if (!s->drive_set) { set_error("lifu_run: call lifu_set_drive first"); return LIFU_ERR_STATE; }
+  if (s->drive_n_el != s->n_el) {
+    set_error("lifu_run: drive has %d elements but the source geometry has %d", s->drive_n_el, s->n_el);
+    return LIFU_ERR_STATE;
+  }
+  if (!s->tables_ready) { set_error("lifu_run: internal error, tables not built"); return LIFU_ERR_STATE; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t user_stream = s->stream;
+  cudaStream_t own = nullptr;
+  if (s->stream == nullptr) {   // stream capture needs a non-default stream
+    LIFU_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking));
+    s->stream = own;
+  }
+  struct Restore {
+    lifu_sim* s; cudaStream_t user, own;
+    ~Restore() {
+      if (own) {
+        cudaStreamSynchronize(own);
+        cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
+        if (s->plans_ready) for (cufftHandle h : hs) cufftSetStream(h, user);
+        cudaStreamDestroy(own);
+      }
+      s->stream = user;
+    }
+  } restore{s, user_stream, own};
+  cudaStream_t st = s->stream;
+  LIFU_CHECK(build_plans(s));
+  {
+    cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
+    for (cufftHandle h : hs) LIFU_CUFFT(cufftSetStream(h, st));
+  }
+  StepParams& P = s->P;
+  SourceParams& S = s->S;
+  S.n_src = s->n_src; S.lin_exp = s->d_lin_exp; S.row_ptr = s->d_row_ptr; S.col = s->d_col; S.w = s->d_w;
+  S.scale = s->d_scale; S.base = s->d_base; S.n_base = s->n_base; S.delay = s->d_delay; S.gain = s->d_gain;
+
+  LIFU_CUDA(cudaEventRecord(s->ev[0], st));
+  const size_t R = sizeof(float) * s->RS;
+  LIFU_CUDA(cudaMemsetAsync(P.p, 0, R, st));
+  LIFU_CUDA(cudaMemsetAsync(P.u, 0, 3 * R, st));
+  LIFU_CUDA(cudaMemsetAsync(P.rho, 0, 3 * R, st));
+  LIFU_CUDA(cudaMemsetAsync(P.S, 0, R, st));
+  LIFU_CUDA(cudaMemsetAsync(P.step, 0, sizeof(int), st));
+  k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmax, s->Vin, -INFINITY);
+  k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmin, s->Vin, INFINITY);
+  LIFU_CUDA(cudaGetLastError());
+
+  const int nt = s->grid.nt;
+  const int L = s->n_src > 0 ? std::min(nt, s->max_delay + s->n_base) : 0;
+  int nk[2] = {0, 0}, nf[2] = {0, 0};
+  // capture one step with and one without the source as CUDA graphs (launch-bound at C1 sizes)
+  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  bool graphs = s->use_graph;
+  if (graphs) {
+    for (int v = 0; v < 2 && graphs; ++v) {
+      if ((v == 0 && L == 0) || (v == 1 && L >= nt)) continue;
+      cudaGraph_t g = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { graphs = false; break; }
+      int rc = enqueue_step(s, v == 0, &nk[v], &nf[v]);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      if (rc != LIFU_OK || ce != cudaSuccess || g == nullptr) { graphs = false; if (g) cudaGraphDestroy(g); break; }
+      ce = cudaGraphInstantiate(&gexec[v], g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { graphs = false; gexec[v] = nullptr; break; }
+    }
+    if (!graphs) {
+      cudaGetLastError();   // clear the sticky-free capture error and run without graphs
+      for (int v = 0; v < 2; ++v) if (gexec[v]) { cudaGraphExecDestroy(gexec[v]); gexec[v] = nullptr; }
+    }
+  }
+  LIFU_CUDA(cudaEventRecord(s->ev[1], st));
+  int rc = LIFU_OK;
+  for (int t = 0; t < nt && rc == LIFU_OK; ++t) {
+    const int v = t < L ? 0 : 1;
+    if (graphs) {
+      if (cudaGraphLaunch(gexec[v], st) != cudaSuccess) { set_error("cudaGraphLaunch failed at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); rc = LIFU_ERR_CUDA; }
+    } else {
+      rc = enqueue_step(s, v == 0, &nk[v], &nf[v]);
+    }
+  }
+  if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  if (rc == LIFU_OK && p_max) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  if (rc == LIFU_OK && p_min) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  cudaError_t se = cudaStreamSynchronize(st);
+  for (int v = 0; v < 2; ++v) if (gexec[v]) cudaGraphExecDestroy(gexec[v]);
+  if (rc == LIFU_ERR_CUDA && g_err.empty()) set_error("lifu_run: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
+  if (rc != LIFU_OK) return rc;
+  if (se != cudaSuccess) { set_error("lifu_run: time loop failed: %s", cudaGetErrorString(se)); return LIFU_ERR_CUDA; }
+
+  lifu_stats& r = s->last;
+  memset(&r, 0, sizeof(r));
+  r.voxels = s->V;
+  for (int a = 0; a < 3; ++a) { r.n_exp[a] = s->N[a]; r.pml[a] = s->pml[a]; }
+  r.steps = nt;
+  r.source_steps = L;
+  r.kernel_launches = (int64_t)L * nk[0] + (int64_t)(nt - L) * nk[1];
+  r.fft_launches = (int64_t)L * nf[0] + (int64_t)(nt - L) * nf[1];
+  float ms = 0;
+  cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); r.loop_ms = ms;
+  cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); r.setup_ms = ms;
+  r.bytes_per_voxel_step = (L * bytes_model(s, true) + (double)(nt - L) * bytes_model(s, false)) / (double)nt;
+  r.homogeneous = s->homogeneous; r.absorbing = s->absorbing;
+  if (stats) *stats = r;
+  return LIFU_OK;
+}
+
+int lifu_get_field(lifu_sim* s, int which, float* out) {
+  if (!s || !out || which < 0 || which > 6) { set_error("lifu_get_field: bad argument"); return LIFU_ERR_INVALID; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  const float* src = which == 0 ? s->P.p : (which <= 3 ? s->P.u + (which - 1) * s->RS : s->P.rho + (which - 4) * s->RS);
+  LIFU_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * s->V, cudaMemcpyDefault, s->stream));
+  LIFU_CUDA(cudaStreamSynchronize(s->stream));
+  return LIFU_OK;
+}
+
+int lifu_get_info(lifu_sim* s, lifu_stats* stats) {
+  if (!s || !stats) { set_error("lifu_get_info: null argument"); return LIFU_ERR_INVALID; }
+  *stats = s->last;
+  stats->voxels = s->V;
+  for (int a = 0; a < 3; ++a) { stats->n_exp[a] = s->N[a]; stats->pml[a] = s->pml[a]; }
+  stats->homogeneous = s->homogeneous; stats->absorbing = s->absorbing;
+  return LIFU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// sim.cuh -- the opaque handle behind lifu_sim.
+#pragma once
+#include "common.cuh"
+
+struct lifu_sim {
+  lifu_grid grid{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int n_sm = 148;
+
+  // geometry
+  int N[3]{}, n[3]{}, pml[3]{}, Nxh = 0;
+  long long V = 0, Vh = 0, Vin = 0, RS = 0, CS = 0;
+  double c_ref = 0.0;
+  bool tables_ready = false;
+
+  // device buffers (all owned)
+  std::vector<void*> allocs;
+  float* d_tables = nullptr;   // all 1-D tables packed
+  lifu::StepParams P{};
+  lifu::SourceParams S{};
+
+  // medium
+  bool medium_set = false;
+  bool homogeneous = true, absorbing = false;
+  int alpha_mode = 0;
+  float alpha_power = 0.9f;
+  float *d_c0e = nullptr, *d_rho0e = nullptr, *d_alphae = nullptr;
+  float c0_s = 0, rho0_s = 0, alpha_s = 0;
+  float* d_med = nullptr;      // packed derived maps
+
+  // source geometry (device)
+  long long n_src = 0, nnz = 0;
+  int n_el = 0;
+  long long* d_idx = nullptr;        // inner-grid linear indices
+  long long* d_lin_exp = nullptr;
+  int* d_row_ptr = nullptr;
+  int* d_col = nullptr;
+  float* d_w = nullptr;
+  float* d_scale = nullptr;
+  bool geometry_set = false;
+
+  // drive
+  float* d_base = nullptr;
+  int n_base = 0;
+  int* d_delay = nullptr;
+  float* d_gain = nullptr;
+  int drive_n_el = 0;
+  int max_delay = 0;
+  int source_mode = 0;
+  bool drive_set = false;
+
+  // FFT plans (cuFFT, shared work area)
+  cufftHandle r2c1 = 0, r2c3 = 0, c2r1 = 0, c2r3 = 0, r2c2 = 0, c2r2 = 0;
+  bool plans_ready = false;
+  void* d_work = nullptr;
+  size_t work_bytes = 0;
+
+  // CUDA graphs of one time step: [0] source active, [1] source off
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  bool use_graph = true;
+
+  lifu_stats last{};
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+
+namespace lifu {
+int dev_alloc(lifu_sim* s, void** p, size_t bytes);
+int bli_build(lifu_sim* s, int n_el, const double* pos, const double* size, const double* ang,
+              double tol, int ups);
+int upload_source_points(lifu_sim* s);
+inline int grid_blocks(const lifu_sim* s, long long n, int threads, int per_sm = 8) {
+  long long need = (n + threads - 1) / threads;
+  long long cap = (long long)s->n_sm * per_sm;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+}  // namespace lifu

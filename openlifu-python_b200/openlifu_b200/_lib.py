@@ -1,0 +1,230 @@
+"""ctypes binding of liblifusim.so (the C ABI in include/lifusim.h).
+
+No CPU fallback: importing this module without the built library, or creating a solver
+without a B200, raises.  Pointers handed to the library may be numpy (host) buffers or raw
+device pointers (ints, e.g. ``torch.Tensor.data_ptr()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("LIFUSIM_LIB", _HERE.parent / "lib" / "liblifusim.so"))
+
+
+class LifuError(RuntimeError):
+    pass
+
+
+class lifu_grid(C.Structure):
+    _fields_ = [("n", C.c_int32 * 3), ("pml", C.c_int32 * 3), ("d", C.c_double * 3), ("dt", C.c_double),
+                ("nt", C.c_int32), ("pml_alpha", C.c_double), ("c_ref", C.c_double)]
+
+
+class lifu_stats(C.Structure):
+    _fields_ = [("voxels", C.c_int64), ("n_exp", C.c_int32 * 3), ("pml", C.c_int32 * 3), ("steps", C.c_int32),
+                ("source_steps", C.c_int32), ("kernel_launches", C.c_int64), ("fft_launches", C.c_int64),
+                ("loop_ms", C.c_double), ("setup_ms", C.c_double), ("bytes_per_voxel_step", C.c_double),
+                ("homogeneous", C.c_int32), ("absorbing", C.c_int32)]
+
+    def as_dict(self):
+        out = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            out[name] = list(v) if hasattr(v, "__len__") else v
+        return out
+
+
+ALPHA_MODES = {"binary": 0, "no_dispersion": 1, "no_absorption": 2}
+SOURCE_MODES = {"additive": 0, "additive-no-correction": 1}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise a clear error when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise LifuError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(nvcc, sm_100a). There is no CPU fallback for the simulation path.")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    sig = {
+        "lifu_abi_version": (C.c_int, []),
+        "lifu_last_error": (C.c_char_p, []),
+        "lifu_make_time": (C.c_int, [C.POINTER(i32), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
+        "lifu_pml_auto": (C.c_int, [C.POINTER(i32), C.POINTER(i32)]),
+        "lifu_create": (C.c_int, [C.POINTER(lifu_grid), C.c_int, vp, C.POINTER(vp)]),
+        "lifu_destroy": (C.c_int, [vp]),
+        "lifu_set_medium": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int]),
+        "lifu_set_elements": (C.c_int, [vp, i32, vp, vp, vp, f64, i32, C.POINTER(i64)]),
+        "lifu_set_source_geometry": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32]),
+        "lifu_get_source_sizes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
+        "lifu_get_source_geometry": (C.c_int, [vp, vp, vp, vp, vp]),
+        "lifu_set_drive": (C.c_int, [vp, vp, i32, vp, vp, i32, C.c_int]),
+        "lifu_run": (C.c_int, [vp, vp, vp, C.POINTER(lifu_stats)]),
+        "lifu_get_field": (C.c_int, [vp, C.c_int, vp]),
+        "lifu_get_info": (C.c_int, [vp, C.POINTER(lifu_stats)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lifu_abi_version() != 1:
+        raise LifuError(f"liblifusim ABI {lib.lifu_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
+            "lifu_set_medium", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
+            "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info"]
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().lifu_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(msg)
+        raise LifuError(f"liblifusim error {rc}: {msg}")
+
+
+def _ptr(a):
+    """numpy array -> host pointer; int -> raw (device) pointer; None -> NULL."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return C.c_void_p(int(a))
+    return C.c_void_p(a.ctypes.data)
+
+
+def make_time(n, d, c_ref=1500.0, cfl=0.5):
+    nt, dt = C.c_int32(), C.c_double()
+    _check(load().lifu_make_time((C.c_int32 * 3)(*[int(v) for v in n]), (C.c_double * 3)(*[float(v) for v in d]),
+                                 c_ref, cfl, C.byref(nt), C.byref(dt)))
+    return nt.value, dt.value
+
+
+def pml_auto(n):
+    out = (C.c_int32 * 3)()
+    _check(load().lifu_pml_auto((C.c_int32 * 3)(*[int(v) for v in n]), out))
+    return tuple(out)
+
+
+class LifuSim:
+    """One solver handle = one (device, stream).  Thin, typed wrapper over the C ABI."""
+
+    def __init__(self, n, d, dt, nt, pml=(-1, -1, -1), device=0, stream=0, pml_alpha=0.0, c_ref=0.0):
+        self._h = C.c_void_p()
+        g = lifu_grid()
+        g.n[:] = [int(v) for v in n]
+        g.pml[:] = [int(v) for v in pml]
+        g.d[:] = [float(v) for v in d]
+        g.dt, g.nt, g.pml_alpha, g.c_ref = float(dt), int(nt), float(pml_alpha), float(c_ref)
+        self.n = tuple(int(v) for v in n)
+        self._lib = load()
+        _check(self._lib.lifu_create(C.byref(g), int(device), C.c_void_p(int(stream) or None), C.byref(self._h)))
+        self._keep = []
+
+    def close(self):
+        if self._h:
+            self._lib.lifu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ medium
+    def set_medium(self, c0, rho0, alpha_db=None, alpha_power=0.9, alpha_mode="binary", device_ptrs=False):
+        """Scalars -> homogeneous; else (Nx,Ny,Nz) maps (any layout; converted to x-fastest float32)
+        or, with ``device_ptrs=True``, raw device pointers to x-fastest float32 inner-grid maps."""
+        mode = ALPHA_MODES[alpha_mode] if isinstance(alpha_mode, str) else int(alpha_mode)
+        if device_ptrs:
+            _check(self._lib.lifu_set_medium(self._h, _ptr(c0), _ptr(rho0), _ptr(alpha_db), alpha_power, mode, 0))
+            return
+        homog = np.ndim(c0) == 0 and np.ndim(rho0) == 0 and (alpha_db is None or np.ndim(alpha_db) == 0)
+        if homog:
+            arrs = [np.array([v if v is not None else 0.0], dtype=np.float32) for v in (c0, rho0, alpha_db)]
+        else:
+            arrs = []
+            for v in (c0, rho0, 0.0 if alpha_db is None else alpha_db):
+                full = np.broadcast_to(np.asarray(v, dtype=np.float32), self.n)
+                arrs.append(np.ascontiguousarray(full.transpose(2, 1, 0)))   # x fastest
+        _check(self._lib.lifu_set_medium(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power, mode,
+                                         1 if homog else 0))
+
+    # ------------------------------------------------------------------ source geometry
+    def set_elements(self, pos_m, size_m, angle_deg, bli_tolerance=0.05, upsampling_rate=5):
+        pos = np.ascontiguousarray(pos_m, dtype=np.float64).reshape(-1, 3)
+        size = np.ascontiguousarray(size_m, dtype=np.float64).reshape(-1, 2)
+        ang = np.ascontiguousarray(angle_deg, dtype=np.float64).reshape(-1, 3)
+        n_src = C.c_int64()
+        _check(self._lib.lifu_set_elements(self._h, pos.shape[0], _ptr(pos), _ptr(size), _ptr(ang),
+                                           float(bli_tolerance), int(upsampling_rate), C.byref(n_src)))
+        return n_src.value
+
+    def set_source_geometry(self, idx, row_ptr, col, w, n_el):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int32)
+        col = np.ascontiguousarray(col, dtype=np.int32)
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        _check(self._lib.lifu_set_source_geometry(self._h, _ptr(idx), _ptr(row_ptr), _ptr(col), _ptr(w),
+                                                  idx.size, col.size, int(n_el)))
+
+    def get_source_geometry(self):
+        n_src, nnz, n_el = C.c_int64(), C.c_int64(), C.c_int32()
+        _check(self._lib.lifu_get_source_sizes(self._h, C.byref(n_src), C.byref(nnz), C.byref(n_el)))
+        idx = np.empty(n_src.value, dtype=np.int64)
+        row_ptr = np.empty(n_src.value + 1, dtype=np.int32)
+        col = np.empty(nnz.value, dtype=np.int32)
+        w = np.empty(nnz.value, dtype=np.float32)
+        _check(self._lib.lifu_get_source_geometry(self._h, _ptr(idx), _ptr(row_ptr), _ptr(col), _ptr(w)))
+        return idx, row_ptr, col, w, n_el.value
+
+    # ------------------------------------------------------------------ drive + run
+    def set_drive(self, base_signal, delay_samples, gains, source_mode="additive"):
+        base = np.ascontiguousarray(base_signal, dtype=np.float32)
+        dly = np.ascontiguousarray(delay_samples, dtype=np.int32)
+        g = np.ascontiguousarray(gains, dtype=np.float32)
+        mode = SOURCE_MODES[source_mode] if isinstance(source_mode, str) else int(source_mode)
+        _check(self._lib.lifu_set_drive(self._h, _ptr(base), base.size, _ptr(dly), _ptr(g), dly.size, mode))
+
+    def run(self, p_max=None, p_min=None):
+        """Run the time loop.  ``p_max``/``p_min``: None -> new numpy arrays are returned; numpy
+        float32 arrays of Nx*Ny*Nz; or raw device pointers (ints)."""
+        nvox = int(np.prod(self.n))
+        own = p_max is None
+        if own:
+            p_max = np.empty(nvox, dtype=np.float32)
+            p_min = np.empty(nvox, dtype=np.float32)
+        st = lifu_stats()
+        _check(self._lib.lifu_run(self._h, _ptr(p_max), _ptr(p_min), C.byref(st)))
+        return p_max, p_min, st.as_dict()
+
+    def get_field(self, which):
+        st = lifu_stats()
+        _check(self._lib.lifu_get_info(self._h, C.byref(st)))
+        out = np.empty(int(st.voxels), dtype=np.float32)
+        _check(self._lib.lifu_get_field(self._h, int(which), _ptr(out)))
+        N = list(st.n_exp)
+        return out.reshape(N[2], N[1], N[0]).transpose(2, 1, 0)
+
+    def info(self):
+        st = lifu_stats()
+        _check(self._lib.lifu_get_info(self._h, C.byref(st)))
+        return st.as_dict()

@@ -1,0 +1,174 @@
+"""``run_simulation``: the drop-in boundary of the treatment-planning hot path.
+
+Same name, keyword arguments, defaults, errors and return value as
+/root/reference/src/openlifu/sim/kwave_if.py:80-146 (module name kept so that
+``openlifu.sim.kwave_if.run_simulation`` / ``openlifu.plan.protocol.run_simulation`` can be
+pointed here unchanged).  Instead of building k-wave-python objects, writing HDF5 and spawning
+the kspaceFirstOrder binary, it drives the C ABI of ``liblifusim.so`` (include/lifusim.h):
+hand-written sm_100a kernels around cuFFT on one B200.  There is NO CPU path: ``gpu=False``
+raises.
+
+What is reused between calls (the reference recomputes all of it per focus):
+solver handle + FFT plans per grid, off-grid source weights per (transducer, grid), medium maps
+per params object.  Only ``(delays, apod)`` -- 2 x n_elements numbers -- go to the GPU per focus.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import zlib
+from typing import List
+
+import numpy as np
+
+from .. import _lib, xa
+from ..util.units import getunitconversion
+
+log = logging.getLogger(__name__)
+
+_SESSIONS: dict = {}
+_MAX_SESSIONS = 2
+
+
+def _same_units(objs, what):
+    units = [o.attrs["units"] for o in objs]
+    if not all(u == units[0] for u in units):
+        raise ValueError(f"All {what} must have the same units")
+    return units[0]
+
+
+def get_kgrid(coords, t_end=0, dt=0, sound_speed_ref=1500, cfl=0.5):
+    """Grid sizes, spacings [m] and time axis (kwave_if.py:13-27).  Returns a dict instead of a
+    kWaveGrid.  Auto time stepping uses ``sound_speed_ref`` (default 1500), not the medium."""
+    scl = getunitconversion(_same_units([coords[d] for d in coords.dims], "coordinates"), "m")
+    sz = [len(c) for c in coords.values()]
+    dx = [float(np.diff(c.data)[0] * scl) for c in coords.values()]
+    if dt == 0 or t_end == 0:
+        nt, dt_ = _lib.make_time(sz, dx, float(sound_speed_ref), float(cfl))
+    else:
+        nt, dt_ = int(round(t_end / dt)), float(dt)
+    return {"N": sz, "d": dx, "Nt": nt, "dt": dt_}
+
+
+def _device():
+    if "LIFU_DEVICE" in os.environ:
+        return int(os.environ["LIFU_DEVICE"])
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    return 0
+
+
+def _sample_checksum(a: np.ndarray) -> int:
+    flat = np.asarray(a).reshape(-1)
+    step = max(1, flat.size // 4096)
+    return zlib.adler32(np.ascontiguousarray(flat[::step]).tobytes()) ^ flat.size
+
+
+class _Session:
+    """Solver handle and what is cached on it."""
+
+    def __init__(self, key, kg, device):
+        self.key = key
+        self.sim = _lib.LifuSim(kg["N"], kg["d"], kg["dt"], kg["Nt"], device=device)
+        self.geometry_key = None
+        self.medium_key = None
+        self.n_src = 0
+
+
+def _session(kg, device):
+    key = (tuple(kg["N"]), tuple(kg["d"]), kg["dt"], kg["Nt"], device)
+    s = _SESSIONS.get(key)
+    if s is None:
+        while len(_SESSIONS) >= _MAX_SESSIONS:
+            _SESSIONS.pop(next(iter(_SESSIONS))).sim.close()
+        s = _SESSIONS[key] = _Session(key, kg, device)
+    return s
+
+
+def clear_sessions():
+    """Release every cached solver handle (GPU memory, FFT plans)."""
+    while _SESSIONS:
+        _SESSIONS.popitem()[1].sim.close()
+
+
+def element_geometry(arr, translation_m):
+    """What get_karray (kwave_if.py:29-47) feeds kWaveArray.add_rect_element: centres [m] shifted
+    by the array offset, (width, length) [m], (el, az, roll) in degrees."""
+    pos = np.array([el.get_position(units="m") for el in arr.elements], dtype=np.float64) + np.asarray(translation_m)
+    size = np.array([el.get_size(units="m") for el in arr.elements], dtype=np.float64)
+    ang = np.array([el.get_angle(units="deg") for el in arr.elements], dtype=np.float64)
+    return pos, size, ang
+
+
+def run_simulation(arr,
+                   params,
+                   delays: np.ndarray | None = None,
+                   apod: np.ndarray | None = None,
+                   freq: float = 1e6,
+                   cycles: float = 20,
+                   amplitude: float = 1,
+                   dt: float = 0,
+                   t_end: float = 0,
+                   cfl: float = 0.5,
+                   bli_tolerance: float = 0.05,
+                   upsampling_rate: int = 5,
+                   gpu: bool = True,
+                   ref_values_only: bool = False):
+    if not gpu:
+        raise RuntimeError("openlifu_b200.run_simulation has no CPU path (gpu=False): the solve runs on a B200 "
+                           "through liblifusim.so only")
+    n_el = arr.numelements()
+    delays = np.zeros(n_el) if delays is None else delays
+    apod = np.ones(n_el) if apod is None else apod
+    kg = get_kgrid(params.coords, dt=dt, t_end=t_end, cfl=cfl)
+    t = np.arange(0, cycles / freq, kg["dt"])
+    input_signal = amplitude * np.sin(2 * np.pi * freq * t)
+    n_delay, gains, base_gain = arr.drive_plan(kg["dt"], delays, apod)
+    scl = getunitconversion(_same_units([params[d] for d in params.dims], "dimensions"), "m")
+    array_offset: List[float] = [-float(c.mean()) * scl for c in params.coords.values()]
+
+    ses = _session(kg, _device())
+    sim = ses.sim
+    # medium (get_medium, kwave_if.py:49-63): alpha_power 0.9; alpha_mode='no_dispersion' is what the
+    # reference asks for but the k-Wave binary only receives alpha_coeff/alpha_power (ledger A7)
+    alpha_mode = os.environ.get("LIFU_ALPHA_MODE", "binary")
+    names = ("sound_speed", "density", "attenuation")
+    if ref_values_only:
+        mkey = ("ref",) + tuple(float(params[k].attrs["ref_value"]) for k in names) + (alpha_mode,)
+        if ses.medium_key != mkey:
+            sim.set_medium(*[float(params[k].attrs["ref_value"]) for k in names], alpha_power=0.9, alpha_mode=alpha_mode)
+    else:
+        maps = [params[k].data for k in names]
+        mkey = ("map",) + tuple((id(m), _sample_checksum(m)) for m in maps) + (alpha_mode,)
+        if ses.medium_key != mkey:
+            if all(float(m.min()) == float(m.max()) for m in maps):
+                sim.set_medium(*[float(m.flat[0]) for m in maps], alpha_power=0.9, alpha_mode=alpha_mode)
+            else:
+                sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode)
+    ses.medium_key = mkey
+    # source geometry (get_karray + get_array_binary_mask + BLI weights), cached per transducer
+    pos, size, ang = element_geometry(arr, array_offset)
+    gkey = (zlib.adler32(pos.tobytes()), zlib.adler32(size.tobytes()), zlib.adler32(ang.tobytes()),
+            float(bli_tolerance), int(upsampling_rate))
+    if ses.geometry_key != gkey:
+        log.info("Computing off-grid source weights on the GPU")
+        ses.n_src = sim.set_elements(pos, size, ang, bli_tolerance, upsampling_rate)
+        ses.geometry_key = gkey
+    sim.set_drive(input_signal * base_gain, n_delay, gains,
+                  source_mode=os.environ.get("LIFU_SOURCE_MODE", "additive"))
+    log.info("Running simulation")
+    p_max_flat, p_min_flat, stats = sim.run()
+    log.info("Simulation Complete")
+    output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
+              "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
+
+    sz = list(params.coords.sizes.values())
+    p_max = xa.DataArray(output["p_max"].reshape(sz, order="F"), coords=params.coords, name="p_max",
+                         attrs={"units": "Pa", "long_name": "PPP"})
+    p_min = xa.DataArray(-1 * output["p_min"].reshape(sz, order="F"), coords=params.coords, name="p_min",
+                         attrs={"units": "Pa", "long_name": "PNP"})
+    Z = params["density"].data * params["sound_speed"].data
+    intensity = xa.DataArray(1e-4 * output["p_min"].reshape(sz, order="F") ** 2 / (2 * Z), coords=params.coords,
+                             name="I", attrs={"units": "W/cm^2", "long_name": "Intensity"})
+    ds = xa.Dataset({"p_max": p_max, "p_min": p_min, "intensity": intensity})
+    return ds, output
