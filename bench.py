@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: k-space simulation throughput (Mvox*step/s) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2|C3|C1]
+
+One bench "step" = one full simulation of one focus (the body of the reference's per-focus loop,
+/root/reference/src/openlifu/plan/protocol.py:318-339): beamforming inputs -> solver time loop
+(Nt time steps over the PML-expanded grid) -> p_max/p_min.  Workload at N=1 is SURVEY.md config C2
+(OpenLIFU 2x64-element array, water, 0.5 mm grid, 216^3 -> 256^3, Nt = 749).  With N > 1 every rank
+simulates its own focus of the C4 Wheel pattern (focus i -> GPU i mod N): weak scaling, no
+data-path collective (foci are independent).
+
+Printed JSON (rank 0, one line):
+  value    Mvox*step/s with everything resident in HBM (solver handle, medium, source weights);
+           per step only the 2 x n_elements drive numbers change; outputs stay on the device.
+  e2e      same metric through the public API `openlifu_b200.sim.run_simulation` with HOST numpy
+           inputs and a HOST xarray-like Dataset out (medium upload + drive upload + p_max/p_min
+           download + packaging inside the timed region).
+  roofline dominant hand-written kernel: algorithmic bytes / CUDA-event time vs measured HBM peak.
+  cpu_baseline  the oracle port (CPU restatement of the k-Wave step) on this box's host cores.
+
+--impl reference times the reference's CPU path.  The real k-Wave OMP binary cannot exist here
+(SURVEY.md 8c), so this is the oracle port (`oracle/`, numpy + scipy.fft with all host threads) on
+a bounded number of time steps of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (str(ROOT / "openlifu-python_b200"), str(ROOT)):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "k-space sim voxel-updates/s"
+UNIT = "Mvox*step/s"
+
+
+def measured_peak_gbs():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "power_w_max": float(np.max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_workload(name, n_inner):
+    from openlifu_b200 import configs
+    if name == "C1":
+        cfg = configs.c1()
+    elif name == "C3":
+        cfg = configs.c3(n_inner)
+    else:
+        cfg = configs.c2(n_inner)
+    # the foci of the C4 wheel: rank r, step s simulates focus (r + s*world) mod 32
+    from openlifu_b200.bf import focal_patterns
+    cfg["focal_pattern"] = focal_patterns.Wheel(center=True, num_spokes=31, spoke_radius=5.0, distance_units="mm")
+    return cfg, configs.prepare(cfg)
+
+
+def oracle_sample(cfg, prep, n_time_steps, workers):
+    """CPU restatement (oracle port) of the same workload for n_time_steps.
+    Returns (seconds spent in the time loop only, expanded voxels, time steps done)."""
+    from oracle import scene as osc
+    from openlifu_b200.sim.kwave_if import element_geometry
+    params, foci, beams, cycles = prep
+    arr = cfg["arr"]
+    pos, size, ang = element_geometry(arr, [0, 0, 0])
+    homog = all(float(params[k].data.min()) == float(params[k].data.max()) for k in ("sound_speed", "density", "attenuation"))
+    med = [float(params[k].data.flat[0]) if homog else params[k].data for k in ("sound_speed", "density", "attenuation")]
+    sc = osc.Scene(coords=[params.coords[d].data for d in ("x", "y", "z")], coord_scale=1e-3, elem_pos_m=pos,
+                   elem_size_m=size, elem_angles_deg=ang, sound_speed=med[0], density=med[1], attenuation=med[2],
+                   sensitivity=arr.sensitivity)
+    # a cheap stand-in geometry (the element centres' nearest nodes) keeps the sample bounded: the time
+    # loop cost does not depend on the number of source points
+    N = [len(c) for c in sc.coords]
+    d = [float(np.diff(c)[0]) * 1e-3 for c in sc.coords]
+    off = np.array([-float(np.mean(c)) * 1e-3 for c in sc.coords])
+    ijk = np.clip(np.round((pos + off) / np.array(d) + np.array(N) // 2).astype(int), 0, np.array(N) - 1)
+    idx = np.unique(ijk[:, 0] + N[0] * (ijk[:, 1] + N[1] * ijk[:, 2])).astype(np.int64)
+    W = np.zeros((idx.size, len(pos)), dtype=np.float32)
+    W[np.searchsorted(idx, ijk[:, 0] + N[0] * (ijk[:, 1] + N[1] * ijk[:, 2])), np.arange(len(pos))] = 1.0
+    delays, apod = beams[0]
+    out = osc.run_simulation(sc, delays=delays, apod=apod, freq=cfg["pulse"].frequency, cycles=cycles,
+                             amplitude=cfg["pulse"].amplitude, geometry=(idx, W), max_steps=n_time_steps, workers=workers)
+    return out["raw"]["loop_s"], int(np.prod(out["raw"]["N_exp"])), out["raw"]["Nt"]
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path (oracle port), rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    cfg, prep = build_workload(args.workload, args.n_inner)
+    total = args.steps + args.warmup
+    # size the per-step sample so that the whole run stays within ~3 minutes
+    t0 = time.perf_counter()
+    t2, V, _ = oracle_sample(cfg, prep, 2, cores)
+    wall2 = time.perf_counter() - t0
+    per_ts = max(t2 / 2.0, 1e-3)
+    fixed = max(wall2 - t2, 0.0)                           # setup outside the time loop, paid every sample
+    n_ts = int(max(2, min(40, (150.0 / max(total, 1) - fixed) / per_ts)))
+    times = []
+    for i in range(total):
+        loop, V, done = oracle_sample(cfg, prep, n_ts, cores)
+        if i >= args.warmup:
+            times.append(loop / done)
+    per = float(np.mean(times))
+    value = V / per / 1e6
+    from openlifu_b200.sim.kwave_if import get_kgrid
+    nt_full = get_kgrid(prep[0].coords)["Nt"]
+    sample = f"{n_ts} of the workload's time steps per bench step, time loop only, {V} voxels"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3 * nt_full, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "note": "CPU restatement (oracle port) of the k-Wave OMP step; "
+                       "the real binary is not obtainable offline"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.workload == "C1":
+        return "C1: 8x8 matrix array, focus 50 mm, water, 1 mm grid 61x61x75 -> 81x81x125, Nt=229"
+    n = args.n_inner
+    kind = "water" if args.workload == "C2" else "skull/brain phantom (c, rho, alpha maps)"
+    return (f"{args.workload}: OpenLIFU 2x64-element array, {kind}, 0.5 mm grid {n}^3 inner"
+            + (" -> 256^3 with PML, Nt=749" if n == 216 else ""))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--n-inner", type=int, default=216)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    os.environ["LIFU_DEVICE"] = str(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    from openlifu_b200 import _lib
+    from openlifu_b200.sim import kwave_if
+    from openlifu_b200.sim.kwave_if import element_geometry, get_kgrid
+
+    cfg, prep = build_workload(args.workload, args.n_inner)
+    params, foci, beams, cycles = prep
+    arr = cfg["arr"]
+    kg = get_kgrid(params.coords, dt=cfg["setup"].dt, t_end=cfg["setup"].t_end, cfl=cfg["setup"].cfl)
+    freq, amp = cfg["pulse"].frequency, cfg["pulse"].amplitude
+    t = np.arange(0, cycles / freq, kg["dt"])
+    base = amp * np.sin(2 * np.pi * freq * t)
+    n_inner_vox = int(np.prod(kg["N"]))
+
+    stream = torch.cuda.Stream()
+    names = ("sound_speed", "density", "attenuation")
+    homog = all(float(params[k].data.min()) == float(params[k].data.max()) for k in names)
+    # ---- resident arm: one handle, everything uploaded once, outputs stay in HBM
+    sim = _lib.LifuSim(kg["N"], kg["d"], kg["dt"], kg["Nt"], device=local_rank, stream=stream.cuda_stream)
+    if homog:
+        sim.set_medium(*[float(params[k].data.flat[0]) for k in names], alpha_power=0.9)
+    else:
+        sim.set_medium(*[params[k].data for k in names], alpha_power=0.9)
+    offset = [-float(c.mean()) * 1e-3 for c in params.coords.values()]
+    pos, size, ang = element_geometry(arr, offset)
+    n_src = sim.set_elements(pos, size, ang, 0.05, 5)
+    d_pmax = torch.empty(n_inner_vox, dtype=torch.float32, device="cuda")
+    d_pmin = torch.empty(n_inner_vox, dtype=torch.float32, device="cuda")
+
+    def focus_for(step):
+        return (rank + step * world) % len(beams)
+
+    def resident_step(step):
+        delays, apod = beams[focus_for(step)]
+        n_delay, gains, base_gain = arr.drive_plan(kg["dt"], delays, apod)
+        sim.set_drive(base * base_gain, n_delay, gains)
+        return sim.run(d_pmax.data_ptr(), d_pmin.data_ptr())[2]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        resident_step(w)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for k in range(args.steps):
+            st = resident_step(args.warmup + k)
+            launches += st["kernel_launches"]
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = ev0.elapsed_time(ev1)
+    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    V = st["voxels"]
+    Nt = st["steps"]
+    value = world * V * Nt * args.steps / (ms_total * 1e-3) / 1e6
+    loop_value = V * Nt / (st["loop_ms"] * 1e-3) / 1e6
+
+    # ---- per-stage profile (dominant hand-written kernel) on rank 0
+    roofline = None
+    stages_out = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        prof = sim.profile_stages(reps=8, with_source=True)
+        own = [(n, ms, b) for n, ms, b in prof if n.startswith("k_") and b > 0]
+        tot = sum(ms for _, ms, _ in prof)
+        name, ms, bpv = max(own, key=lambda r: r[1])
+        ach = bpv * V / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_voxel": bpv,
+                    "kernel_ms": ms, "share_of_step": ms / tot,
+                    "step": {"algorithmic_bytes_per_voxel_step": st["bytes_per_voxel_step"],
+                             "achieved": st["bytes_per_voxel_step"] * V * Nt / (st["loop_ms"] * 1e-3) / 1e9,
+                             "frac": st["bytes_per_voxel_step"] * V * Nt / (st["loop_ms"] * 1e-3) / 1e9 / peak}}
+        stages_out = [{"stage": n, "ms": round(ms, 4), "GBps": (round(b * V / (ms * 1e-3) / 1e9, 1) if ms > 0 else None)}
+                      for n, ms, b in prof]
+    sim.close()
+    del d_pmax, d_pmin
+
+    # ---- e2e arm: public API, host numpy in, host Dataset out
+    e2e = None
+    if not args.no_e2e:
+        kwave_if.clear_sessions()
+        h2d = d2h = 0
+
+        def api_step(step):
+            nonlocal h2d, d2h
+            delays, apod = beams[focus_for(step)]
+            ses = next(iter(kwave_if._SESSIONS.values()), None)
+            if ses is not None:
+                ses.medium_key = None          # the medium is an input of every call: upload it every step
+            ds, out = kwave_if.run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=freq, cycles=cycles,
+                                              dt=cfg["setup"].dt, t_end=cfg["setup"].t_end, cfl=cfg["setup"].cfl,
+                                              amplitude=amp, gpu=True)
+            med = 3 * 4 if homog else 3 * 4 * n_inner_vox
+            h2d = med + 4 * base.size + 8 * arr.numelements()
+            d2h = 2 * 4 * n_inner_vox
+            return float(ds["p_min"].data.max())
+
+        for w in range(max(1, min(args.warmup, 3))):
+            api_step(w)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            api_step(args.warmup + k)
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        te = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * V * Nt * args.steps / float(te.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "foci_per_s": world * args.steps / float(te.item())}
+        kwave_if.clear_sessions()
+
+    # ---- CPU baseline (oracle port) on rank 0 at N=1
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_ts = 8 if V > 4e6 else 60
+        loop_s, Vc, done = oracle_sample(cfg, prep, n_ts, cores)
+        per = max(loop_s, 1e-6) / done
+        cpu = {"value": Vc / per / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_ts} time steps of the same workload ({Vc} voxels), scipy.fft + numpy, {cores} threads"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args), "voxels": V, "time_steps": Nt, "n_src": int(n_src),
+                           "foci": "C4 wheel: rank r, step s -> focus (r + s*N) mod 32",
+                           "l2": "working set (~20 fields x 67 MB) exceeds the 126 MB L2; no flush needed",
+                           "fft": "cuFFT 3-D R2C/C2R (v1 pipeline)", "time_loop_only_value": loop_value},
+                "e2e": e2e, "gpu_launches": int(launches), "fft_launches": int(st["fft_launches"] * args.steps),
+                "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages": stages_out}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,13 @@ int lifu_run(lifu_sim* sim, float* p_max, float* p_min, lifu_stats* stats);
 int lifu_get_field(lifu_sim* sim, int which, float* out);
 int lifu_get_info(lifu_sim* sim, lifu_stats* stats);
 
+/* Measurement aid (bench.py roofline): after a lifu_run, execute `reps` further time steps with a
+ * CUDA event after every stage on the handle's stream and return the mean duration per stage
+ * [ms], its name and its algorithmic bytes per voxel.  with_source selects the
+ * source-active step variant.  names: max_stages * name_stride chars (may be NULL). */
+int lifu_profile_stages(lifu_sim* sim, int reps, int with_source, int max_stages, char* names,
+                        int name_stride, double* ms, double* bytes_per_voxel, int* n_stages);
+
 #ifdef __cplusplus
 }
 #endif

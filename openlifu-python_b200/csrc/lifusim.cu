@@ -348,6 +348,7 @@ int lifu_destroy(lifu_sim* s) {
   cudaFree(s->d_idx); cudaFree(s->d_lin_exp); cudaFree(s->d_row_ptr); cudaFree(s->d_col);
   cudaFree(s->d_w); cudaFree(s->d_scale); cudaFree(s->d_base); cudaFree(s->d_delay); cudaFree(s->d_gain);
   for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+  for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
   delete s;
   return LIFU_OK;
 }
@@ -561,28 +562,50 @@ static void launch_rho_p(lifu_sim* s, int gb) {
 static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts) {
   StepParams& P = s->P;
   cudaStream_t st = s->stream;
+  // optional per-stage timing (lifu_profile_stages): an event after every stage
+  auto mark = [&](const char* name, double bytes_per_voxel) {
+    if (!s->prof_on) return;
+    cudaEvent_t e = nullptr;
+    if (s->prof_used < (int)s->prof_ev.size()) e = s->prof_ev[s->prof_used];
+    else { cudaEventCreate(&e); s->prof_ev.push_back(e); }
+    cudaEventRecord(e, st);
+    if (s->prof_used >= (int)s->prof_names.size()) { s->prof_names.push_back(name); s->prof_bytes.push_back(bytes_per_voxel); }
+    ++s->prof_used;
+  };
+  mark("begin", 0);
   const int gbh = grid_blocks(s, s->Vh, 256);
   const int gbr = grid_blocks(s, s->V, 256);
   int nk = 0, nf = 0;
   // (1) grad p -> u
   LIFU_CUFFT(cufftExecR2C(s->r2c1, P.p, (cufftComplex*)P.c1)); nf += 1;
+  mark("cufft_r2c_p", 8);
   k_grad_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+  mark("k_grad_spectral", 16);
   LIFU_CUFFT(cufftExecC2R(s->c2r3, (cufftComplex*)P.c3, P.r3)); nf += 3;
+  mark("cufft_c2r_grad_x3", 24);
   if (s->N[0] % 4 == 0) launch_update_u<4>(s, grid_blocks(s, s->V / 4, 256));
   else launch_update_u<1>(s, gbr);
   ++nk;
+  mark("k_update_u", s->homogeneous ? 36 : 48);
   // (2) div u
   LIFU_CUFFT(cufftExecR2C(s->r2c3, P.u, (cufftComplex*)P.c3)); nf += 3;
+  mark("cufft_r2c_u_x3", 24);
   k_div_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+  mark("k_div_spectral", 24);
   LIFU_CUFFT(cufftExecC2R(s->c2r3, (cufftComplex*)P.c3, P.r3)); nf += 3;
+  mark("cufft_c2r_div_x3", 24);
   // (4) source field
   int src = 0;
   if (src_active) {
     k_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(P, s->S); ++nk;
+    mark("k_source_scatter", 0);
     if (s->source_mode == LIFU_SOURCE_ADDITIVE) {
       LIFU_CUFFT(cufftExecR2C(s->r2c1, P.S, (cufftComplex*)P.c1)); nf += 1;
+      mark("cufft_r2c_src", 8);
       k_source_filter<<<gbh, 256, 0, st>>>(P); ++nk;
+      mark("k_source_filter", 8);
       LIFU_CUFFT(cufftExecC2R(s->c2r1, (cufftComplex*)P.c1, P.Sf)); nf += 1;
+      mark("cufft_c2r_src", 8);
       src = 1;
     } else {
       src = 2;
@@ -595,14 +618,19 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
     if (src == 0) launch_rho_p<false, 0>(s, gbr); else if (src == 1) launch_rho_p<false, 1>(s, gbr); else launch_rho_p<false, 2>(s, gbr);
   }
   ++nk;
+  mark("k_update_rho_p", (s->homogeneous ? 56 : 64) + (src ? 4 : 0));
   if (s->absorbing) {
     LIFU_CUFFT(cufftExecR2C(s->r2c2, P.r3, (cufftComplex*)P.c3)); nf += 2;
+    mark("cufft_r2c_absorb_x2", 16);
     k_absorb_spectral<<<gbh, 256, 0, st>>>(P); ++nk;
+    mark("k_absorb_spectral", 16);
     LIFU_CUFFT(cufftExecC2R(s->c2r2, (cufftComplex*)P.c3, P.r3)); nf += 2;
+    mark("cufft_c2r_absorb_x2", 16);
     const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
     if (s->homogeneous) k_pressure_absorb<true><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
     else k_pressure_absorb<false><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
     ++nk;
+    mark("k_pressure_absorb", s->homogeneous ? 32 : 44);
   }
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
@@ -735,6 +763,49 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   r.bytes_per_voxel_step = (L * bytes_model(s, true) + (double)(nt - L) * bytes_model(s, false)) / (double)nt;
   r.homogeneous = s->homogeneous; r.absorbing = s->absorbing;
   if (stats) *stats = r;
+  return LIFU_OK;
+}
+
+int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, char* names, int name_stride,
+                        double* ms, double* bytes_per_voxel, int* n_stages) {
+  if (!s || reps <= 0 || !ms || !n_stages) { set_error("lifu_profile_stages: bad argument"); return LIFU_ERR_INVALID; }
+  if (!s->plans_ready || !s->medium_set || !s->geometry_set || !s->drive_set) {
+    set_error("lifu_profile_stages: call lifu_run once first");
+    return LIFU_ERR_STATE;
+  }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t user = s->stream, own = nullptr;
+  if (!user) { LIFU_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking)); s->stream = own; }
+  cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
+  for (cufftHandle h : hs) cufftSetStream(h, s->stream);
+  std::vector<double> acc;
+  int rc = LIFU_OK;
+  s->prof_names.clear(); s->prof_bytes.clear();
+  for (int r = 0; r < reps && rc == LIFU_OK; ++r) {
+    if (with_source) cudaMemsetAsync(s->P.step, 0, sizeof(int), s->stream);
+    s->prof_on = true; s->prof_used = 0;
+    rc = enqueue_step(s, with_source != 0 && s->n_src > 0, nullptr, nullptr);
+    s->prof_on = false;
+    if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("lifu_profile_stages: step failed"); rc = LIFU_ERR_CUDA; }
+    if (rc != LIFU_OK) break;
+    if (acc.empty()) acc.assign(s->prof_used, 0.0);
+    for (int i = 1; i < s->prof_used; ++i) {
+      float t = 0; cudaEventElapsedTime(&t, s->prof_ev[i - 1], s->prof_ev[i]);
+      acc[i] += t;
+    }
+  }
+  for (cufftHandle h : hs) cufftSetStream(h, user);
+  if (own) { cudaStreamDestroy(own); }
+  s->stream = user;
+  if (rc != LIFU_OK) return rc;
+  int n = (int)acc.size() - 1;
+  if (n > max_stages) n = max_stages;
+  for (int i = 0; i < n; ++i) {
+    ms[i] = acc[i + 1] / reps;
+    if (bytes_per_voxel) bytes_per_voxel[i] = s->prof_bytes[i + 1];
+    if (names && name_stride > 0) { strncpy(names + (size_t)i * name_stride, s->prof_names[i + 1], name_stride - 1); names[(size_t)i * name_stride + name_stride - 1] = 0; }
+  }
+  *n_stages = n;
   return LIFU_OK;
 }
 

@@ -60,6 +60,13 @@ struct lifu_sim {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   bool use_graph = true;
 
+  // per-stage profiling (lifu_profile_stages)
+  bool prof_on = false;
+  int prof_used = 0;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<const char*> prof_names;
+  std::vector<double> prof_bytes;
+
   lifu_stats last{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };

@@ -71,6 +71,8 @@ def load():
         "lifu_run": (C.c_int, [vp, vp, vp, C.POINTER(lifu_stats)]),
         "lifu_get_field": (C.c_int, [vp, C.c_int, vp]),
         "lifu_get_info": (C.c_int, [vp, C.POINTER(lifu_stats)]),
+        "lifu_profile_stages": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(f64),
+                                          C.POINTER(f64), C.POINTER(C.c_int)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -84,7 +86,8 @@ def load():
 
 EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
             "lifu_set_medium", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
-            "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info"]
+            "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info",
+            "lifu_profile_stages"]
 
 
 def _check(rc):
@@ -223,6 +226,18 @@ class LifuSim:
         _check(self._lib.lifu_get_field(self._h, int(which), _ptr(out)))
         N = list(st.n_exp)
         return out.reshape(N[2], N[1], N[0]).transpose(2, 1, 0)
+
+    def profile_stages(self, reps=5, with_source=True, max_stages=32):
+        """Mean CUDA-event time per stage of one time step: list of (name, ms, bytes_per_voxel)."""
+        stride = 32
+        names = C.create_string_buffer(max_stages * stride)
+        ms = (C.c_double * max_stages)()
+        bpv = (C.c_double * max_stages)()
+        n = C.c_int()
+        _check(self._lib.lifu_profile_stages(self._h, int(reps), int(bool(with_source)), max_stages, names, stride,
+                                             ms, bpv, C.byref(n)))
+        raw = names.raw
+        return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), ms[i], bpv[i]) for i in range(n.value)]
 
     def info(self):
         st = lifu_stats()

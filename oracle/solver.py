@@ -122,6 +122,8 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
     p_min = np.full(N_in, np.inf, dtype=rdt)
 
     Nt = int(inp.Nt) if max_steps is None else min(int(inp.Nt), int(max_steps))
+    import time as _time
+    t_loop0 = _time.perf_counter()
     for t in range(Nt):
         # (1) pressure gradient -> particle velocity on the staggered grid
         P = fwd(p)
@@ -160,7 +162,9 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
         if progress is not None:
             progress(t, p)
 
+    loop_s = _time.perf_counter() - t_loop0
     out = {
+        "loop_s": loop_s,
         "p_max": p_max.flatten("F"),
         "p_min": p_min.flatten("F"),
         "pml": pml, "N_exp": N, "c_ref": c_ref, "Nt": Nt, "L": L,

@@ -1,0 +1,137 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): source index masks / integer geometry bit-exact;
+p_max / p_min within 1e-4 relative L2 (float32 CUDA vs float32 oracle).
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _check_fields(got, want, tol=TOL):
+    for k in ("p_max", "p_min"):
+        err = cases.rel_l2(got[k], want[k])
+        assert err < tol, f"{k}: rel-L2 {err:.3e} >= {tol}"
+
+
+def test_small_water_bli_and_fields(lifu_lib):
+    case = cases.small_water_case()
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert got["Nt"] == want["Nt"]
+    assert tuple(got["stats"]["pml"]) == tuple(want["pml"])
+    assert tuple(got["stats"]["n_exp"]) == tuple(want["N_exp"])
+    assert np.array_equal(got["n_delay"], want["n_delay"])
+    assert np.array_equal(got["src_idx"], want["src_idx"])          # bit-exact source mask
+    Wg = cases.csr_to_dense(got["src_idx"].size, len(case["pos_m"]), got["row_ptr"], got["col"], got["w"])
+    assert np.allclose(Wg, want["W"], rtol=2e-6, atol=1e-7)
+    _check_fields(got, want)
+    assert got["stats"]["kernel_launches"] > 0
+
+
+def test_oracle_geometry_through_abi(lifu_lib):
+    """lifu_set_source_geometry (explicit CSR upload) gives the same fields as the GPU-built one."""
+    case = cases.small_water_case()
+    want = cases.run_oracle_case(case)
+    W = want["W"]
+    rows, cols = np.nonzero(W)
+    row_ptr = np.zeros(W.shape[0] + 1, dtype=np.int32)
+    np.add.at(row_ptr, rows + 1, 1)
+    row_ptr = np.cumsum(row_ptr).astype(np.int32)
+    got = cases.run_cuda_case(case, geometry=(want["src_idx"], row_ptr, cols.astype(np.int32), W[rows, cols], W.shape[1]))
+    _check_fields(got, want)
+
+
+def test_no_kspace_source_correction(lifu_lib):
+    from oracle.solver import Assumptions
+    case = cases.small_water_case()
+    want = cases.run_oracle_case(case, asm=Assumptions(source_kspace_correction=False))
+    got = cases.run_cuda_case(case, source_mode="additive-no-correction")
+    _check_fields(got, want)
+
+
+def test_homogeneous_absorbing(lifu_lib):
+    case = cases.small_water_case()
+    case["alpha"] = 0.75
+    case["c0"] = 1540.0
+    case["rho0"] = 1050.0
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert got["stats"]["absorbing"] == 1
+    _check_fields(got, want)
+
+
+def _phantom(N):
+    """Layered water / skull-like slab / tissue phantom with per-material c, rho, alpha."""
+    c0 = np.full(N, 1500.0)
+    rho0 = np.full(N, 1000.0)
+    al = np.full(N, 0.0022)
+    z = np.arange(N[2])[None, None, :] + 0 * np.arange(N[0])[:, None, None]
+    x = np.arange(N[0])[:, None, None]
+    slab = (z + (x // 6) >= 12) & (z + (x // 6) < 16)
+    tissue = (z + (x // 6)) >= 16
+    slab = np.broadcast_to(slab, N)
+    tissue = np.broadcast_to(tissue, N)
+    c0[slab], rho0[slab], al[slab] = 2800.0, 1900.0, 6.0
+    c0[tissue], rho0[tissue], al[tissue] = 1540.0, 1050.0, 0.3
+    return c0, rho0, al
+
+
+@pytest.mark.parametrize("alpha_mode", ["binary", "no_dispersion"])
+def test_heterogeneous_absorbing(lifu_lib, alpha_mode):
+    from oracle.solver import Assumptions
+    case = cases.small_water_case()
+    case["c0"], case["rho0"], case["alpha"] = _phantom(tuple(case["N"]))
+    case["dt"], case["t_end"] = 1.5e-7, 80 * 1.5e-7
+    want = cases.run_oracle_case(case, asm=Assumptions(absorb_eta=alpha_mode == "binary"))
+    got = cases.run_cuda_case(case, alpha_mode=alpha_mode)
+    assert got["stats"]["homogeneous"] == 0 and got["stats"]["absorbing"] == 1
+    _check_fields(got, want)
+
+
+def test_tilted_elements_mask_bit_exact(lifu_lib):
+    """Rotated, off-grid elements on an even-sized grid (half-voxel origin quirk, App. B 8)."""
+    pos = np.array([[-4.3, 1.1, 0.7], [3.9, -2.2, 1.4], [0.2, 5.1, -0.3]])
+    size = np.array([[2.3, 3.1], [2.0, 2.0], [3.3, 1.7]])
+    ang = np.array([[0.0, 14.17, 0.0], [-9.0, 0.0, 0.0], [5.0, -7.0, 30.0]])
+    case = cases.make_case([(-12, 11.5), (-10, 10), (-3, 20.5)], 0.5, 0, 0, 0, 0, (0, 0, 12), 500e3, 2,
+                           elem_pos_mm=pos, elem_size_mm=size, angles_deg=ang, dt=1.2e-7, t_end=50 * 1.2e-7)
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    Wg = cases.csr_to_dense(got["src_idx"].size, 3, got["row_ptr"], got["col"], got["w"])
+    assert np.allclose(Wg, want["W"], rtol=2e-6, atol=1e-7)
+    _check_fields(got, want)
+
+
+def test_c1_full(lifu_lib):
+    """SURVEY.md config C1 end to end (81x81x125 expanded grid, 229 steps)."""
+    case = cases.c1_case()
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert got["Nt"] == 229 and tuple(got["stats"]["n_exp"]) == (81, 81, 125)
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    _check_fields(got, want)
+
+
+def test_repeatable(lifu_lib):
+    case = cases.small_water_case()
+    a = cases.run_cuda_case(case)
+    b = cases.run_cuda_case(case)
+    assert np.array_equal(a["p_max"], b["p_max"]) and np.array_equal(a["p_min"], b["p_min"])
+
+
+def test_errors(lifu_lib):
+    from openlifu_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.LifuSim([0, 4, 4], [1e-3] * 3, 1e-7, 10)
+    with _lib.LifuSim([16, 16, 16], [1e-3] * 3, 1e-7, 4) as sim:
+        with pytest.raises(_lib.LifuError, match="lifu_set_medium first"):
+            sim.run()
