@@ -19,8 +19,8 @@ class ClassKeyed:
         d["class"] = type(self).__name__
         return d
 
-    @classmethod
-    def _from_dict(cls, family_root, d):
+    @staticmethod
+    def _from_dict(family_root, d):
         d = dict(d)
         name = d.pop("class")
         return family_root._family[name](**d)

@@ -21,7 +21,7 @@ class ApodizationMethod(ClassKeyed, ABC):
 
     @staticmethod
     def from_dict(d):
-        return ClassKeyed._from_dict(ApodizationMethod, ApodizationMethod, d)
+        return ClassKeyed._from_dict(ApodizationMethod, d)
 
     @abstractmethod
     def to_table(self):

@@ -19,7 +19,7 @@ class DelayMethod(ClassKeyed, ABC):
 
     @staticmethod
     def from_dict(d):
-        return ClassKeyed._from_dict(DelayMethod, DelayMethod, d)
+        return ClassKeyed._from_dict(DelayMethod, d)
 
     @abstractmethod
     def to_table(self):

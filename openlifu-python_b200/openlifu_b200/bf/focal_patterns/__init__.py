@@ -36,7 +36,7 @@ class FocalPattern(ClassKeyed, ABC):
 
     @staticmethod
     def from_dict(d):
-        return ClassKeyed._from_dict(FocalPattern, FocalPattern, d)
+        return ClassKeyed._from_dict(FocalPattern, d)
 
     @abstractmethod
     def to_table(self):

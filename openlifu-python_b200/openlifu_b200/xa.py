@@ -426,7 +426,9 @@ if not HAVE_XARRAY:
         del _inplace
 
         # -- reductions
-        def _reduce(self, fn, dim=None, keep_attrs=False, **kw):
+        def _reduce(self, fn, dim=None, keep_attrs=False, axis=None, **kw):
+            if dim is None and axis is not None:
+                dim = [self.dims[a] for a in np.atleast_1d(axis)]
             if dim is None:
                 axes = None
                 dims = ()
@@ -437,21 +439,21 @@ if not HAVE_XARRAY:
             data = np.asarray(fn(self._data, axis=axes, **kw))
             return self._replace(data, dims=dims, keep_attrs=keep_attrs)
 
-        def max(self, dim=None, keep_attrs=False, skipna=True):
+        def max(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
             fn = np.nanmax if (skipna and self._data.dtype.kind == "f") else np.max
-            return self._reduce(_quiet(fn), dim, keep_attrs)
+            return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
-        def min(self, dim=None, keep_attrs=False, skipna=True):
+        def min(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
             fn = np.nanmin if (skipna and self._data.dtype.kind == "f") else np.min
-            return self._reduce(_quiet(fn), dim, keep_attrs)
+            return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
-        def mean(self, dim=None, keep_attrs=False, skipna=True):
+        def mean(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
             fn = np.nanmean if (skipna and self._data.dtype.kind == "f") else np.mean
-            return self._reduce(_quiet(fn), dim, keep_attrs)
+            return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
-        def sum(self, dim=None, keep_attrs=False, skipna=True):
+        def sum(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
             fn = np.nansum if (skipna and self._data.dtype.kind == "f") else np.sum
-            return self._reduce(fn, dim, keep_attrs)
+            return self._reduce(fn, dim, keep_attrs, axis=axis)
 
         def any(self, dim=None):
             return self._reduce(np.any, dim)

@@ -1,0 +1,112 @@
+"""Host-side mirror of the reference interface: signatures, defaults, error behaviour (no GPU)."""
+from __future__ import annotations
+
+import inspect
+
+import numpy as np
+import pytest
+
+import openlifu_b200 as ol
+from openlifu_b200 import xa
+from openlifu_b200.sim import kwave_if
+
+
+def test_run_simulation_signature_matches_reference():
+    """kwave_if.py:80-94: names, order and defaults of the boundary."""
+    sig = inspect.signature(kwave_if.run_simulation)
+    got = [(p.name, p.default) for p in sig.parameters.values()]
+    want = [("arr", inspect._empty), ("params", inspect._empty), ("delays", None), ("apod", None), ("freq", 1e6),
+            ("cycles", 20), ("amplitude", 1), ("dt", 0), ("t_end", 0), ("cfl", 0.5), ("bli_tolerance", 0.05),
+            ("upsampling_rate", 5), ("gpu", True), ("ref_values_only", False)]
+    assert got == want
+
+
+def _scene():
+    arr = ol.Transducer.gen_matrix_array(nx=2, ny=2, pitch=2, kerf=.5, units="mm", sensitivity=1e5)
+    ss = ol.SimSetup(dt=2e-7, t_end=3 * 2e-7, x_extent=(-10, 10), y_extent=(-10, 10), z_extent=(-2, 10))
+    params = ol.seg_methods.UniformWater().ref_params(ss.get_coords())
+    return arr, ss, params
+
+
+def test_no_cpu_path():
+    arr, ss, params = _scene()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        kwave_if.run_simulation(arr=arr, params=params, gpu=False)
+
+
+def test_unit_mismatch_errors():
+    arr, ss, params = _scene()
+    params.coords["z"].attrs["units"] = "m"
+    with pytest.raises(ValueError, match="All coordinates must have the same units"):
+        kwave_if.run_simulation(arr=arr, params=params)
+
+
+def test_get_kgrid_time_axis():
+    arr, ss, params = _scene()
+    kg = kwave_if.get_kgrid(params.coords, dt=ss.dt, t_end=ss.t_end)
+    assert kg["N"] == [21, 21, 13] and kg["Nt"] == 3 and kg["dt"] == 2e-7       # tests/test_sim.py:22-29 grid
+    kg = kwave_if.get_kgrid(params.coords)
+    assert kg["Nt"] == int(np.floor(np.sqrt(21 ** 2 * 2 + 13 ** 2) * 1e-3 / 1500 / (0.5e-3 / 1500))) + 1
+
+
+def test_simsetup_validation_and_dict_roundtrip():
+    with pytest.raises(ValueError, match="x_extent must be in the form"):
+        ol.SimSetup(x_extent=(3, 1))
+    with pytest.raises(ValueError, match="units must be a length unit"):
+        ol.SimSetup(units="s")
+    with pytest.raises(TypeError, match="spacing must be a number"):
+        ol.SimSetup(spacing="1")
+    ss = ol.SimSetup(spacing=0.5, x_extent=(-5, 5))
+    ss2 = ol.SimSetup.from_dict(ss.to_dict())
+    assert ss2 == ss
+    assert ss.get_size().tolist() == [21, 121, 129]
+
+
+def test_method_dict_roundtrips():
+    for obj in (ol.delay_methods.Direct(c0=1540), ol.apod_methods.MaxAngle(25.0), ol.apod_methods.PiecewiseLinear(80, 30),
+                ol.apod_methods.Uniform(0.5)):
+        base = ol.DelayMethod if isinstance(obj, ol.DelayMethod) else ol.ApodizationMethod
+        assert base.from_dict(obj.to_dict()) == obj
+    w = ol.focal_patterns.Wheel(num_spokes=6, spoke_radius=3.0)
+    assert ol.FocalPattern.from_dict(w.to_dict()) == w and w.num_foci() == 7
+    with pytest.raises(ValueError):
+        ol.apod_methods.PiecewiseLinear(zero_angle=10, rolloff_angle=20)
+    with pytest.raises(TypeError):
+        ol.apod_methods.MaxAngle("x")
+    sm = ol.seg_methods.UniformWater()
+    assert type(ol.SegmentationMethod.from_dict(sm.to_dict())) is type(sm)
+
+
+def test_transducer_reference_kats():
+    """tests/test_transducer.py:39-70 of the reference: convert_transform and effective origin."""
+    arr = ol.Transducer.gen_matrix_array(nx=3, ny=2, units="cm")
+    m = np.eye(4)
+    m[:3, 3] = [1.0, 2.0, 3.0]
+    out = arr.convert_transform(m, units="mm")
+    assert np.allclose(out[:3, 3], [0.1, 0.2, 0.3]) and np.allclose(out[:3, :3], np.eye(3))
+    apod = np.zeros(6)
+    apod[[1, 4]] = 1
+    want = arr.get_positions()[[1, 4]].mean(axis=0)
+    assert np.allclose(arr.get_effective_origin(apod), want)
+    assert np.allclose(arr.get_effective_origin(apod, units="mm"), want * 10)
+
+
+def test_xa_shim_surface():
+    coords = xa.Coordinates({"x": np.arange(3.0), "y": np.arange(2.0)})
+    coords["x"].attrs["units"] = "mm"
+    a = xa.DataArray(np.arange(6.0).reshape(3, 2), coords=coords, dims=("x", "y"), attrs={"units": "Pa"})
+    assert a.dims == ("x", "y") and a.sizes == {"x": 3, "y": 2}
+    assert float(a.max()) == 5 and float(a.where(a > 2).max()) == 5 and np.isnan(a.where(a > 2).data[0, 0])
+    assert a.isel(x=1).dims == ("y",) and float(a.sel(x=2.0, y=1.0)) == 5
+    stacked = xa.concat([xa.Dataset({"p": a}).assign_coords(focal_point_index=i) for i in range(2)], dim="focal_point_index")
+    assert stacked["p"].dims == ("focal_point_index", "x", "y")
+    view = stacked["p"][1]
+    view.data *= 2                                   # writes through (solution.py:334-336 relies on it)
+    assert stacked["p"].data[1, 2, 1] == 10 and stacked["p"].data[0, 2, 1] == 5
+    agg = stacked["p"].max(dim="focal_point_index", keep_attrs=True)
+    assert agg.attrs["units"] == "Pa" and agg.dims == ("x", "y")
+    ds = stacked.drop_dims("focal_point_index")
+    assert len(ds.data_vars) == 0 and "x" in ds.coords
+    line = a.interp(x=xa.DataArray([0.5, 1.5], coords={"s": [0.0, 1.0]}), y=xa.DataArray([0.5, 0.5], coords={"s": [0.0, 1.0]}))
+    assert line.dims == ("s",) and np.allclose(line.data, [1.5, 3.5])
+    assert (a * xa.DataArray(np.array([1.0, 2.0]), dims=("y",))).shape == (3, 2)

@@ -1,0 +1,102 @@
+"""Known-answer tests for the solver oracle (the part of the path whose parity is unpinned by the
+reference): they tie the CPU restatement to physics instead of to golden fields.
+
+  * free-space spherical wave: arrival time r/c and 1/r amplitude decay (Green's function)
+  * exactness of the k-space scheme in a homogeneous medium: measured phase speed == c0 at CFL 0.5
+  * PML: outgoing pulse is absorbed (late-time energy << peak energy)
+  * power-law absorption: amplitude ratio follows exp(-alpha * f^y * d)
+  * float32 oracle vs float64 oracle: the noise floor quoted next to the 1e-4 GPU tolerance
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import kgrid as kg
+from oracle.solver import Assumptions, SolverInputs, simulate
+
+
+def point_source_run(N=(40, 40, 40), d=1e-3, c0=1500.0, alpha=0.0, f0=250e3, cycles=2, nt=150, cfl=0.3, dtype=np.float64,
+                     src=(8, 20, 20), asm=None):
+    dt = cfl * d / c0
+    t = np.arange(0, cycles / f0, dt)
+    sig = np.sin(2 * np.pi * f0 * t) * np.hanning(t.size)
+    idx = np.array([src[0] + N[0] * (src[1] + N[1] * src[2])], dtype=np.int64)
+    inp = SolverInputs(N=N, d=(d, d, d), dt=dt, Nt=nt, c0=c0, rho0=1000.0, alpha_db=alpha, src_idx=idx, src_p=sig[None, :])
+    trace = []
+    out = simulate(inp, dtype=dtype, asm=asm, progress=lambda i, p: trace.append(p.copy()), return_p_final=True)
+    return out, np.array(trace), dt, sig
+
+
+def test_spherical_spreading_and_speed():
+    out, tr, dt, sig = point_source_run()
+    pml = out["pml"]
+    s = np.array([8, 20, 20]) + np.array(pml)
+    r1, r2 = 10, 20
+    a1 = tr[:, s[0] + r1, s[1], s[2]]
+    a2 = tr[:, s[0] + r2, s[1], s[2]]
+    # arrival time difference from the cross-correlation peak, sub-sample by parabolic fit
+    xc = np.correlate(a2, a1, mode="full")
+    k = int(np.argmax(xc))
+    y0, y1, y2 = xc[k - 1], xc[k], xc[k + 1]
+    lag = (k - (len(a1) - 1)) + 0.5 * (y0 - y2) / (y0 - 2 * y1 + y2)
+    c_meas = (r2 - r1) * 1e-3 / (lag * dt)
+    assert abs(c_meas - 1500.0) / 1500.0 < 5e-3
+    # 1/r decay of the peak amplitude
+    ratio = np.abs(a1).max() / np.abs(a2).max()
+    assert abs(ratio - r2 / r1) / (r2 / r1) < 0.03
+
+
+def test_pml_absorbs_outgoing_wave():
+    out, tr, dt, sig = point_source_run(nt=260)
+    pml = out["pml"]
+    inner = tuple(slice(pml[a], pml[a] + 40) for a in range(3))
+    energy = np.array([np.sum(p[inner] ** 2) for p in tr])
+    assert energy[-1] < 1e-5 * energy.max()
+
+
+def test_power_law_absorption_decay():
+    f0, y, alpha_db = 500e3, 0.9, 3.0
+    lossless, tr0, dt, _ = point_source_run(alpha=0.0, f0=f0, cycles=4, nt=170, asm=Assumptions(alpha_power=y))
+    lossy, tr1, _, _ = point_source_run(alpha=alpha_db, f0=f0, cycles=4, nt=170, asm=Assumptions(alpha_power=y))
+    s = np.array([8, 20, 20]) + np.array(lossless["pml"])
+    r1, r2 = 8, 24
+    def amp(tr, r):
+        return np.abs(tr[:, s[0] + r, s[1], s[2]]).max()
+    measured = (amp(tr1, r2) / amp(tr1, r1)) / (amp(tr0, r2) / amp(tr0, r1))
+    alpha_np_per_m = alpha_db * (f0 / 1e6) ** y * 100.0 / 8.685889638
+    expected = np.exp(-alpha_np_per_m * (r2 - r1) * 1e-3)
+    assert abs(measured - expected) / expected < 0.03
+
+
+def test_float32_noise_floor():
+    o64, _, _, _ = point_source_run(dtype=np.float64, nt=120)
+    o32, _, _, _ = point_source_run(dtype=np.float32, nt=120)
+    err = np.linalg.norm(o32["p_max"].astype(np.float64) - o64["p_max"]) / np.linalg.norm(o64["p_max"])
+    assert err < 2e-5
+
+
+def test_source_scaling_and_sign_convention():
+    """Additive source: 2 dt/(3 c0 dx) per split component -> first-step pressure at the node equals
+    c0^2 * 3 * scale * s[0] (no k-space correction), i.e. 2 c0 dt / dx * s."""
+    N, d, c0 = (24, 24, 24), 1e-3, 1500.0
+    dt = 0.3 * d / c0
+    idx = np.array([12 + 24 * (12 + 24 * 12)], dtype=np.int64)
+    sig = np.array([[1.0, 0.0, 0.0]])
+    inp = SolverInputs(N=N, d=(d, d, d), dt=dt, Nt=1, c0=c0, rho0=1000.0, alpha_db=0.0, src_idx=idx, src_p=sig)
+    out = simulate(inp, dtype=np.float64, asm=Assumptions(source_kspace_correction=False), return_p_final=True)
+    pml = out["pml"]
+    val = out["p_final"][12 + pml[0], 12 + pml[1], 12 + pml[2]]
+    assert np.isclose(val, 2 * c0 * dt / d, rtol=1e-12)
+
+
+def test_kgrid_conventions():
+    assert np.allclose(kg.x_vec(4, 1.0), [-2, -1, 0, 1])
+    assert np.allclose(kg.x_vec(5, 1.0), [-2, -1, 0, 1, 2])
+    k = kg.k_vec_fft(4, 1.0)
+    assert np.isclose(k[2], -np.pi)                       # negative Nyquist
+    p = kg.pml_profile(30, 1e-3, 1e-7, 1500.0, 10)
+    assert p[10:20].min() == 1.0 and p[0] < p[9] < 1.0 and p[-1] == p[0]
+    sg = kg.pml_profile(30, 1e-3, 1e-7, 1500.0, 10, staggered=True)
+    assert sg[-1] < p[-1] and sg[0] > p[0]                 # shifted by +1/2 cell
+    assert kg.largest_prime_factor(81) == 3 and kg.largest_prime_factor(125) == 5 and kg.largest_prime_factor(97) == 97
