@@ -298,7 +298,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         prof = sim.profile_stages(reps=8, with_source=True)
-        own = [(n, ms, b) for n, ms, b in prof if n.startswith("k_") and b > 0]
+        own = [(n, ms, b) for n, ms, b in prof if n.startswith(("k_", "k2_")) and b > 0]
         tot = sum(ms for _, ms, _ in prof)
         name, ms, bpv = max(own, key=lambda r: r[1])
         ach = bpv * V / (ms * 1e-3) / 1e9
@@ -365,7 +365,7 @@ def main():
                 "config": {"workload": workload_name(args), "voxels": V, "time_steps": Nt, "n_src": int(n_src),
                            "foci": "C4 wheel: rank r, step s -> focus (r + s*N) mod 32",
                            "l2": "working set (~20 fields x 67 MB) exceeds the 126 MB L2; no flush needed",
-                           "fft": "cuFFT 3-D R2C/C2R (v1 pipeline)", "time_loop_only_value": loop_value},
+                           "fft": ("hand-written fused FFT passes (v2 pipeline)" if st["fft_launches"] == 0 else "cuFFT 3-D R2C/C2R (v1 pipeline)"), "time_loop_only_value": loop_value},
                 "e2e": e2e, "gpu_launches": int(launches), "fft_launches": int(st["fft_launches"] * args.steps),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "stages": stages_out}
         print(json.dumps(line), flush=True)

@@ -97,4 +97,23 @@ struct SourceParams {
   const float* gain;          // per element
 };
 
+// Per-pipeline parameters (device pointers owned by the handle).
+struct V2Params {
+  int Nx, Ny, Nz, Nxh, PH;          // PH = row pitch of the H layout (multiple of 16)
+  long long HS;                     // stride between batched H fields  (Nz*Ny*PH)
+  long long ZS;                     // stride between batched Z fields  (Nz*(Ny/2)*Nx)
+  const float2 *twx, *twy, *twz;    // inter-stage twiddles exp(-2 pi i m / N), m = 0..N-1, per axis
+  float2* ZP;                       // x-spectrum of the pressure (row pairs)
+  float2* Z4;                       // [4][ZS] packed spectra (gradients, then velocity, then divergence + source)
+  float2* H4;                       // [4][HS] half spectra
+  float norm;                       // 1 / (2 * Nx*Ny*Nz): FFT normalisation and the row-pair split factor
+  // source slab (planes z0s .. z0s+nzs-1 of the expanded grid)
+  int z0s, nzs;
+  float* Sslab;                     // [nzs][Ny][Nx] dense source field on the slab
+  float2* ZSslab;                   // [nzs][Ny/2][Nx]
+  float2* HSslab;                   // [nzs][Ny][PH]
+  int store_p;                      // write the real-space pressure (last step / debugging)
+};
+
+
 }  // namespace lifu

@@ -5,9 +5,11 @@
 // (/root/reference/src/openlifu/sim/kwave_if.py:117-129): PML sizing and grid expansion,
 // k-space operators, the time loop and the p_max/p_min sensor reduction.
 #include <cstdarg>
+#include <functional>
 
 #include "sim.cuh"
 #include "step_kernels.cuh"
+#include "fft_v2.cuh"
 
 namespace lifu {
 
@@ -309,6 +311,8 @@ int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** ou
   s->CS = round_up(s->Vh, 64);
   const char* ng = getenv("LIFU_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
+  const char* pl = getenv("LIFU_PIPELINE");
+  s->pipeline = (pl && !strcmp(pl, "v1")) ? 1 : ((pl && !strcmp(pl, "v2")) ? 2 : 0);
 
   StepParams& P = s->P;
   P.Nx = s->N[0]; P.Ny = s->N[1]; P.Nz = s->N[2]; P.Nxh = s->Nxh;
@@ -558,6 +562,138 @@ static void launch_rho_p(lifu_sim* s, int gb) {
   else k_update_rho_p<HOMOG, SRC, false><<<gb, 256, 0, s->stream>>>(s->P);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// pipeline v2: fused hand-written FFT passes (fft_v2.cuh)
+static int radix_of(int n) { return n == 64 ? 8 : (n == 256 ? 16 : 0); }
+
+static bool v2_eligible(const lifu_sim* s) {
+  if (s->pipeline == 1) return false;
+  if (s->absorbing) return false;
+  for (int a = 0; a < 3; ++a) if (radix_of(s->N[a]) == 0) return false;
+  return true;
+}
+
+static int v2_setup(lifu_sim* s) {
+  V2Params& Q = s->Q;
+  if (!s->v2_ready) {
+    Q.Nx = s->N[0]; Q.Ny = s->N[1]; Q.Nz = s->N[2]; Q.Nxh = s->Nxh;
+    Q.PH = (int)round_up(s->Nxh, 16);
+    Q.HS = (long long)Q.Nz * Q.Ny * Q.PH;
+    Q.ZS = (long long)Q.Nz * (Q.Ny / 2) * Q.Nx;
+    Q.norm = (float)(1.0 / (2.0 * (double)s->V));
+    for (int a = 0; a < 3; ++a) {
+      s->R[a] = radix_of(s->N[a]);
+      const int n = s->N[a];
+      std::vector<float2> tw(n);
+      for (int m = 0; m < n; ++m) {
+        double ang = -2.0 * M_PI * (double)m / (double)n;
+        tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      }
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_tw[a], sizeof(float2) * n));
+      LIFU_CUDA(cudaMemcpyAsync(s->d_tw[a], tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+      LIFU_CUDA(cudaStreamSynchronize(s->stream));
+    }
+    Q.twx = s->d_tw[0]; Q.twy = s->d_tw[1]; Q.twz = s->d_tw[2];
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.ZP, sizeof(float2) * Q.ZS));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.Z4, sizeof(float2) * 4 * Q.ZS));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.H4, sizeof(float2) * 4 * Q.HS));
+    s->v2_ready = true;
+  }
+  // source slab: z range of the mask (indices are sorted, x fastest, so first/last give min/max z)
+  int z0 = 0, nz = 1;
+  if (s->n_src > 0) {
+    long long first = 0, last = 0;
+    LIFU_CUDA(cudaMemcpyAsync(&first, s->d_lin_exp, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaMemcpyAsync(&last, s->d_lin_exp + (s->n_src - 1), sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaStreamSynchronize(s->stream));
+    const long long plane = (long long)s->N[0] * s->N[1];
+    z0 = (int)(first / plane);
+    nz = (int)(last / plane) - z0 + 1;
+  }
+  if (nz > s->slab_planes_alloc) {
+    // (re)allocate the slab buffers; old ones stay in the handle's allocation list until destroy
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.Sslab, sizeof(float) * (size_t)nz * s->N[1] * s->N[0]));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.ZSslab, sizeof(float2) * (size_t)nz * (s->N[1] / 2) * s->N[0]));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.HSslab, sizeof(float2) * (size_t)nz * s->N[1] * Q.PH));
+    s->slab_planes_alloc = nz;
+  }
+  Q.z0s = z0; Q.nzs = nz;
+  Q.store_p = 0;
+  return LIFU_OK;
+}
+
+#define V2_DISPATCH_R(RVAL, CALL8, CALL16) do { if ((RVAL) == 8) { CALL8; } else { CALL16; } } while (0)
+
+template <int R> static void v2_launch_x_u(lifu_sim* s, int grid, size_t sm) {
+  if (s->homogeneous) k2_x_u<R, true><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+  else k2_x_u<R, false><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+}
+template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int grid, size_t sm) {
+  if (s->homogeneous) k2_x_rho_p<R, true, SRC><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+  else k2_x_rho_p<R, false, SRC><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+}
+
+static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
+  const V2Params& Q = s->Q;
+  cudaStream_t st = s->stream;
+  const int Rx = s->R[0], Ry = s->R[1], Rz = s->R[2];
+  const int tiles = Q.PH / 16;
+  const size_t sm_y = sizeof(float2) * Ry * Ry * 16, sm_z = sizeof(float2) * Rz * Rz * 16;
+  const size_t sm_x = sizeof(float2) * 256 * (Rx + 1);
+  const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (256 / Rx));
+  int nk = 0;
+  const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
+  const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
+  // (1) pressure gradient
+  V2_DISPATCH_R(Ry, (k2_y_fwd<8, 0><<<dim3(tiles, Q.Nz, 1), 128, sm_y, st>>>(s->P, Q)),
+                    (k2_y_fwd<16, 0><<<dim3(tiles, Q.Nz, 1), 256, sm_y, st>>>(s->P, Q)));
+  ++nk; mark("k2_y_fwd_p", 8);
+  V2_DISPATCH_R(Rz, (k2_z_grad<8><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
+                    (k2_z_grad<16><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
+  ++nk; mark("k2_z_grad", 12);
+  V2_DISPATCH_R(Ry, (k2_y_inv_grad<8><<<dim3(tiles, Q.Nz), 128, sm_y, st>>>(s->P, Q)),
+                    (k2_y_inv_grad<16><<<dim3(tiles, Q.Nz), 256, sm_y, st>>>(s->P, Q)));
+  ++nk; mark("k2_y_inv_grad", 20);
+  // (2) velocity update + forward x transform of the new velocity
+  V2_DISPATCH_R(Rx, (v2_launch_x_u<8>(s, gx, sm_x)), (v2_launch_x_u<16>(s, gx, sm_x)));
+  ++nk; mark("k2_x_u", s->homogeneous ? 48 : 60);
+  V2_DISPATCH_R(Ry, (k2_y_fwd<8, 1><<<dim3(tiles, Q.Nz, 3), 128, sm_y, st>>>(s->P, Q)),
+                    (k2_y_fwd<16, 1><<<dim3(tiles, Q.Nz, 3), 256, sm_y, st>>>(s->P, Q)));
+  ++nk; mark("k2_y_fwd_u", 24);
+  // (3) source field on its slab
+  if (src != 0) {
+    k2_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, Q, s->S);
+    ++nk; mark("k2_source_scatter", 0);
+    if (src == 1) {
+      const int gs = (int)(((long long)Q.nzs * (Q.Ny / 2) + (256 / Rx) - 1) / (256 / Rx));
+      V2_DISPATCH_R(Rx, (k2_x_src<8><<<gs, 256, sm_x, st>>>(s->P, Q)), (k2_x_src<16><<<gs, 256, sm_x, st>>>(s->P, Q)));
+      ++nk; mark("k2_x_src", 8 * srcf);
+      V2_DISPATCH_R(Ry, (k2_y_fwd<8, 2><<<dim3(tiles, Q.nzs, 1), 128, sm_y, st>>>(s->P, Q)),
+                        (k2_y_fwd<16, 2><<<dim3(tiles, Q.nzs, 1), 256, sm_y, st>>>(s->P, Q)));
+      ++nk; mark("k2_y_fwd_src", 8 * srcf);
+    }
+  }
+  // (4) divergence (+ filtered source) through z and back through y
+  const int ncomp = src == 1 ? 4 : 3;
+  V2_DISPATCH_R(Rz, (k2_z_div<8><<<dim3(tiles, Q.Ny, ncomp), 128, sm_z, st>>>(s->P, Q, 0)),
+                    (k2_z_div<16><<<dim3(tiles, Q.Ny, ncomp), 256, sm_z, st>>>(s->P, Q, 0)));
+  ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
+  V2_DISPATCH_R(Ry, (k2_y_inv<8><<<dim3(tiles, Q.Nz, ncomp), 128, sm_y, st>>>(s->P, Q)),
+                    (k2_y_inv<16><<<dim3(tiles, Q.Nz, ncomp), 256, sm_y, st>>>(s->P, Q)));
+  ++nk; mark("k2_y_inv", 8 * ncomp);
+  // (5) density update, source, equation of state, sensor, forward x transform of p
+  if (src == 0) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 0>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 0>(s, gx, sm_x)));
+  else if (src == 1) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 1>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 1>(s, gx, sm_x)));
+  else V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 2>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 2>(s, gx, sm_x)));
+  ++nk;
+  const double inner = (double)s->Vin / (double)s->V;
+  mark("k2_x_rho_p", 12 + 24 + 16 * inner + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+  LIFU_CUDA(cudaGetLastError());
+  if (n_kernels) *n_kernels = nk;
+  return LIFU_OK;
+}
+
 // Enqueue one time step on the handle's stream.  Counts hand-written kernels / FFT executions.
 static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts) {
   StepParams& P = s->P;
@@ -573,6 +709,11 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
     ++s->prof_used;
   };
   mark("begin", 0);
+  if (s->last_used_v2) {
+    int rc2 = enqueue_step_v2(s, src_active, n_kernels, mark);
+    if (n_ffts) *n_ffts = 0;
+    return rc2;
+  }
   const int gbh = grid_blocks(s, s->Vh, 256);
   const int gbr = grid_blocks(s, s->V, 256);
   int nk = 0, nf = 0;
@@ -686,8 +827,16 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     }
   } restore{s, user_stream, own};
   cudaStream_t st = s->stream;
-  LIFU_CHECK(build_plans(s));
-  {
+  if (s->pipeline == 2 && !v2_eligible(s)) {
+    set_error("lifu_run: LIFU_PIPELINE=v2 needs a lossless medium and 64- or 256-point axes (grid is %dx%dx%d)",
+              s->N[0], s->N[1], s->N[2]);
+    return LIFU_ERR_STATE;
+  }
+  s->last_used_v2 = v2_eligible(s);
+  if (s->last_used_v2) {
+    LIFU_CHECK(v2_setup(s));
+  } else {
+    LIFU_CHECK(build_plans(s));
     cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
     for (cufftHandle h : hs) LIFU_CUFFT(cufftSetStream(h, st));
   }
@@ -703,6 +852,10 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   LIFU_CUDA(cudaMemsetAsync(P.rho, 0, 3 * R, st));
   LIFU_CUDA(cudaMemsetAsync(P.S, 0, R, st));
   LIFU_CUDA(cudaMemsetAsync(P.step, 0, sizeof(int), st));
+  if (s->last_used_v2) {
+    LIFU_CUDA(cudaMemsetAsync(s->Q.ZP, 0, sizeof(float2) * s->Q.ZS, st));
+    LIFU_CUDA(cudaMemsetAsync(s->Q.Sslab, 0, sizeof(float) * (size_t)s->Q.nzs * s->N[1] * s->N[0], st));
+  }
   k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmax, s->Vin, -INFINITY);
   k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmin, s->Vin, INFINITY);
   LIFU_CUDA(cudaGetLastError());
@@ -734,7 +887,13 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   int rc = LIFU_OK;
   for (int t = 0; t < nt && rc == LIFU_OK; ++t) {
     const int v = t < L ? 0 : 1;
-    if (graphs) {
+    if (s->last_used_v2 && t == nt - 1) {   // last step also materialises the real-space pressure
+      s->Q.store_p = 1;
+      int k1 = 0, f1 = 0;
+      rc = enqueue_step(s, v == 0, &k1, &f1);
+      s->Q.store_p = 0;
+      if (nk[v] == 0) { nk[v] = k1; nf[v] = f1; }
+    } else if (graphs) {
       if (cudaGraphLaunch(gexec[v], st) != cudaSuccess) { set_error("cudaGraphLaunch failed at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); rc = LIFU_ERR_CUDA; }
     } else {
       rc = enqueue_step(s, v == 0, &nk[v], &nf[v]);
@@ -769,7 +928,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
 int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, char* names, int name_stride,
                         double* ms, double* bytes_per_voxel, int* n_stages) {
   if (!s || reps <= 0 || !ms || !n_stages) { set_error("lifu_profile_stages: bad argument"); return LIFU_ERR_INVALID; }
-  if (!s->plans_ready || !s->medium_set || !s->geometry_set || !s->drive_set) {
+  if (!(s->plans_ready || s->v2_ready) || !s->medium_set || !s->geometry_set || !s->drive_set) {
     set_error("lifu_profile_stages: call lifu_run once first");
     return LIFU_ERR_STATE;
   }
@@ -777,7 +936,7 @@ int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, 
   cudaStream_t user = s->stream, own = nullptr;
   if (!user) { LIFU_CUDA(cudaStreamCreateWithFlags(&own, cudaStreamNonBlocking)); s->stream = own; }
   cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
-  for (cufftHandle h : hs) cufftSetStream(h, s->stream);
+  if (s->plans_ready) for (cufftHandle h : hs) cufftSetStream(h, s->stream);
   std::vector<double> acc;
   int rc = LIFU_OK;
   s->prof_names.clear(); s->prof_bytes.clear();
@@ -794,7 +953,7 @@ int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, 
       acc[i] += t;
     }
   }
-  for (cufftHandle h : hs) cufftSetStream(h, user);
+  if (s->plans_ready) for (cufftHandle h : hs) cufftSetStream(h, user);
   if (own) { cudaStreamDestroy(own); }
   s->stream = user;
   if (rc != LIFU_OK) return rc;

@@ -60,6 +60,15 @@ struct lifu_sim {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   bool use_graph = true;
 
+  // pipeline v2 (fused hand-written FFT passes); used when every axis is 64 or 256 and the medium is lossless
+  int pipeline = 0;            // 0 auto, 1 force v1 (cuFFT), 2 force v2
+  bool v2_ready = false;
+  int R[3] = {0, 0, 0};        // radix per axis (N = R*R)
+  lifu::V2Params Q{};
+  float2* d_tw[3] = {nullptr, nullptr, nullptr};
+  long long slab_planes_alloc = 0;
+  bool last_used_v2 = false;
+
   // per-stage profiling (lifu_profile_stages)
   bool prof_on = false;
   int prof_used = 0;

@@ -39,6 +39,12 @@ def small_water_case():
                      dt=3e-7, t_end=60 * 3e-7, name="small_water")
 
 
+def v2_small_case(steps=80):
+    """Inner 40x44x36 at 1 mm -> PML (12,10,14) -> 64^3: the smallest grid the fused-FFT pipeline (v2) takes."""
+    return make_case([(-20, 19), (-22, 21), (-3, 32)], 1.0, 2, 2, 3.0, 0.5, (0, 0, 18), 400e3, 2,
+                     dt=3e-7, t_end=steps * 3e-7, name="v2_small")
+
+
 def c1_case():
     """8x8 array, 4 mm pitch, focus 50 mm, water, 1 mm grid."""
     return make_case([(-30, 30), (-30, 30), (-4, 70)], 1.0, 8, 8, 4.0, 0.5, (0, 0, 50), 400e3, 10, name="C1")
@@ -59,9 +65,17 @@ def run_oracle_case(case, dtype=np.float32, asm=None, max_steps=None):
             "N_exp": out["raw"]["N_exp"]}
 
 
-def run_cuda_case(case, alpha_mode="binary", source_mode="additive", geometry=None, max_steps=None, device=0):
-    """Drive the C ABI exactly like openlifu_b200.sim.run_simulation does, from plain data."""
+def run_cuda_case(case, alpha_mode="binary", source_mode="additive", geometry=None, max_steps=None, device=0,
+                  pipeline=None, fields=()):
+    """Drive the C ABI exactly like openlifu_b200.sim.run_simulation does, from plain data.
+    pipeline: None (auto) | "v1" (cuFFT) | "v2" (fused FFT passes); read by lifu_create from LIFU_PIPELINE."""
+    import os
     from openlifu_b200 import _lib
+
+    if pipeline is None:
+        os.environ.pop("LIFU_PIPELINE", None)
+    else:
+        os.environ["LIFU_PIPELINE"] = pipeline
 
     sc = scene_of(case)
     N, d, Nt, dt = osc.time_axis(sc, case["dt"], case["t_end"], 0.5)
@@ -82,7 +96,9 @@ def run_cuda_case(case, alpha_mode="binary", source_mode="additive", geometry=No
         sim.set_drive(base, n_delay, case["apod"], source_mode=source_mode)
         p_max, p_min, stats = sim.run()
         idx, row_ptr, col, w, n_el = sim.get_source_geometry()
-    return {"p_max": p_max, "p_min": p_min, "stats": stats, "src_idx": idx, "row_ptr": row_ptr, "col": col, "w": w,
+        extra = {f"field{k}": sim.get_field(k) for k in fields}
+    os.environ.pop("LIFU_PIPELINE", None)
+    return {**extra, "p_max": p_max, "p_min": p_min, "stats": stats, "src_idx": idx, "row_ptr": row_ptr, "col": col, "w": w,
             "n_delay": n_delay, "Nt": Nt, "dt": dt}
 
 

@@ -135,3 +135,84 @@ def test_errors(lifu_lib):
     with _lib.LifuSim([16, 16, 16], [1e-3] * 3, 1e-7, 4) as sim:
         with pytest.raises(_lib.LifuError, match="lifu_set_medium first"):
             sim.run()
+
+
+# ---------------------------------------------------------------------------------------------
+# pipeline v2 (hand-written fused FFT passes) -- same oracle, same tolerances
+def _is_v2(got):
+    return got["stats"]["fft_launches"] == 0
+
+
+def test_v2_small_water(lifu_lib):
+    case = cases.v2_small_case()
+    want = cases.run_oracle_case(case)
+    assert tuple(want["N_exp"]) == (64, 64, 64)
+    got = cases.run_cuda_case(case)
+    assert _is_v2(got), "auto selection should pick the fused pipeline on a 64^3 lossless grid"
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    _check_fields(got, want)
+
+
+def test_v2_matches_v1(lifu_lib):
+    case = cases.v2_small_case()
+    a = cases.run_cuda_case(case, pipeline="v1", fields=(0, 1, 2, 3, 4, 5, 6))
+    b = cases.run_cuda_case(case, pipeline="v2", fields=(0, 1, 2, 3, 4, 5, 6))
+    assert not _is_v2(a) and _is_v2(b)
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(b[k], a[k]) < 2e-5
+    for f in range(7):
+        assert cases.rel_l2(b[f"field{f}"], a[f"field{f}"]) < 2e-4, f"state field {f} differs between pipelines"
+
+
+def test_v2_no_source_correction(lifu_lib):
+    from oracle.solver import Assumptions
+    case = cases.v2_small_case()
+    want = cases.run_oracle_case(case, asm=Assumptions(source_kspace_correction=False))
+    got = cases.run_cuda_case(case, source_mode="additive-no-correction")
+    assert _is_v2(got)
+    _check_fields(got, want)
+
+
+def test_v2_heterogeneous_lossless(lifu_lib):
+    case = cases.v2_small_case()
+    c0, rho0, _ = _phantom(tuple(case["N"]))
+    case["c0"], case["rho0"], case["alpha"] = c0, rho0, 0.0
+    case["dt"], case["t_end"] = 1.5e-7, 100 * 1.5e-7
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert _is_v2(got) and got["stats"]["homogeneous"] == 0
+    _check_fields(got, want)
+
+
+def test_v2_mixed_axes_tilted(lifu_lib):
+    """256 x 64 x 64 expanded grid (different radix per axis), rotated off-grid elements."""
+    pos = np.array([[-20.3, 1.1, 0.7], [13.9, -2.2, 1.4], [40.2, 3.1, -0.3]])
+    size = np.array([[2.3, 3.1], [2.0, 2.0], [3.3, 1.7]])
+    ang = np.array([[0.0, 14.17, 0.0], [-9.0, 0.0, 0.0], [5.0, -7.0, 30.0]])
+    case = cases.make_case([(-54, 53.5), (-10, 9.5), (-3, 18.5)], 0.5, 0, 0, 0, 0, (0, 0, 12), 500e3, 2,
+                           elem_pos_mm=pos, elem_size_mm=size, angles_deg=ang, dt=1.2e-7, t_end=60 * 1.2e-7)
+    want = cases.run_oracle_case(case)
+    assert tuple(want["N_exp"]) == (256, 64, 64)
+    got = cases.run_cuda_case(case)
+    assert _is_v2(got)
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    _check_fields(got, want)
+
+
+def test_v2_c2_grid_short(lifu_lib):
+    """The headline grid (216^3 -> 256^3, 2x64-element array) for 24 time steps against the oracle."""
+    from openlifu_b200 import configs
+    arr = configs.openlifu_2x_array()
+    half = 53.75
+    pos = np.array([el.position for el in arr.elements])
+    size = np.array([el.size for el in arr.elements])
+    ang = np.array([el.get_angle(units="deg") for el in arr.elements])
+    dt = 0.5 * 0.5e-3 / 1500
+    case = cases.make_case([(-half, half), (-half, half), (-4, 103.5)], 0.5, 0, 0, 0, 0, (0, 0, 50), 400e3, 20,
+                           elem_pos_mm=pos, elem_size_mm=size, angles_deg=ang, sensitivity=None, dt=dt, t_end=24 * dt)
+    want = cases.run_oracle_case(case)
+    assert tuple(want["N_exp"]) == (256, 256, 256)
+    got = cases.run_cuda_case(case)
+    assert _is_v2(got)
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    _check_fields(got, want)
