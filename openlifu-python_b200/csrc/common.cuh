@@ -53,6 +53,7 @@ struct StepParams {
   long long Vh;               // Nxh*Ny*Nz
   long long RS, CS;           // strides between batched real / complex fields
   float invN;                 // 1/(Nx*Ny*Nz): cuFFT transforms are unnormalised
+  int poly_ok;                // (c_ref k dt/2)^2 <= 9.8 everywhere: polynomial sinc/cos are valid
   // 1-D tables
   const float2 *dpx, *dpy, *dpz;   // i k exp(+i k d/2)
   const float2 *dnx, *dny, *dnz;   // i k exp(-i k d/2)

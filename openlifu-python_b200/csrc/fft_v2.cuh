@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(16 * R) k2_y_fwd(StepParams P, V2Params Q) {
 
 // z pass of the pressure gradient: H4[0] -> H4[0] (kappa p^) and H4[1] (i kz e^{+i kz dz/2} kappa p^),
 // both already inverse transformed along z.  grid (PH/16, Ny)
-template <int R>
+template <int R, bool POLY>
 __global__ void __launch_bounds__(16 * R) k2_z_grad(StepParams P, V2Params Q) {
   extern __shared__ float2 smem[];
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(16 * R) k2_z_grad(StepParams P, V2Params Q) {
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
     const int kz = t + R * k1;
-    const float kap = kappa_of(axy + P.az2[kz]) * Q.norm;
+    const float a2 = axy + P.az2[kz];
+    const float kap = (POLY ? sinc_sqrt_poly(a2) : kappa_of(a2)) * Q.norm;
     v[k1] = cscale(v[k1], kap);
     w[k1] = cmul2(v[k1], P.dpz[kz]);
   }
@@ -299,45 +300,57 @@ __global__ void __launch_bounds__(16 * R) k2_y_inv_grad(StepParams P, V2Params Q
 }
 
 // z pass of the velocity divergence (comp 0..2, in place) and of the source field (comp 3).
-// grid (PH/16, Ny, ncomp).  comp 2 additionally gets i kz e^{-i kz dz/2}; comp 3 reads the slab planes
-// only and is filtered with cos(c_ref k dt/2).
-template <int R>
-__global__ void __launch_bounds__(16 * R) k2_z_div(StepParams P, V2Params Q, int first_comp) {
+// grid (PH/16, Ny); the CTA walks the components so that kappa is evaluated once per (kx,ky,kz).
+// comp 2 additionally gets i kz e^{-i kz dz/2}; comp 3 reads the slab planes only and is filtered with
+// cos(c_ref k dt/2).
+template <int R, bool POLY>
+__global__ void __launch_bounds__(16 * R, 2) k2_z_div(StepParams P, V2Params Q, int ncomp) {
   extern __shared__ float2 smem[];
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, ky = blockIdx.y, comp = first_comp + blockIdx.z;
+  const int kx = blockIdx.x * 16 + l, ky = blockIdx.y;
   const bool active = kx < Q.Nxh;
   const long long zs = (long long)Q.Ny * Q.PH;
   const long long base = (long long)ky * Q.PH + kx;
-  float2* H = Q.H4 + comp * Q.HS;
-  float2 v[R];
-  if (comp < 3) {
-#pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = active ? H[base + (long long)(t + R * j) * zs] : make_float2(0.f, 0.f);
-  } else {
-#pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int zr = t + R * j - Q.z0s;
-      v[j] = (active && zr >= 0 && zr < Q.nzs) ? Q.HSslab[base + (long long)zr * zs] : make_float2(0.f, 0.f);
-    }
-  }
-  strided_fft<R, false>(v, Q.twz, smem, l, t);
   const float axy = active ? P.ax2[kx] + P.ay2[ky] : 0.f;
+  float kap[R];
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
-    const int kz = t + R * k1;
-    const float a2 = axy + P.az2[kz];
-    if (comp < 3) {
-      v[k1] = cscale(v[k1], kappa_of(a2) * Q.norm);
-      if (comp == 2) v[k1] = cmul2(v[k1], P.dnz[kz]);
-    } else {
-      v[k1] = cscale(v[k1], cosf(sqrtf(a2)) * Q.norm);
-    }
+    const float a2 = axy + P.az2[t + R * k1];
+    kap[k1] = (POLY ? sinc_sqrt_poly(a2) : kappa_of(a2)) * Q.norm;
   }
-  strided_fft<R, true>(v, Q.twz, smem, l, t);
-  if (active) {
+#pragma unroll 1
+  for (int comp = 0; comp < ncomp; ++comp) {
+    float2* H = Q.H4 + comp * Q.HS;
+    float2 v[R];
+    if (comp < 3) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) H[base + (long long)(t + R * j) * zs] = v[j];
+      for (int j = 0; j < R; ++j) v[j] = active ? H[base + (long long)(t + R * j) * zs] : make_float2(0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int zr = t + R * j - Q.z0s;
+        v[j] = (active && zr >= 0 && zr < Q.nzs) ? Q.HSslab[base + (long long)zr * zs] : make_float2(0.f, 0.f);
+      }
+    }
+    strided_fft<R, false>(v, Q.twz, smem, l, t);
+    if (comp < 2) {
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) v[k1] = cscale(v[k1], kap[k1]);
+    } else if (comp == 2) {
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) v[k1] = cmul2(cscale(v[k1], kap[k1]), P.dnz[t + R * k1]);
+    } else {
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) {
+        const float a2 = axy + P.az2[t + R * k1];
+        v[k1] = cscale(v[k1], (POLY ? cos_sqrt_poly(a2) : cosf(sqrtf(a2))) * Q.norm);
+      }
+    }
+    strided_fft<R, true>(v, Q.twz, smem, l, t);
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < R; ++j) H[base + (long long)(t + R * j) * zs] = v[j];
+    }
   }
 }
 
@@ -363,115 +376,234 @@ __global__ void __launch_bounds__(16 * R) k2_y_inv(StepParams P, V2Params Q) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// x passes.  blockDim = 256: 256/R groups of R lanes, one row pair (z, m) per group.
-template <int R, bool HOMOG>
-__global__ void __launch_bounds__(256) k2_x_u(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
-  constexpr int G = 256 / R;
-  const int g = threadIdx.x / R, t = threadIdx.x % R;
-  float2* sm = smem + g * R * (R + 1);
-  const long long pair = (long long)blockIdx.x * G + g;          // z*(Ny/2) + m
-  const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
-  const long long zoff = pair * Q.Nx;
-  const long long r0 = ((long long)z * Q.Ny + 2 * m) * Q.Nx;     // first row of the pair in a real field
-  const float sy0 = P.sgy[2 * m], sy1 = P.sgy[2 * m + 1], szz = P.sgz[z];
+// x passes.  Persistent CTAs of 128 threads = 128/R groups of R lanes; a group owns one row pair at a
+// time and walks its work as a sequence of "items" (one packed spectrum line + one pair of real rows).
+// Items are prefetched two deep with cp.async into the group's private shared-memory stages, so the
+// memory latency of item q+1 overlaps the transforms of item q regardless of occupancy.  The FFT
+// exchange runs inside the (already consumed) spectrum stage with an XOR swizzle instead of padding.
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPENDING) : "memory"); }
+
+template <int R, bool INV>
+__device__ __forceinline__ void line_fft_sw(float2 (&v)[R], const float2* __restrict__ tw, float2* sm, int t) {
+  constexpr int N = R * R;
+  if constexpr (!INV) {
+    dft<R, false>(v);
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
+    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul2(v[k2], tw[(t * k2) & (N - 1)]);
+#pragma unroll
+    for (int k2 = 0; k2 < R; ++k2) sm[t * R + (k2 ^ t)] = v[k2];
+    __syncwarp();
+#pragma unroll
+    for (int tt = 0; tt < R; ++tt) v[tt] = sm[tt * R + (t ^ tt)];
+    __syncwarp();
+    dft<R, false>(v);
+  } else {
+    dft<R, true>(v);
+#pragma unroll
+    for (int tt = 1; tt < R; ++tt) v[tt] = cmulc(v[tt], tw[(tt * t) & (N - 1)]);
+#pragma unroll
+    for (int tt = 0; tt < R; ++tt) sm[tt * R + (t ^ tt)] = v[tt];
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < R; ++k2) v[k2] = sm[t * R + (k2 ^ t)];
+    __syncwarp();
+    dft<R, true>(v);
+  }
+}
+
+// One group's staging: stage s = [ N float2 spectrum line | 2N floats (row pair) ]
+template <int R>
+struct XStage {
+  static constexpr int N = R * R;
+  static constexpr int BYTES = 16 * N;          // per stage
+  static constexpr int GROUPS = 128 / R;
+  static constexpr int SMEM = GROUPS * 2 * BYTES + 8 * N;   // + twiddle table
+  // copy `bytes` (multiple of 16*R) from global to shared with the R lanes of the group
+  static __device__ __forceinline__ void copy(char* sdst, const char* gsrc, int bytes, int t) {
+#pragma unroll
+    for (int o = 0; o < 8 * N; o += 16 * R)
+      if (o < bytes) cp_async16(sdst + o + 16 * t, gsrc + o + 16 * t);
+  }
+};
+
+template <int R, bool HOMOG>
+__global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
+  using XS = XStage<R>;
+  constexpr int N = R * R, G = XS::GROUPS;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float2* tw = reinterpret_cast<float2*>(smraw + G * 2 * XS::BYTES);
+  for (int i = threadIdx.x; i < N; i += 128) tw[i] = Q.twx[i];
+  __syncthreads();
+  const int g = threadIdx.x / R, t = threadIdx.x % R;
+  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  const long long nbatch = (long long)Q.Nz * (Q.Ny / 2) / G;
+  const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long nitems = my_iters * 3;
+
+  auto issue = [&](long long q) {
+    if (q < nitems) {
+      const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
+      const int c = (int)(q % 3);
+      const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+      char* st = gbase + (q & 1) * XS::BYTES;
+      XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + pair * N), 8 * N, t);
+      XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + ((long long)z * Q.Ny + 2 * m) * N), 8 * N, t);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  for (long long q = 0; q < nitems; ++q) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
+    const int c = (int)(q % 3);
+    const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+    float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
+    const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
+    const long long r0 = ((long long)z * Q.Ny + 2 * m) * N;
     float2 v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = Q.Z4[c * Q.ZS + zoff + t + R * j];
-    line_fft<R, true>(v, Q.twx, sm, t);
+    for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+    __syncwarp();
+    line_fft_sw<R, true>(v, tw, zb, t);
     float* u = P.u + c * P.RS;
+    float s0, s1;
+    if (c == 1) { s0 = P.sgy[2 * m]; s1 = P.sgy[2 * m + 1]; } else { s0 = s1 = P.sgz[z]; }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int x = t + R * j;
-      float s0, s1;
-      if (c == 0) { s0 = s1 = P.sgx[x]; } else if (c == 1) { s0 = sy0; s1 = sy1; } else { s0 = s1 = szz; }
+      if (c == 0) s0 = s1 = P.sgx[x];
       float d0, d1;
       if constexpr (HOMOG) { d0 = d1 = P.dt_rho0_sg_s; }
-      else { d0 = P.dt_rho0_sg[c * P.RS + r0 + x]; d1 = P.dt_rho0_sg[c * P.RS + r0 + Q.Nx + x]; }
-      const float u0 = s0 * (s0 * u[r0 + x] - d0 * v[j].x);
-      const float u1 = s1 * (s1 * u[r0 + Q.Nx + x] - d1 * v[j].y);
+      else { d0 = P.dt_rho0_sg[c * P.RS + r0 + x]; d1 = P.dt_rho0_sg[c * P.RS + r0 + N + x]; }
+      const float u0 = s0 * (s0 * rb[x] - d0 * v[j].x);
+      const float u1 = s1 * (s1 * rb[N + x] - d1 * v[j].y);
       u[r0 + x] = u0;
-      u[r0 + Q.Nx + x] = u1;
+      u[r0 + N + x] = u1;
       v[j] = make_float2(u0, u1);
     }
-    line_fft<R, false>(v, Q.twx, sm, t);
+    line_fft_sw<R, false>(v, tw, zb, t);
+    float2* zo = Q.Z4 + c * Q.ZS + pair * N;
 #pragma unroll
-    for (int k1 = 0; k1 < R; ++k1) Q.Z4[c * Q.ZS + zoff + t + R * k1] = v[k1];
+    for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = v[k1];
+    __syncwarp();
+    issue(q + 2);
   }
+  cp_async_wait<0>();
 }
 
 // SRC: 0 none, 1 filtered source in Z4[3], 2 unfiltered dense slab
 template <int R, bool HOMOG, int SRC>
-__global__ void __launch_bounds__(256) k2_x_rho_p(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
-  constexpr int G = 256 / R;
+__global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
+  using XS = XStage<R>;
+  constexpr int N = R * R, G = XS::GROUPS;
+  constexpr int NI = SRC == 1 ? 4 : 3;                 // items per row pair: [source], rho_x, rho_y, rho_z
+  extern __shared__ __align__(16) unsigned char smraw[];
+  float2* tw = reinterpret_cast<float2*>(smraw + G * 2 * XS::BYTES);
+  for (int i = threadIdx.x; i < N; i += 128) tw[i] = Q.twx[i];
+  __syncthreads();
   const int g = threadIdx.x / R, t = threadIdx.x % R;
-  float2* sm = smem + g * R * (R + 1);
-  const long long pair = (long long)blockIdx.x * G + g;
-  const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
-  const long long zoff = pair * Q.Nx;
-  const long long r0 = ((long long)z * Q.Ny + 2 * m) * Q.Nx;
-  const float py0 = P.pmly[2 * m], py1 = P.pmly[2 * m + 1], pzz = P.pmlz[z];
-  float2 src[R];
-  if constexpr (SRC == 1) {
-#pragma unroll
-    for (int j = 0; j < R; ++j) src[j] = Q.Z4[3 * Q.ZS + zoff + t + R * j];
-    line_fft<R, true>(src, Q.twx, sm, t);
-  } else if constexpr (SRC == 2) {
-    const int zr = z - Q.z0s;
-    const bool in = zr >= 0 && zr < Q.nzs;
-    const long long s0 = ((long long)zr * Q.Ny + 2 * m) * Q.Nx;
-#pragma unroll
-    for (int j = 0; j < R; ++j)
-      src[j] = in ? make_float2(Q.Sslab[s0 + t + R * j], Q.Sslab[s0 + Q.Nx + t + R * j]) : make_float2(0.f, 0.f);
-  }
-  float2 sum[R];
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
+  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  const long long nbatch = (long long)Q.Nz * (Q.Ny / 2) / G;
+  const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long nitems = my_iters * NI;
+
+  auto issue = [&](long long q) {
+    if (q < nitems) {
+      const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
+      const int it = (int)(q % NI);
+      const int c = SRC == 1 ? it - 1 : it;              // -1: the source item
+      const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+      char* st = gbase + (q & 1) * XS::BYTES;
+      XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + pair * N), 8 * N, t);
+      if (c >= 0)
+        XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + ((long long)z * Q.Ny + 2 * m) * N), 8 * N, t);
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  issue(1);
+  float2 src[R], sum[R];
+  for (long long q = 0; q < nitems; ++q) {
+    cp_async_wait<1>();
+    __syncwarp();
+    const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
+    const int it = (int)(q % NI);
+    const int c = SRC == 1 ? it - 1 : it;
+    const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+    float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
+    const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
+    const long long r0 = ((long long)z * Q.Ny + 2 * m) * N;
     float2 v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = Q.Z4[c * Q.ZS + zoff + t + R * j];
-    line_fft<R, true>(v, Q.twx, sm, t);
-    float* rho = P.rho + c * P.RS;
+    for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+    __syncwarp();
+    line_fft_sw<R, true>(v, tw, zb, t);
+    if (c < 0) {
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int x = t + R * j;
+      for (int j = 0; j < R; ++j) src[j] = v[j];
+    } else {
+      if (SRC == 2 && c == 0) {
+        const int zr = z - Q.z0s;
+        const bool in = zr >= 0 && zr < Q.nzs;
+        const long long so = ((long long)zr * Q.Ny + 2 * m) * N;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          src[j] = in ? make_float2(Q.Sslab[so + t + R * j], Q.Sslab[so + N + t + R * j]) : make_float2(0.f, 0.f);
+      }
+      float* rho = P.rho + c * P.RS;
       float a0, a1;
-      if (c == 0) { a0 = a1 = P.pmlx[x]; } else if (c == 1) { a0 = py0; a1 = py1; } else { a0 = a1 = pzz; }
-      float d0, d1;
-      if constexpr (HOMOG) { d0 = d1 = P.dt_rho0_s; }
-      else { d0 = P.dt_rho0[r0 + x]; d1 = P.dt_rho0[r0 + Q.Nx + x]; }
-      float q0 = a0 * (a0 * rho[r0 + x] - d0 * v[j].x);
-      float q1 = a1 * (a1 * rho[r0 + Q.Nx + x] - d1 * v[j].y);
-      if constexpr (SRC != 0) { q0 += src[j].x; q1 += src[j].y; }
-      rho[r0 + x] = q0;
-      rho[r0 + Q.Nx + x] = q1;
-      if (c == 0) sum[j] = make_float2(q0, q1);
-      else { sum[j].x += q0; sum[j].y += q1; }     // (rho_x + rho_y) + rho_z
+      if (c == 1) { a0 = P.pmly[2 * m]; a1 = P.pmly[2 * m + 1]; } else { a0 = a1 = P.pmlz[z]; }
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int x = t + R * j;
+        if (c == 0) a0 = a1 = P.pmlx[x];
+        float d0, d1;
+        if constexpr (HOMOG) { d0 = d1 = P.dt_rho0_s; }
+        else { d0 = P.dt_rho0[r0 + x]; d1 = P.dt_rho0[r0 + N + x]; }
+        float q0 = a0 * (a0 * rb[x] - d0 * v[j].x);
+        float q1 = a1 * (a1 * rb[N + x] - d1 * v[j].y);
+        if constexpr (SRC != 0) { q0 += src[j].x; q1 += src[j].y; }
+        rho[r0 + x] = q0;
+        rho[r0 + N + x] = q1;
+        if (c == 0) sum[j] = make_float2(q0, q1);
+        else { sum[j].x += q0; sum[j].y += q1; }          // (rho_x + rho_y) + rho_z
+      }
+      if (c == 2) {
+        // equation of state, sensor reduction, forward transform of the new pressure
+        const int jz = z - P.pz, jy0 = 2 * m - P.py, jy1 = jy0 + 1;
+        const bool zin = (unsigned)jz < (unsigned)P.nz;
+        const bool in0 = zin && (unsigned)jy0 < (unsigned)P.ny, in1 = zin && (unsigned)jy1 < (unsigned)P.ny;
+        const long long s0 = ((long long)jz * P.ny + jy0) * P.nx - P.px, s1 = s0 + P.nx;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int x = t + R * j;
+          float c0, c1;
+          if constexpr (HOMOG) { c0 = c1 = P.c2_s; } else { c0 = P.c2[r0 + x]; c1 = P.c2[r0 + N + x]; }
+          const float p0 = c0 * sum[j].x, p1 = c1 * sum[j].y;
+          sum[j] = make_float2(p0, p1);
+          if (Q.store_p) { P.p[r0 + x] = p0; P.p[r0 + N + x] = p1; }
+          const bool xin = (unsigned)(x - P.px) < (unsigned)P.nx;
+          if (xin && in0) { P.pmax[s0 + x] = fmaxf(P.pmax[s0 + x], p0); P.pmin[s0 + x] = fminf(P.pmin[s0 + x], p0); }
+          if (xin && in1) { P.pmax[s1 + x] = fmaxf(P.pmax[s1 + x], p1); P.pmin[s1 + x] = fminf(P.pmin[s1 + x], p1); }
+        }
+        line_fft_sw<R, false>(sum, tw, zb, t);
+        float2* zo = Q.ZP + pair * N;
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
+      }
     }
+    __syncwarp();
+    issue(q + 2);
   }
-  const int jz = z - P.pz;
-  const int jy0 = 2 * m - P.py, jy1 = jy0 + 1;
-  const bool zin = (unsigned)jz < (unsigned)P.nz;
-  const bool in0 = zin && (unsigned)jy0 < (unsigned)P.ny, in1 = zin && (unsigned)jy1 < (unsigned)P.ny;
-  const long long s0 = ((long long)jz * P.ny + jy0) * P.nx - P.px, s1 = s0 + P.nx;
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    const int x = t + R * j;
-    float c0, c1;
-    if constexpr (HOMOG) { c0 = c1 = P.c2_s; } else { c0 = P.c2[r0 + x]; c1 = P.c2[r0 + Q.Nx + x]; }
-    const float p0 = c0 * sum[j].x, p1 = c1 * sum[j].y;
-    sum[j] = make_float2(p0, p1);
-    if (Q.store_p) { P.p[r0 + x] = p0; P.p[r0 + Q.Nx + x] = p1; }
-    const bool xin = (unsigned)(x - P.px) < (unsigned)P.nx;
-    if (xin && in0) { P.pmax[s0 + x] = fmaxf(P.pmax[s0 + x], p0); P.pmin[s0 + x] = fminf(P.pmin[s0 + x], p0); }
-    if (xin && in1) { P.pmax[s1 + x] = fmaxf(P.pmax[s1 + x], p1); P.pmin[s1 + x] = fminf(P.pmin[s1 + x], p1); }
-  }
-  line_fft<R, false>(sum, Q.twx, sm, t);
-#pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) Q.ZP[zoff + t + R * k1] = sum[k1];
+  cp_async_wait<0>();
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.step = *P.step + 1;
 }
 

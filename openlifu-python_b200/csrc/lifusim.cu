@@ -126,6 +126,11 @@ static int build_tables(lifu_sim* s) {
   P.kx2 = T + off_k2[0]; P.ky2 = T + off_k2[1]; P.kz2 = T + off_k2[2];
   P.pmlx = T + off_pml[0]; P.pmly = T + off_pml[1]; P.pmlz = T + off_pml[2];
   P.sgx = T + off_sg[0]; P.sgy = T + off_sg[1]; P.sgz = T + off_sg[2];
+  {
+    double smax = 0;
+    for (int a = 0; a < 3; ++a) { double arg = c * (M_PI / d[a]) * dt / 2.0; smax += arg * arg; }
+    P.poly_ok = smax <= 9.8 ? 1 : 0;
+  }
   s->tables_ready = true;
   return LIFU_OK;
 }
@@ -625,13 +630,19 @@ static int v2_setup(lifu_sim* s) {
 
 #define V2_DISPATCH_R(RVAL, CALL8, CALL16) do { if ((RVAL) == 8) { CALL8; } else { CALL16; } } while (0)
 
-template <int R> static void v2_launch_x_u(lifu_sim* s, int grid, size_t sm) {
-  if (s->homogeneous) k2_x_u<R, true><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
-  else k2_x_u<R, false><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+template <typename K> static void v2_launch_persistent(lifu_sim* s, K kernel, int max_grid, size_t sm) {
+  // persistent x kernels: 3 CTAs of 128 threads per SM, dynamic shared memory above the 48 KB default
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  int grid = std::min(max_grid, s->n_sm * 3);
+  kernel<<<grid, 128, sm, s->stream>>>(s->P, s->Q);
 }
-template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int grid, size_t sm) {
-  if (s->homogeneous) k2_x_rho_p<R, true, SRC><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
-  else k2_x_rho_p<R, false, SRC><<<grid, 256, sm, s->stream>>>(s->P, s->Q);
+template <int R> static void v2_launch_x_u(lifu_sim* s, int nbatch) {
+  if (s->homogeneous) v2_launch_persistent(s, k2_x_u<R, true>, nbatch, XStage<R>::SMEM);
+  else v2_launch_persistent(s, k2_x_u<R, false>, nbatch, XStage<R>::SMEM);
+}
+template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int nbatch) {
+  if (s->homogeneous) v2_launch_persistent(s, k2_x_rho_p<R, true, SRC>, nbatch, XStage<R>::SMEM);
+  else v2_launch_persistent(s, k2_x_rho_p<R, false, SRC>, nbatch, XStage<R>::SMEM);
 }
 
 static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
@@ -641,7 +652,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   const int tiles = Q.PH / 16;
   const size_t sm_y = sizeof(float2) * Ry * Ry * 16, sm_z = sizeof(float2) * Rz * Rz * 16;
   const size_t sm_x = sizeof(float2) * 256 * (Rx + 1);
-  const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (256 / Rx));
+  const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (128 / Rx));   // row-pair batches of the persistent x kernels
   int nk = 0;
   const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
   const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
@@ -649,14 +660,16 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   V2_DISPATCH_R(Ry, (k2_y_fwd<8, 0><<<dim3(tiles, Q.Nz, 1), 128, sm_y, st>>>(s->P, Q)),
                     (k2_y_fwd<16, 0><<<dim3(tiles, Q.Nz, 1), 256, sm_y, st>>>(s->P, Q)));
   ++nk; mark("k2_y_fwd_p", 8);
-  V2_DISPATCH_R(Rz, (k2_z_grad<8><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
-                    (k2_z_grad<16><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
+  if (s->P.poly_ok) V2_DISPATCH_R(Rz, (k2_z_grad<8, true><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
+                                      (k2_z_grad<16, true><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
+  else V2_DISPATCH_R(Rz, (k2_z_grad<8, false><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
+                         (k2_z_grad<16, false><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
   ++nk; mark("k2_z_grad", 12);
   V2_DISPATCH_R(Ry, (k2_y_inv_grad<8><<<dim3(tiles, Q.Nz), 128, sm_y, st>>>(s->P, Q)),
                     (k2_y_inv_grad<16><<<dim3(tiles, Q.Nz), 256, sm_y, st>>>(s->P, Q)));
   ++nk; mark("k2_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
-  V2_DISPATCH_R(Rx, (v2_launch_x_u<8>(s, gx, sm_x)), (v2_launch_x_u<16>(s, gx, sm_x)));
+  V2_DISPATCH_R(Rx, (v2_launch_x_u<8>(s, gx)), (v2_launch_x_u<16>(s, gx)));
   ++nk; mark("k2_x_u", s->homogeneous ? 48 : 60);
   V2_DISPATCH_R(Ry, (k2_y_fwd<8, 1><<<dim3(tiles, Q.Nz, 3), 128, sm_y, st>>>(s->P, Q)),
                     (k2_y_fwd<16, 1><<<dim3(tiles, Q.Nz, 3), 256, sm_y, st>>>(s->P, Q)));
@@ -676,16 +689,18 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   }
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src == 1 ? 4 : 3;
-  V2_DISPATCH_R(Rz, (k2_z_div<8><<<dim3(tiles, Q.Ny, ncomp), 128, sm_z, st>>>(s->P, Q, 0)),
-                    (k2_z_div<16><<<dim3(tiles, Q.Ny, ncomp), 256, sm_z, st>>>(s->P, Q, 0)));
+  if (s->P.poly_ok) V2_DISPATCH_R(Rz, (k2_z_div<8, true><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q, ncomp)),
+                                      (k2_z_div<16, true><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q, ncomp)));
+  else V2_DISPATCH_R(Rz, (k2_z_div<8, false><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q, ncomp)),
+                         (k2_z_div<16, false><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q, ncomp)));
   ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
   V2_DISPATCH_R(Ry, (k2_y_inv<8><<<dim3(tiles, Q.Nz, ncomp), 128, sm_y, st>>>(s->P, Q)),
                     (k2_y_inv<16><<<dim3(tiles, Q.Nz, ncomp), 256, sm_y, st>>>(s->P, Q)));
   ++nk; mark("k2_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
-  if (src == 0) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 0>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 0>(s, gx, sm_x)));
-  else if (src == 1) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 1>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 1>(s, gx, sm_x)));
-  else V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 2>(s, gx, sm_x)), (v2_launch_x_rho_p<16, 2>(s, gx, sm_x)));
+  if (src == 0) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 0>(s, gx)), (v2_launch_x_rho_p<16, 0>(s, gx)));
+  else if (src == 1) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 1>(s, gx)), (v2_launch_x_rho_p<16, 1>(s, gx)));
+  else V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 2>(s, gx)), (v2_launch_x_rho_p<16, 2>(s, gx)));
   ++nk;
   const double inner = (double)s->Vin / (double)s->V;
   mark("k2_x_rho_p", 12 + 24 + 16 * inner + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));

@@ -22,6 +22,43 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
 
+// sinc(sqrt(s)) and cos(sqrt(s)) as Taylor polynomials in s = (c_ref k dt/2)^2, valid (abs. error < 2e-7) for
+// s <= 9.8; the host checks the bound (StepParams::poly_ok) and the kernels fall back to sinf/cosf otherwise.
+__device__ __forceinline__ float sinc_sqrt_poly(float s) {
+  float r = -9.183689864e-29f;
+  r = fmaf(r, s, 6.446950284e-26f);
+  r = fmaf(r, s, -3.868170171e-23f);
+  r = fmaf(r, s, 1.957294106e-20f);
+  r = fmaf(r, s, -8.220635247e-18f);
+  r = fmaf(r, s, 2.811457254e-15f);
+  r = fmaf(r, s, -7.647163732e-13f);
+  r = fmaf(r, s, 1.605904384e-10f);
+  r = fmaf(r, s, -2.505210839e-08f);
+  r = fmaf(r, s, 2.755731922e-06f);
+  r = fmaf(r, s, -1.984126984e-04f);
+  r = fmaf(r, s, 8.333333333e-03f);
+  r = fmaf(r, s, -1.666666667e-01f);
+  r = fmaf(r, s, 1.000000000e+00f);
+  return r;
+}
+__device__ __forceinline__ float cos_sqrt_poly(float s) {
+  float r = -2.479596263e-27f;
+  r = fmaf(r, s, 1.611737571e-24f);
+  r = fmaf(r, s, -8.896791392e-22f);
+  r = fmaf(r, s, 4.110317623e-19f);
+  r = fmaf(r, s, -1.561920697e-16f);
+  r = fmaf(r, s, 4.779477332e-14f);
+  r = fmaf(r, s, -1.147074560e-11f);
+  r = fmaf(r, s, 2.087675699e-09f);
+  r = fmaf(r, s, -2.755731922e-07f);
+  r = fmaf(r, s, 2.480158730e-05f);
+  r = fmaf(r, s, -1.388888889e-03f);
+  r = fmaf(r, s, 4.166666667e-02f);
+  r = fmaf(r, s, -5.000000000e-01f);
+  r = fmaf(r, s, 1.000000000e+00f);
+  return r;
+}
+
 __device__ __forceinline__ float kappa_of(float a2) {
   // kappa = sinc(c_ref k dt / 2); a2 = (c_ref k dt / 2)^2 <= (cfl*pi*sqrt(3)/2)^2, no range issues
   float a = sqrtf(a2);
