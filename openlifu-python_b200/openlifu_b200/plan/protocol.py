@@ -1,0 +1,276 @@
+"""``Protocol.calc_solution``: per-focus beamform -> simulate -> stack -> scale -> aggregate -> analyze.
+
+Mirrors /root/reference/src/openlifu/plan/protocol.py (``Protocol:33``, ``beamform:129-132``,
+``check_target:207-224``, ``fix_pulse_mismatch:226-240``, ``calc_solution:242-398``): same
+attributes, keyword arguments, defaults, errors and returned triple
+``(Solution, aggregated Dataset, SolutionAnalysis)``.  ``run_simulation`` is bound at module level
+exactly like the reference (``protocol.py:24``) so it can be patched by name.
+
+What differs is the execution of the per-focus loop (``protocol.py:318-339``): the iterations are
+independent, so with several B200s visible the foci are sharded one simulation per GPU
+(focus i -> device i mod G, one worker thread per device; each device keeps its own solver handle,
+medium and source weights -- no data-path collective).  With one device, or when
+``run_simulation`` has been replaced (tests), the loop runs serially in the reference's order.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import math
+import os
+from concurrent.futures import ThreadPoolExecutor
+from copy import deepcopy
+from dataclasses import asdict, dataclass, field
+from datetime import datetime
+from enum import Enum
+from pathlib import Path
+from typing import Any, Dict, List, Tuple
+
+import numpy as np
+import pandas as pd
+
+from .. import bf, geo, seg, sim, xa, xdc
+from ..geo import Point
+from ..sim import kwave_if, run_simulation
+from ..util.checkgpu import gpu_available
+from ..xdc import Transducer
+from .param_constraint import ParameterConstraint
+from .solution import Solution, _Encoder
+from .solution_analysis import SolutionAnalysis, SolutionAnalysisOptions
+from .target_constraints import TargetConstraints
+
+OnPulseMismatchAction = Enum("OnPulseMismatchAction", ["ERROR", "ROUND", "ROUNDUP", "ROUNDDOWN"])
+
+
+def _visible_devices() -> int:
+    """Number of GPUs the foci may be sharded over (``LIFU_FOCI_GPUS`` caps it; 1 under torchrun,
+    where each rank owns one device)."""
+    if "LOCAL_RANK" in os.environ or "LIFU_DEVICE" in os.environ:
+        return 1
+    try:
+        from pynvml import nvmlDeviceGetCount, nvmlInit, nvmlShutdown
+        nvmlInit()
+        n = nvmlDeviceGetCount()
+        nvmlShutdown()
+    except Exception:  # noqa: BLE001
+        n = 1
+    cvd = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if cvd:
+        n = min(n, len([x for x in cvd.split(",") if x.strip()]))
+    cap = int(os.environ.get("LIFU_FOCI_GPUS", "0") or 0)
+    return max(1, min(n, cap) if cap > 0 else n)
+
+
+@dataclass
+class Protocol:
+    id: str = "protocol"
+    name: str = "Protocol"
+    description: str = ""
+    allowed_roles: List[str] = field(default_factory=list)
+    pulse: bf.Pulse = field(default_factory=bf.Pulse)
+    sequence: bf.Sequence = field(default_factory=bf.Sequence)
+    focal_pattern: bf.FocalPattern = field(default_factory=bf.focal_patterns.SinglePoint)
+    sim_setup: sim.SimSetup = field(default_factory=sim.SimSetup)
+    delay_method: bf.DelayMethod = field(default_factory=bf.delay_methods.Direct)
+    apod_method: bf.ApodizationMethod = field(default_factory=bf.apod_methods.Uniform)
+    seg_method: seg.SegmentationMethod = field(default_factory=seg.seg_methods.UniformWater)
+    param_constraints: dict = field(default_factory=dict)
+    target_constraints: List[TargetConstraints] = field(default_factory=list)
+    analysis_options: SolutionAnalysisOptions = field(default_factory=SolutionAnalysisOptions)
+    virtual_fit_options: Any = None      # virtual fit is out of scope here; the field is carried through untouched
+
+    def __post_init__(self):
+        self.logger = logging.getLogger(__name__)
+
+    # ------------------------------------------------------------------------------ (de)serialisation
+    @staticmethod
+    def from_dict(d: Dict[str, Any]) -> "Protocol":
+        d = dict(d)
+        d["pulse"] = bf.Pulse.from_dict(d.get("pulse", {}))
+        d["sequence"] = bf.Sequence.from_dict(d.get("sequence", {}))
+        d["focal_pattern"] = bf.FocalPattern.from_dict(d.get("focal_pattern", {"class": "SinglePoint"}))
+        d["sim_setup"] = sim.SimSetup.from_dict(d.get("sim_setup", {}))
+        d["delay_method"] = bf.DelayMethod.from_dict(d.get("delay_method", {"class": "Direct"}))
+        d["apod_method"] = bf.ApodizationMethod.from_dict(d.get("apod_method", {"class": "Uniform"}))
+        seg_d = dict(d.get("seg_method", {"class": "UniformWater"}))
+        if "materials" in d:
+            mats = d.pop("materials")
+            seg_d["materials"] = {k: (m if isinstance(m, seg.Material) else seg.Material.from_dict(m)) for k, m in mats.items()}
+        d["seg_method"] = seg.SegmentationMethod.from_dict(seg_d)
+        d["param_constraints"] = {k: (v if isinstance(v, ParameterConstraint) else ParameterConstraint.from_dict(v))
+                                  for k, v in d.get("param_constraints", {}).items()}
+        if "target_constraints" in d:
+            d["target_constraints"] = [t if isinstance(t, TargetConstraints) else TargetConstraints.from_dict(t)
+                                       for t in d["target_constraints"]]
+        d["analysis_options"] = SolutionAnalysisOptions.from_dict(d.get("analysis_options", {}))
+        return Protocol(**d)
+
+    def to_dict(self):
+        vf = self.virtual_fit_options
+        return {
+            "id": self.id,
+            "name": self.name,
+            "description": self.description,
+            "allowed_roles": self.allowed_roles,
+            "pulse": self.pulse.to_dict(),
+            "sequence": self.sequence.to_dict(),
+            "focal_pattern": self.focal_pattern.to_dict(),
+            "sim_setup": asdict(self.sim_setup),
+            "delay_method": self.delay_method.to_dict(),
+            "apod_method": self.apod_method.to_dict(),
+            "seg_method": self.seg_method.to_dict(),
+            "param_constraints": {k: pc.to_dict() for k, pc in self.param_constraints.items()},
+            "target_constraints": [tc.to_dict() for tc in self.target_constraints],
+            "virtual_fit_options": vf.to_dict() if hasattr(vf, "to_dict") else vf,
+            "analysis_options": self.analysis_options.to_dict(),
+        }
+
+    @staticmethod
+    def from_file(filename):
+        with open(filename) as f:
+            return Protocol.from_dict(json.load(f))
+
+    @staticmethod
+    def from_json(json_string: str) -> "Protocol":
+        return Protocol.from_dict(json.loads(json_string))
+
+    def to_json(self, compact: bool) -> str:
+        if compact:
+            return json.dumps(self.to_dict(), separators=(",", ":"), cls=_Encoder)
+        return json.dumps(self.to_dict(), indent=4, cls=_Encoder)
+
+    def to_file(self, filename: str):
+        Path(filename).parent.mkdir(parents=True, exist_ok=True)
+        Path(filename).write_text(self.to_json(compact=False))
+
+    def to_table(self) -> pd.DataFrame:
+        parts = [pd.DataFrame.from_records([{"Category": "", "Name": n, "Value": v, "Unit": ""}
+                                            for n, v in (("ID", self.id), ("Name", self.name), ("Description", self.description))])]
+
+        def add(category, sub):
+            sub = sub.copy()
+            sub.insert(0, "Category", category)
+            parts.append(sub)
+
+        for cat, obj in (("Pulse", self.pulse), ("Sequence", self.sequence), ("Focal Pattern", self.focal_pattern),
+                         ("Delay Method", self.delay_method), ("Apodization Method", self.apod_method),
+                         ("Segmentation Method", self.seg_method), ("Simulation Setup", self.sim_setup)):
+            add(cat, obj.to_table())
+        for tc in self.target_constraints:
+            add("Target Constraints", tc.to_table())
+        for pid, pc in self.param_constraints.items():
+            tp = pc.to_table()
+            tp["Value"] = tp["Value"].str.replace("value", pid)
+            add("Parameter Constraints", tp)
+        return pd.concat(parts, ignore_index=True)
+
+    # ------------------------------------------------------------------------------ planning
+    def beamform(self, arr: xdc.Transducer, target: geo.Point, params):
+        delays = self.delay_method.calc_delays(arr, target, params)
+        apod = self.apod_method.calc_apodization(arr, target, params)
+        return delays, apod
+
+    def check_target(self, target: Point):
+        if isinstance(target, list):
+            raise ValueError(f"Input target {target} not supposed to be a list!")
+        for tc in self.target_constraints:
+            if tc.dim in target.dims:
+                tc.check_bounds(target.get_position(dim=tc.dim, units=tc.units))
+
+    def fix_pulse_mismatch(self, on_pulse_mismatch: OnPulseMismatchAction, foci: List[Point]):
+        """Make ``sequence.pulse_count`` a multiple of the number of foci, in place."""
+        n = len(foci)
+        if on_pulse_mismatch is OnPulseMismatchAction.ERROR:
+            raise ValueError(f"Pulse Count {self.sequence.pulse_count} is not a multiple of the number of foci {n}")
+        ratio = self.sequence.pulse_count / n
+        rounder = {OnPulseMismatchAction.ROUND: round, OnPulseMismatchAction.ROUNDUP: math.ceil,
+                   OnPulseMismatchAction.ROUNDDOWN: math.floor}.get(on_pulse_mismatch)
+        if rounder is not None:
+            self.sequence.pulse_count = rounder(ratio) * n
+        self.logger.warning(f"Pulse Count {self.sequence.pulse_count} is not a multiple of the number of foci {n}."
+                            f"Rounding to {self.sequence.pulse_count}.")
+
+    def _simulate_foci(self, transducer, params, beams, cycles, sim_options, voltage, use_gpu):
+        """Run one simulation per focus.  Serial unless several GPUs are visible and the stock
+        ``run_simulation`` is in place; then focus i runs on device i mod G."""
+        def one(i):
+            delays, apod = beams[i]
+            ds, _ = run_simulation(arr=transducer, params=params, delays=delays, apod=apod, freq=self.pulse.frequency,
+                                   cycles=cycles, dt=sim_options.dt, t_end=sim_options.t_end, cfl=sim_options.cfl,
+                                   amplitude=self.pulse.amplitude * voltage, gpu=use_gpu)
+            return ds
+
+        n_dev = _visible_devices() if (use_gpu and run_simulation is kwave_if.run_simulation and len(beams) > 1) else 1
+        if n_dev <= 1:
+            return [one(i) for i in range(len(beams))]
+        results: list = [None] * len(beams)
+
+        def worker(dev):
+            with kwave_if.use_device(dev):
+                for i in range(dev, len(beams), n_dev):
+                    self.logger.info(f"Simulate focus {i} on GPU {dev}...")
+                    results[i] = one(i)
+
+        with ThreadPoolExecutor(max_workers=n_dev) as pool:
+            for f in [pool.submit(worker, d) for d in range(n_dev)]:
+                f.result()
+        return results
+
+    def calc_solution(self, target: Point, transducer: Transducer, volume=None, session=None, simulate: bool = True,
+                      scale: bool = True, sim_options: sim.SimSetup | None = None,
+                      analysis_options: SolutionAnalysisOptions | None = None,
+                      on_pulse_mismatch: OnPulseMismatchAction = OnPulseMismatchAction.ERROR,
+                      use_gpu: bool | None = None, voltage: float = 1.0) -> Tuple[Solution, Any, SolutionAnalysis]:
+        """Delays/apodizations per focus, simulated fields, scaling to the target pressure and
+        the beam analysis (reference semantics, protocol.py:242-398)."""
+        if use_gpu is None:
+            use_gpu = gpu_available()
+        sim_options = self.sim_setup if sim_options is None else sim_options
+        analysis_options = self.analysis_options if analysis_options is None else analysis_options
+        self.check_target(target)
+        params = sim_options.setup_sim_scene(self.seg_method, volume=volume)
+
+        foci: List[Point] = self.focal_pattern.get_targets(target)
+        simulation_cycles = np.min([np.round(self.pulse.duration * self.pulse.frequency), 20])
+        if (self.sequence.pulse_count % len(foci)) != 0:
+            self.fix_pulse_mismatch(on_pulse_mismatch, foci)
+
+        beams = []
+        for focus in foci:
+            self.logger.info(f"Beamform for focus {focus}...")
+            beams.append(self.beamform(arr=transducer, target=focus, params=params))
+        stacked = xa.Dataset()
+        if simulate:
+            outputs = self._simulate_foci(transducer, params, beams, simulation_cycles, sim_options, voltage, use_gpu)
+            stacked = xa.concat([o.assign_coords(focal_point_index=i) for i, o in enumerate(outputs)],
+                                dim="focal_point_index")
+
+        timestamp = datetime.now().strftime("%Y%m%d_%H%M%S_%f")
+        solution_id = timestamp if session is None else f"{session.id}_{timestamp}"
+        description = (f"A solution computed for the {self.name} protocol with transducer {transducer.name}"
+                       f" for target {target.id}."
+                       f" This solution was created for the session {session.id} for subject {session.subject_id}."
+                       if session is not None else "")
+        solution = Solution(id=solution_id, name=f"Solution {timestamp}", protocol_id=self.id, transducer=transducer,
+                            delays=np.stack([b[0] for b in beams], axis=0),
+                            apodizations=np.stack([b[1] for b in beams], axis=0), pulse=self.pulse, voltage=voltage,
+                            sequence=self.sequence, foci=foci, target=target, simulation_result=stacked, approved=False,
+                            description=description)
+        if scale:
+            if not simulate:
+                msg = f"Cannot scale solution {solution.id} if simulation is not enabled!"
+                self.logger.error(msg=msg)
+                raise ValueError(msg)
+            self.logger.info(f"Scaling solution {solution.id}...")
+            solution.scale(self.focal_pattern, analysis_options=analysis_options)
+
+        if not simulate:
+            return solution, None, None
+        # pressures: max over foci; intensity: mean over foci (protocol.py:382-392)
+        res = solution.simulation_result
+        aggregated = deepcopy(res).drop_dims("focal_point_index")
+        aggregated["p_min"] = res["p_min"].max(dim="focal_point_index", keep_attrs=True)
+        aggregated["p_max"] = res["p_max"].max(dim="focal_point_index", keep_attrs=True)
+        aggregated["intensity"] = res["intensity"].mean(dim="focal_point_index", keep_attrs=True)
+        analysis = solution.analyze(options=analysis_options, param_constraints=self.param_constraints)
+        return solution, aggregated, analysis

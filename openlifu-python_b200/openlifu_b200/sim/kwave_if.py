@@ -14,8 +14,10 @@ per params object.  Only ``(delays, apod)`` -- 2 x n_elements numbers -- go to t
 """
 from __future__ import annotations
 
+import contextlib
 import logging
 import os
+import threading
 import zlib
 from typing import List
 
@@ -27,7 +29,21 @@ from ..util.units import getunitconversion
 log = logging.getLogger(__name__)
 
 _SESSIONS: dict = {}
-_MAX_SESSIONS = 2
+_MAX_SESSIONS = 2          # cached solver handles per device
+_LOCK = threading.Lock()
+_TLS = threading.local()
+
+
+@contextlib.contextmanager
+def use_device(device: int):
+    """Pin ``run_simulation`` calls made by this thread to one GPU (foci sharding: one worker
+    thread per device).  Handles on distinct devices run concurrently."""
+    prev = getattr(_TLS, "device", None)
+    _TLS.device = int(device)
+    try:
+        yield
+    finally:
+        _TLS.device = prev
 
 
 def _same_units(objs, what):
@@ -51,6 +67,8 @@ def get_kgrid(coords, t_end=0, dt=0, sound_speed_ref=1500, cfl=0.5):
 
 
 def _device():
+    if getattr(_TLS, "device", None) is not None:
+        return _TLS.device
     if "LIFU_DEVICE" in os.environ:
         return int(os.environ["LIFU_DEVICE"])
     if "LOCAL_RANK" in os.environ:
@@ -77,18 +95,21 @@ class _Session:
 
 def _session(kg, device):
     key = (tuple(kg["N"]), tuple(kg["d"]), kg["dt"], kg["Nt"], device)
-    s = _SESSIONS.get(key)
-    if s is None:
-        while len(_SESSIONS) >= _MAX_SESSIONS:
-            _SESSIONS.pop(next(iter(_SESSIONS))).sim.close()
-        s = _SESSIONS[key] = _Session(key, kg, device)
+    with _LOCK:
+        s = _SESSIONS.get(key)
+        if s is None:
+            mine = [k for k in _SESSIONS if k[-1] == device]
+            while len(mine) >= _MAX_SESSIONS:
+                _SESSIONS.pop(mine.pop(0)).sim.close()
+            s = _SESSIONS[key] = _Session(key, kg, device)
     return s
 
 
 def clear_sessions():
     """Release every cached solver handle (GPU memory, FFT plans)."""
-    while _SESSIONS:
-        _SESSIONS.popitem()[1].sim.close()
+    with _LOCK:
+        while _SESSIONS:
+            _SESSIONS.popitem()[1].sim.close()
 
 
 def element_geometry(arr, translation_m):

@@ -739,8 +739,36 @@ if not HAVE_XARRAY:
             return None
 
         def to_netcdf(self, path=None, engine=None, **kw):
-            raise ImportError("writing netCDF needs xarray with the 'h5netcdf' or 'scipy' backend, which is not "
-                              "installed; use openlifu_b200.io_npz.save_dataset for a dependency-free container")
+            """NetCDF-3 (classic) container through ``scipy.io.netcdf_file`` -- what
+            ``engine='scipy'`` writes in xarray.  There is no HDF5 writer in this image, so
+            ``engine='h5netcdf'`` (solution.py:515) also lands in the classic format; real
+            xarray reads either transparently."""
+            from scipy.io import netcdf_file
+            f = netcdf_file(path, "w", version=2)
+            try:
+                for d, n in self.sizes.items():
+                    f.createDimension(d, int(n))
+
+                def put(name, da):
+                    data = np.asarray(da.data)
+                    if data.dtype == np.bool_:
+                        data = data.astype(np.int8)
+                    if data.dtype == np.int64:
+                        data = data.astype(np.int32) if np.all(np.abs(data) < 2 ** 31) else data.astype(np.float64)
+                    v = f.createVariable(name, data.dtype, tuple(da.dims))
+                    v[...] = data
+                    for k, a in da.attrs.items():
+                        if isinstance(a, (str, int, float, np.integer, np.floating)):
+                            setattr(v, k, a)
+                for k, c in self._coords._vars.items():
+                    put(k, c)
+                for k, v in self._vars.items():
+                    put(k, v)
+                for k, a in self.attrs.items():
+                    if isinstance(a, (str, int, float)):
+                        setattr(f, k, a)
+            finally:
+                f.close()
 
     def concat(objs: Iterable, dim: str):
         objs = list(objs)
@@ -772,5 +800,29 @@ if not HAVE_XARRAY:
         out._coords._vars[dim] = DataArray(np.asarray(labels), dims=(dim,), name=dim, _plain=True)
         return out
 
-    def open_dataset(*a, **k):
-        raise ImportError("reading netCDF needs xarray, which is not installed")
+    def open_dataset(filename_or_obj, engine=None, **k):
+        """Read a NetCDF-3 file (path or bytes) written by ``Dataset.to_netcdf``."""
+        import io
+        from scipy.io import netcdf_file
+        src = io.BytesIO(filename_or_obj) if isinstance(filename_or_obj, (bytes, bytearray)) else str(filename_or_obj)
+        f = netcdf_file(src, "r", mmap=False)
+        try:
+            def attrs_of(v):
+                out = {}
+                for k2, a in v._attributes.items():
+                    out[k2] = a.decode() if isinstance(a, bytes) else (a.item() if isinstance(a, np.ndarray) and a.size == 1 else a)
+                return out
+            coords, data = {}, {}
+            for name, v in f.variables.items():
+                arr = np.array(v[...])
+                if arr.dtype.byteorder == ">":
+                    arr = arr.astype(arr.dtype.newbyteorder("="))
+                da = DataArray(arr, dims=tuple(v.dimensions), name=name, attrs=attrs_of(v), _plain=True)
+                (coords if (len(v.dimensions) == 1 and v.dimensions[0] == name) else data)[name] = da
+            ds = Dataset(coords=coords)
+            for name, da in data.items():
+                ds[name] = DataArray(da.data, coords={d: coords[d] for d in da.dims if d in coords}, dims=da.dims, name=name,
+                                     attrs=da.attrs)
+            return ds
+        finally:
+            f.close()
