@@ -101,12 +101,16 @@ struct SourceParams {
 // Per-pipeline parameters (device pointers owned by the handle).
 struct V2Params {
   int Nx, Ny, Nz, Nxh, PH;          // PH = row pitch of the H layout (multiple of 16)
+  int nxt;                          // regular 16-lane kx tiles of the strided passes (Nx/32); tile nxt = Nyquist column
+  int Ry;                           // radix of the y axis: rows y and y+Ry form a packed row pair
   long long HS;                     // stride between batched H fields  (Nz*Ny*PH)
   long long ZS;                     // stride between batched Z fields  (Nz*(Ny/2)*Nx)
-  const float2 *twx, *twy, *twz;    // inter-stage twiddles exp(-2 pi i m / N), m = 0..N-1, per axis
+  const float4 *tw4x, *tw4y, *tw4z; // (w, i w), w = exp(-2 pi i m / N), m = 0..N (entry N = entry 0), per axis
+  const float4 *dpy4, *dny4, *dpz4, *dnz4;   // derivative multipliers i k e^{+-i k d/2} as (m, i m)
   float2* ZP;                       // x-spectrum of the pressure (row pairs)
   float2* Z4;                       // [4][ZS] packed spectra (gradients, then velocity, then divergence + source)
   float2* H4;                       // [4][HS] half spectra
+  float2* pm;                       // [Nz][Ny][Nx] running (p_max, p_min) on the expanded grid
   float norm;                       // 1 / (2 * Nx*Ny*Nz): FFT normalisation and the row-pair split factor
   // source slab (planes z0s .. z0s+nzs-1 of the expanded grid)
   int z0s, nzs;

@@ -4,6 +4,11 @@
 // What this replaces: the 10-12 cuFFT 3-D transforms + 5 element-wise kernels of pipeline v1, i.e. the
 // per-step body of kspaceFirstOrder3D reached from /root/reference/src/openlifu/sim/kwave_if.py:124-129.
 //
+// Arithmetic.  The passes are instruction-issue bound as much as HBM bound (ncu, profiles/r1_v2_*), so
+// all complex arithmetic uses the sm_100 packed-FP32 pipe: one FADD2 / FMUL2 / FFMA2 works on a whole
+// complex number (register pair).  A 16-point register DFT is 68 packed instructions instead of ~205
+// scalar ones; twiddles are stored as (w, i*w) pairs so a complex multiply is FMUL2 + FFMA2.
+//
 // Transform structure.  A length-N line (N = R*R, R in {8, 16}) is transformed by R threads:
 // thread t holds x[t + R*j] (j = 0..R-1) in registers, does a register DFT of size R over j, multiplies
 // the inter-stage twiddle w_N^(t*k2), exchanges through shared memory, and does a second register DFT
@@ -12,11 +17,17 @@
 //
 // Layouts (float2 = complex):
 //   real field   R[z][y][x]                                       (x fastest)
-//   Z layout     Z[z][m][kx], m = y/2, kx = 0..Nx-1               x-spectrum of the ROW PAIR
-//                (row 2m) + i*(row 2m+1): two real lines share one complex transform
+//   Z layout     Z[z][m][kx], kx = 0..Nx-1                        x-spectrum of a ROW PAIR
+//                row(y_lo) + i*row(y_lo + Ry), m = (y_lo / 2Ry)*Ry + y_lo % Ry: the two rows of a pair
+//                are the ones that land in adjacent registers of ONE thread of the y pass, so splitting
+//                and merging pairs needs no shuffles
 //   H layout     H[z][ky][kx], kx = 0..Nx/2, row pitch PH         half spectrum
 // The x passes therefore are plain complex transforms; the y passes split (on load) or merge (on
 // store) the packed row pairs with the Hermitian pairing kx <-> Nx-kx.
+//
+// Tiles of the strided (y, z) passes: CTA = 16 lanes x R threads.  Lanes are 16 consecutive kx for the
+// Nx/32 regular tiles; the single Nyquist column kx = Nx/2 is handled by extra CTAs whose 16 lanes run
+// over the other in-plane index instead, so no lane is ever idle.
 //
 // Kernels (one time step, lossless medium):
 //   k2_y_fwd      Z -> H        split row pairs, [x-derivative multiplier], FFT_y, [y-derivative mult.]
@@ -35,24 +46,33 @@
 namespace lifu {
 
 // ------------------------------------------------------------------------------------------------
-// complex helpers
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul2(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// packed complex helpers (FADD2 / FMUL2 / FFMA2; operand swaps, broadcasts and whole-pair negation
+// are free operand modifiers in SASS)
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 cswap(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 cadd_i(float2 a, float2 b) { return __ffma2_rn(cswap(b), make_float2(-1.f, 1.f), a); }   // a + i b
+__device__ __forceinline__ float2 csub_i(float2 a, float2 b) { return __ffma2_rn(cswap(b), make_float2(1.f, -1.f), a); }   // a - i b
+__device__ __forceinline__ float2 cadd_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(1.f, -1.f), a); }      // a + conj b
+__device__ __forceinline__ float2 csub_conj(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, 1.f), a); }      // a - conj b
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return __fmul2_rn(cswap(a), make_float2(1.f, -1.f)); }             // -i a
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+__device__ __forceinline__ float2 cscale(float2 a, float s) { return __fmul2_rn(a, make_float2(s, s)); }
+// a * w, with w given together with i*w:  q = (w.x, w.y, -w.y, w.x)
+__device__ __forceinline__ float2 cmul4(float2 a, float4 q) {
+  return __ffma2_rn(make_float2(a.x, a.x), make_float2(q.x, q.y), __fmul2_rn(make_float2(a.y, a.y), make_float2(q.z, q.w)));
 }
-__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {   // a * conj(b)
-  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
-}
-__device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
+__device__ __forceinline__ float2 cmul2(float2 a, float2 b) { return cmul4(a, make_float4(b.x, b.y, -b.y, b.x)); }
+__device__ __forceinline__ float4 with_i(float2 w) { return make_float4(w.x, w.y, -w.y, w.x); }
 
 template <int N, bool INV>
-__device__ __forceinline__ float2 tw_const(int m) {   // exp(-+2 pi i m / N), N | 32
+__device__ __forceinline__ float2 cmul_const(float2 a, int m) {   // a * exp(-+2 pi i m / N), N | 32, m compile-time
   const int k = (m * (32 / N)) & 31;
-  return make_float2(w32_re(k), INV ? -w32_im(k) : w32_im(k));
+  const float wr = w32_re(k), wi = INV ? -w32_im(k) : w32_im(k);
+  return cmul4(a, make_float4(wr, wi, -wi, wr));
 }
 
-// Register DFT of size N (2, 4, 8, 16, 32), natural order in and out, unnormalised.
+// Register DFT of size N (2, 4, 8, 16), natural order in and out, unnormalised.
 template <int N, bool INV>
 __device__ __forceinline__ void dft(float2 (&x)[N]) {
   if constexpr (N == 2) {
@@ -64,13 +84,8 @@ __device__ __forceinline__ void dft(float2 (&x)[N]) {
     float2 s1 = cadd(x[1], x[3]), d1 = csub(x[1], x[3]);
     x[0] = cadd(s0, s1);
     x[2] = csub(s0, s1);
-    if constexpr (!INV) {          // X1 = d0 - i d1, X3 = d0 + i d1
-      x[1] = make_float2(d0.x + d1.y, d0.y - d1.x);
-      x[3] = make_float2(d0.x - d1.y, d0.y + d1.x);
-    } else {
-      x[1] = make_float2(d0.x - d1.y, d0.y + d1.x);
-      x[3] = make_float2(d0.x + d1.y, d0.y - d1.x);
-    }
+    if constexpr (!INV) { x[1] = csub_i(d0, d1); x[3] = cadd_i(d0, d1); }
+    else                { x[1] = cadd_i(d0, d1); x[3] = csub_i(d0, d1); }
   } else {
     constexpr int A = 4, B = N / 4;   // n = b + B*a, k = ka + A*kb
     float2 y[B][A];
@@ -81,7 +96,7 @@ __device__ __forceinline__ void dft(float2 (&x)[N]) {
       for (int a = 0; a < A; ++a) s[a] = x[b + B * a];
       dft<A, INV>(s);
 #pragma unroll
-      for (int ka = 0; ka < A; ++ka) y[b][ka] = (b * ka == 0) ? s[ka] : cmul2(s[ka], tw_const<N, INV>(b * ka));
+      for (int ka = 0; ka < A; ++ka) y[b][ka] = (b * ka == 0) ? s[ka] : cmul_const<N, INV>(s[ka], b * ka);
     }
 #pragma unroll
     for (int ka = 0; ka < A; ++ka) {
@@ -96,222 +111,217 @@ __device__ __forceinline__ void dft(float2 (&x)[N]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Strided-axis transforms (y and z passes).  CTA = 16 lanes (consecutive kx) x R threads per line.
-// Thread (l, t): l = tid & 15, t = tid >> 4.  Exchange buffer: R*R*16 float2.
+// Strided-axis transforms (y and z passes).  CTA = 16 lanes x R threads per line; thread (l, t):
+// l = tid & 15, t = tid >> 4.  `tw` is the shared-memory copy of the (w, i w) table with N + 1 entries
+// (entry N = entry 0, so the inverse can index N - m).  `sm` is one exchange buffer of N*16 float2;
+// callers alternate between two buffers, which makes a single barrier per transform sufficient.
 template <int R, bool INV>
-__device__ __forceinline__ void strided_fft(float2 (&v)[R], const float2* __restrict__ tw, float2* sm, int l, int t) {
+__device__ __forceinline__ void strided_fft(float2 (&v)[R], const float4* __restrict__ tw, float2* sm, int l, int t) {
   constexpr int N = R * R;
+  dft<R, INV>(v);
   if constexpr (!INV) {
-    dft<R, false>(v);                                   // over j -> k2
 #pragma unroll
-    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul2(v[k2], tw[(t * k2) & (N - 1)]);
+    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul4(v[k2], tw[t * k2]);
+    float2* w = sm + t * (R * 16) + l;
 #pragma unroll
-    for (int k2 = 0; k2 < R; ++k2) sm[(t * R + k2) * 16 + l] = v[k2];
+    for (int k2 = 0; k2 < R; ++k2) w[k2 * 16] = v[k2];
     __syncthreads();
+    const float2* r = sm + t * 16 + l;
 #pragma unroll
-    for (int tt = 0; tt < R; ++tt) v[tt] = sm[(tt * R + t) * 16 + l];   // this thread now owns k2 = t
-    __syncthreads();
-    dft<R, false>(v);                                   // over t -> k1 ; X[t + R*k1] = v[k1]
+    for (int tt = 0; tt < R; ++tt) v[tt] = r[tt * (R * 16)];      // this thread now owns k2 = t
   } else {
-    dft<R, true>(v);                                    // over k1 -> tt, for k2 = t
 #pragma unroll
-    for (int tt = 1; tt < R; ++tt) v[tt] = cmulc(v[tt], tw[(tt * t) & (N - 1)]);
+    for (int tt = 1; tt < R; ++tt) v[tt] = cmul4(v[tt], tw[N - tt * t]);
+    float2* w = sm + t * 16 + l;
 #pragma unroll
-    for (int tt = 0; tt < R; ++tt) sm[(tt * R + t) * 16 + l] = v[tt];
+    for (int tt = 0; tt < R; ++tt) w[tt * (R * 16)] = v[tt];
     __syncthreads();
+    const float2* r = sm + t * (R * 16) + l;
 #pragma unroll
-    for (int k2 = 0; k2 < R; ++k2) v[k2] = sm[(t * R + k2) * 16 + l];
+    for (int k2 = 0; k2 < R; ++k2) v[k2] = r[k2 * 16];
+  }
+  dft<R, INV>(v);
+}
+
+template <int R>
+struct Strided {
+  static constexpr int N = R * R;
+  static constexpr int THREADS = 16 * R;
+  static constexpr int XCH = N * 16 * 8;                       // bytes of one exchange buffer
+  static constexpr int TW = (N + 1) * 16;                      // bytes of the twiddle table
+  static constexpr int smem(int nbuf) { return nbuf * XCH + TW; }
+  static __device__ __forceinline__ const float4* load_tw(unsigned char* smraw, int nbuf, const float4* __restrict__ g) {
+    float4* s = reinterpret_cast<float4*>(smraw + nbuf * XCH);
+    for (int i = threadIdx.x; i <= N; i += THREADS) s[i] = g[i];
     __syncthreads();
-    dft<R, true>(v);                                    // over k2 -> j ; x[t + R*j] = v[j]
+    return s;
   }
+};
+
+// lane -> (kx, other index) of a strided-pass CTA; false when the CTA has no work.
+// grid.x = nxt regular tiles + 1 Nyquist slot; grid.y runs over the other index (regular) or its 16-blocks.
+__device__ __forceinline__ bool lane_map(const V2Params& Q, int n_other, int l, int& kx, int& o) {
+  if ((int)blockIdx.x < Q.nxt) { kx = blockIdx.x * 16 + l; o = blockIdx.y; return true; }
+  if ((int)blockIdx.y * 16 >= n_other) return false;
+  kx = Q.Nx >> 1;
+  o = blockIdx.y * 16 + l;
+  return true;
 }
 
-// Contiguous-axis transforms (x passes).  R consecutive lanes of a warp own one line; exchange region of
-// R*(R+1) float2 per line, warp-synchronous.
-template <int R, bool INV>
-__device__ __forceinline__ void line_fft(float2 (&v)[R], const float2* __restrict__ tw, float2* sm, int t) {
-  constexpr int N = R * R;
-  constexpr int P = R + 1;
-  if constexpr (!INV) {
-    dft<R, false>(v);
+// Merge the two rows of a pair (adjacent registers A = row y_lo, B = row y_lo + R) into the packed
+// x-spectrum: Z[kx] = A + iB, Z[Nx-kx] = conj(A) + i conj(B) = conj(A - iB).  Bins 0 and Nx/2 keep the
+// real parts only, as a C2R transform would.
+template <int R>
+__device__ __forceinline__ void merge_store(float2* __restrict__ zp, const float2 (&v)[R], int kx, int Nx, bool live) {
+  const bool selfm = (kx == 0) || (2 * kx == Nx);
+  const int km = Nx - kx;
+  const int qstep = R * Nx;
 #pragma unroll
-    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul2(v[k2], tw[(t * k2) & (N - 1)]);
-#pragma unroll
-    for (int k2 = 0; k2 < R; ++k2) sm[t * P + k2] = v[k2];
-    __syncwarp();
-#pragma unroll
-    for (int tt = 0; tt < R; ++tt) v[tt] = sm[tt * P + t];
-    __syncwarp();
-    dft<R, false>(v);
-  } else {
-    dft<R, true>(v);
-#pragma unroll
-    for (int tt = 1; tt < R; ++tt) v[tt] = cmulc(v[tt], tw[(tt * t) & (N - 1)]);
-#pragma unroll
-    for (int tt = 0; tt < R; ++tt) sm[tt * P + t] = v[tt];
-    __syncwarp();
-#pragma unroll
-    for (int k2 = 0; k2 < R; ++k2) v[k2] = sm[t * P + k2];
-    __syncwarp();
-    dft<R, true>(v);
-  }
-}
-
-__device__ __forceinline__ float2 shfl_xor16(float2 v) {
-  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, 16), __shfl_xor_sync(0xffffffffu, v.y, 16));
-}
-
-// Merge the row pair held by two adjacent half-warps (t even: row 2m, t odd: row 2m+1) into the packed
-// x-spectrum and store it: Z[kx] = A + iB, Z[Nx-kx] = conj(A) + i conj(B).  Bins 0 and Nx/2 keep real
-// parts only, as a C2R transform would.
-__device__ __forceinline__ void store_row_pair(float2* __restrict__ zline, float2 own, int t, int kx, int Nx, bool active) {
-  float2 other = shfl_xor16(own);
-  if (!active) return;
-  const bool self_mirror = (kx == 0) || (2 * kx == Nx);
-  if ((t & 1) == 0) {
-    float2 A = own, B = other;
-    zline[kx] = self_mirror ? make_float2(A.x, B.x) : make_float2(A.x - B.y, A.y + B.x);
-  } else if (!self_mirror) {
-    float2 A = other, B = own;
-    zline[Nx - kx] = make_float2(A.x + B.y, B.x - A.y);
+  for (int q = 0; q < R / 2; ++q) {
+    const float2 A = v[2 * q], B = v[2 * q + 1];
+    const float2 lo = selfm ? make_float2(A.x, B.x) : cadd_i(A, B);
+    if (live) zp[q * qstep + kx] = lo;
+    if (live && !selfm) zp[q * qstep + km] = cconj(csub_i(A, B));
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// y forward: packed row pairs -> half spectrum.  grid (PH/16, Nz, ncomp)
+// y forward: packed row pairs -> half spectrum.  grid (nxt+1, Nz | Nz/16.., ncomp)
 // MODE 0: pressure (no multipliers)   MODE 1: velocity (comp 0: i kx e^{-i kx dx/2}; comp 1: i ky e^{-i ky dy/2})
 // MODE 2: source slab (z index relative to the slab)
 template <int R, int MODE>
-__global__ void __launch_bounds__(16 * R) k2_y_fwd(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
+__global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, z = blockIdx.y, comp = blockIdx.z;
-  const bool active = kx < Q.Nxh;
+  const int comp = blockIdx.z;
+  const int nz = MODE == 2 ? Q.nzs : Q.Nz;
+  int kx, z;
+  if (!lane_map(Q, nz, l, kx, z)) return;
+  const bool live = z < nz;                       // only a slab's Nyquist tile can run past the end
+  const int zc = live ? z : nz - 1;
+  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
+  float2* xa = reinterpret_cast<float2*>(smraw);
   const float2* Zin = MODE == 0 ? Q.ZP : (MODE == 1 ? Q.Z4 + comp * Q.ZS : Q.ZSslab);
   float2* Hout = MODE == 2 ? Q.HSslab : Q.H4 + comp * Q.HS;
-  const long long zb = (long long)z * (Q.Ny / 2) * Q.Nx;
   const int km = (Q.Nx - kx) & (Q.Nx - 1);
+  const float2* zp = Zin + ((long long)zc * (Q.Ny / 2) + t) * Q.Nx;     // packed line m = q*R + t
+  const int qstep = R * Q.Nx;
   float2 v[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    float2 d = make_float2(0.f, 0.f), m = d;
-    if (active) {
-      const long long row = zb + (long long)((t >> 1) + (R / 2) * j) * Q.Nx;
-      d = Zin[row + kx];
-      m = Zin[row + km];
-    }
-    // 2A = Z[k] + conj Z[-k] ; 2B = -i (Z[k] - conj Z[-k])
-    v[j] = (t & 1) == 0 ? make_float2(d.x + m.x, d.y - m.y) : make_float2(d.y + m.y, m.x - d.x);
+  for (int q = 0; q < R / 2; ++q) {
+    const float2 d = zp[q * qstep + kx], m = zp[q * qstep + km];
+    v[2 * q] = cadd_conj(d, m);                  // 2A = Z[k] + conj Z[-k]          (row t + R*2q)
+    v[2 * q + 1] = cmul_mi(csub_conj(d, m));     // 2B = -i (Z[k] - conj Z[-k])     (row t + R*(2q+1))
   }
-  if (MODE == 1 && comp == 0 && active) {
-    const float2 mx = P.dnx[kx];
+  if (MODE == 1 && comp == 0) {
+    const float4 mx = with_i(P.dnx[kx]);
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = cmul2(v[j], mx);
+    for (int j = 0; j < R; ++j) v[j] = cmul4(v[j], mx);
   }
-  strided_fft<R, false>(v, Q.twy, smem, l, t);
-  if (active) {
-    const long long hb = (long long)z * Q.Ny * Q.PH + kx;
+  strided_fft<R, false>(v, tw, xa, l, t);
+  if (live) {
+    float2* hp = Hout + ((long long)z * Q.Ny + t) * Q.PH + kx;
+    const int kstep = R * Q.PH;
 #pragma unroll
     for (int k1 = 0; k1 < R; ++k1) {
-      const int ky = t + R * k1;
       float2 o = v[k1];
-      if (MODE == 1 && comp == 1) o = cmul2(o, P.dny[ky]);
-      Hout[hb + (long long)ky * Q.PH] = o;
+      if (MODE == 1 && comp == 1) o = cmul4(o, Q.dny4[t + R * k1]);
+      hp[k1 * kstep] = o;
     }
   }
 }
 
 // z pass of the pressure gradient: H4[0] -> H4[0] (kappa p^) and H4[1] (i kz e^{+i kz dz/2} kappa p^),
-// both already inverse transformed along z.  grid (PH/16, Ny)
+// both already inverse transformed along z.  grid (nxt+1, Ny)
 template <int R, bool POLY>
-__global__ void __launch_bounds__(16 * R) k2_z_grad(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
+__global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_grad(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, ky = blockIdx.y;
-  const bool active = kx < Q.Nxh;
-  const long long zs = (long long)Q.Ny * Q.PH;
-  const long long base = (long long)ky * Q.PH + kx;
-  float2 v[R];
+  int kx, ky;
+  if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
+  const int zs = Q.Ny * Q.PH, jstep = R * zs;
+  float2* hp = Q.H4 + (long long)t * zs + ky * Q.PH + kx;               // z = t + R*j
+  float2 v[R], w[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) v[j] = active ? Q.H4[base + (long long)(t + R * j) * zs] : make_float2(0.f, 0.f);
-  strided_fft<R, false>(v, Q.twz, smem, l, t);
-  float2 w[R];
-  const float axy = active ? P.ax2[kx] + P.ay2[ky] : 0.f;
+  for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
+  strided_fft<R, false>(v, tw, xa, l, t);
+  const float axy = P.ax2[kx] + P.ay2[ky];
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
     const int kz = t + R * k1;
     const float a2 = axy + P.az2[kz];
     const float kap = (POLY ? sinc_sqrt_poly(a2) : kappa_of(a2)) * Q.norm;
     v[k1] = cscale(v[k1], kap);
-    w[k1] = cmul2(v[k1], P.dpz[kz]);
+    w[k1] = cmul4(v[k1], Q.dpz4[kz]);
   }
-  strided_fft<R, true>(v, Q.twz, smem, l, t);
-  if (active) {
+  strided_fft<R, true>(v, tw, xb, l, t);
 #pragma unroll
-    for (int j = 0; j < R; ++j) Q.H4[base + (long long)(t + R * j) * zs] = v[j];
-  }
-  strided_fft<R, true>(w, Q.twz, smem, l, t);
-  if (active) {
+  for (int j = 0; j < R; ++j) hp[j * jstep] = v[j];
+  strided_fft<R, true>(w, tw, xa, l, t);
+  float2* hq = hp + Q.HS;
 #pragma unroll
-    for (int j = 0; j < R; ++j) Q.H4[Q.HS + base + (long long)(t + R * j) * zs] = w[j];
-  }
+  for (int j = 0; j < R; ++j) hq[j * jstep] = w[j];
 }
 
-// y inverse of the three gradient components + row-pair merge.  grid (PH/16, Nz)
+// y inverse of the three gradient components + row-pair merge.  grid (nxt+1, Nz)
 //   Z4[0] <- i kx e^{+i kx dx/2} * IFFT_y[H4[0]]     (d/dx)
 //   Z4[1] <-                      IFFT_y[i ky e^{+i ky dy/2} H4[0]]   (d/dy)
 //   Z4[2] <-                      IFFT_y[H4[1]]                      (d/dz)
 template <int R>
-__global__ void __launch_bounds__(16 * R) k2_y_inv_grad(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
+__global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_y_inv_grad(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, z = blockIdx.y;
-  const bool active = kx < Q.Nxh;
-  const long long hb = (long long)z * Q.Ny * Q.PH + kx;
-  const long long zb = (long long)z * (Q.Ny / 2) * Q.Nx;
+  int kx, z;
+  if (!lane_map(Q, Q.Nz, l, kx, z)) return;
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4y);
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
+  const float2* hp = Q.H4 + ((long long)z * Q.Ny + t) * Q.PH + kx;      // ky = t + R*k1
+  const int kstep = R * Q.PH;
+  float2* zp = Q.Z4 + ((long long)z * (Q.Ny / 2) + t) * Q.Nx;
   float2 a[R], c[R];
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
-    const int ky = t + R * k1;
-    a[k1] = active ? Q.H4[hb + (long long)ky * Q.PH] : make_float2(0.f, 0.f);
-    c[k1] = cmul2(a[k1], P.dpy[ky]);
+    a[k1] = hp[k1 * kstep];
+    c[k1] = cmul4(a[k1], Q.dpy4[t + R * k1]);
   }
-  strided_fft<R, true>(a, Q.twy, smem, l, t);
-  const float2 mx = active ? P.dpx[kx] : make_float2(0.f, 0.f);
+  strided_fft<R, true>(a, tw, xa, l, t);
+  const float4 mx = with_i(P.dpx[kx]);
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    float2* zl = Q.Z4 + zb + (long long)((t >> 1) + (R / 2) * j) * Q.Nx;
-    store_row_pair(zl, cmul2(a[j], mx), t, kx, Q.Nx, active);
-  }
-  strided_fft<R, true>(c, Q.twy, smem, l, t);
+  for (int j = 0; j < R; ++j) a[j] = cmul4(a[j], mx);
+  merge_store<R>(zp, a, kx, Q.Nx, true);
+  strided_fft<R, true>(c, tw, xb, l, t);
+  merge_store<R>(zp + Q.ZS, c, kx, Q.Nx, true);
+  const float2* hq = hp + Q.HS;
 #pragma unroll
-  for (int j = 0; j < R; ++j) {
-    float2* zl = Q.Z4 + Q.ZS + zb + (long long)((t >> 1) + (R / 2) * j) * Q.Nx;
-    store_row_pair(zl, c[j], t, kx, Q.Nx, active);
-  }
-#pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) a[k1] = active ? Q.H4[Q.HS + hb + (long long)(t + R * k1) * Q.PH] : make_float2(0.f, 0.f);
-  strided_fft<R, true>(a, Q.twy, smem, l, t);
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    float2* zl = Q.Z4 + 2 * Q.ZS + zb + (long long)((t >> 1) + (R / 2) * j) * Q.Nx;
-    store_row_pair(zl, a[j], t, kx, Q.Nx, active);
-  }
+  for (int k1 = 0; k1 < R; ++k1) a[k1] = hq[k1 * kstep];
+  strided_fft<R, true>(a, tw, xa, l, t);
+  merge_store<R>(zp + 2 * Q.ZS, a, kx, Q.Nx, true);
 }
 
 // z pass of the velocity divergence (comp 0..2, in place) and of the source field (comp 3).
-// grid (PH/16, Ny); the CTA walks the components so that kappa is evaluated once per (kx,ky,kz).
+// grid (nxt+1, Ny); the CTA walks the components so that kappa is evaluated once per (kx,ky,kz).
 // comp 2 additionally gets i kz e^{-i kz dz/2}; comp 3 reads the slab planes only and is filtered with
 // cos(c_ref k dt/2).
 template <int R, bool POLY>
-__global__ void __launch_bounds__(16 * R, 2) k2_z_div(StepParams P, V2Params Q, int ncomp) {
-  extern __shared__ float2 smem[];
+__global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_z_div(StepParams P, V2Params Q, int ncomp) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, ky = blockIdx.y;
-  const bool active = kx < Q.Nxh;
-  const long long zs = (long long)Q.Ny * Q.PH;
-  const long long base = (long long)ky * Q.PH + kx;
-  const float axy = active ? P.ax2[kx] + P.ay2[ky] : 0.f;
+  int kx, ky;
+  if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
+  const int zs = Q.Ny * Q.PH, jstep = R * zs;
+  const long long off = (long long)t * zs + ky * Q.PH + kx;
+  const float axy = P.ax2[kx] + P.ay2[ky];
   float kap[R];
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
@@ -320,25 +330,26 @@ __global__ void __launch_bounds__(16 * R, 2) k2_z_div(StepParams P, V2Params Q, 
   }
 #pragma unroll 1
   for (int comp = 0; comp < ncomp; ++comp) {
-    float2* H = Q.H4 + comp * Q.HS;
+    float2* hp = Q.H4 + comp * Q.HS + off;
     float2 v[R];
     if (comp < 3) {
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = active ? H[base + (long long)(t + R * j) * zs] : make_float2(0.f, 0.f);
+      for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
     } else {
+      const float2* sp = Q.HSslab + (long long)(t - Q.z0s) * zs + ky * Q.PH + kx;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int zr = t + R * j - Q.z0s;
-        v[j] = (active && zr >= 0 && zr < Q.nzs) ? Q.HSslab[base + (long long)zr * zs] : make_float2(0.f, 0.f);
+        v[j] = (zr >= 0 && zr < Q.nzs) ? sp[j * jstep] : make_float2(0.f, 0.f);
       }
     }
-    strided_fft<R, false>(v, Q.twz, smem, l, t);
+    strided_fft<R, false>(v, tw, xa, l, t);
     if (comp < 2) {
 #pragma unroll
       for (int k1 = 0; k1 < R; ++k1) v[k1] = cscale(v[k1], kap[k1]);
     } else if (comp == 2) {
 #pragma unroll
-      for (int k1 = 0; k1 < R; ++k1) v[k1] = cmul2(cscale(v[k1], kap[k1]), P.dnz[t + R * k1]);
+      for (int k1 = 0; k1 < R; ++k1) v[k1] = cmul4(cscale(v[k1], kap[k1]), Q.dnz4[t + R * k1]);
     } else {
 #pragma unroll
       for (int k1 = 0; k1 < R; ++k1) {
@@ -346,41 +357,39 @@ __global__ void __launch_bounds__(16 * R, 2) k2_z_div(StepParams P, V2Params Q, 
         v[k1] = cscale(v[k1], (POLY ? cos_sqrt_poly(a2) : cosf(sqrtf(a2))) * Q.norm);
       }
     }
-    strided_fft<R, true>(v, Q.twz, smem, l, t);
-    if (active) {
+    strided_fft<R, true>(v, tw, xb, l, t);
 #pragma unroll
-      for (int j = 0; j < R; ++j) H[base + (long long)(t + R * j) * zs] = v[j];
-    }
+    for (int j = 0; j < R; ++j) hp[j * jstep] = v[j];
   }
 }
 
-// y inverse + row-pair merge of H4[comp] -> Z4[comp].  grid (PH/16, Nz, ncomp)
+// y inverse + row-pair merge of H4[comp] -> Z4[comp].  grid (nxt+1, Nz, ncomp)
 template <int R>
-__global__ void __launch_bounds__(16 * R) k2_y_inv(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
+__global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_inv(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int kx = blockIdx.x * 16 + l, z = blockIdx.y, comp = blockIdx.z;
-  const bool active = kx < Q.Nxh;
-  const long long hb = (long long)z * Q.Ny * Q.PH + kx;
-  const long long zb = (long long)z * (Q.Ny / 2) * Q.Nx;
-  const float2* H = Q.H4 + comp * Q.HS;
+  const int comp = blockIdx.z;
+  int kx, z;
+  if (!lane_map(Q, Q.Nz, l, kx, z)) return;
+  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  const float2* hp = Q.H4 + comp * Q.HS + ((long long)z * Q.Ny + t) * Q.PH + kx;
+  const int kstep = R * Q.PH;
   float2 a[R];
 #pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) a[k1] = active ? H[hb + (long long)(t + R * k1) * Q.PH] : make_float2(0.f, 0.f);
-  strided_fft<R, true>(a, Q.twy, smem, l, t);
-#pragma unroll
-  for (int j = 0; j < R; ++j) {
-    float2* zl = Q.Z4 + comp * Q.ZS + zb + (long long)((t >> 1) + (R / 2) * j) * Q.Nx;
-    store_row_pair(zl, a[j], t, kx, Q.Nx, active);
-  }
+  for (int k1 = 0; k1 < R; ++k1) a[k1] = hp[k1 * kstep];
+  strided_fft<R, true>(a, tw, xa, l, t);
+  merge_store<R>(Q.Z4 + comp * Q.ZS + ((long long)z * (Q.Ny / 2) + t) * Q.Nx, a, kx, Q.Nx, true);
 }
 
 // ------------------------------------------------------------------------------------------------
 // x passes.  Persistent CTAs of 128 threads = 128/R groups of R lanes; a group owns one row pair at a
-// time and walks its work as a sequence of "items" (one packed spectrum line + one pair of real rows).
-// Items are prefetched two deep with cp.async into the group's private shared-memory stages, so the
-// memory latency of item q+1 overlaps the transforms of item q regardless of occupancy.  The FFT
-// exchange runs inside the (already consumed) spectrum stage with an XOR swizzle instead of padding.
+// time and walks its work as a sequence of "items" (one packed spectrum line + the pair of real rows,
+// or the pair of sensor rows).  Items are prefetched two deep with cp.async into the group's private
+// shared-memory stages, so the memory latency of item q+1 overlaps the transforms of item q regardless
+// of occupancy.  The FFT exchange runs inside the (already consumed) spectrum stage with an XOR swizzle
+// instead of padding.
 __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
@@ -390,59 +399,70 @@ template <int NPENDING>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPENDING) : "memory"); }
 
 template <int R, bool INV>
-__device__ __forceinline__ void line_fft_sw(float2 (&v)[R], const float2* __restrict__ tw, float2* sm, int t) {
+__device__ __forceinline__ void line_fft_sw(float2 (&v)[R], const float4* __restrict__ tw, float2* sm, int t) {
   constexpr int N = R * R;
+  dft<R, INV>(v);
   if constexpr (!INV) {
-    dft<R, false>(v);
 #pragma unroll
-    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul2(v[k2], tw[(t * k2) & (N - 1)]);
+    for (int k2 = 1; k2 < R; ++k2) v[k2] = cmul4(v[k2], tw[t * k2]);
 #pragma unroll
     for (int k2 = 0; k2 < R; ++k2) sm[t * R + (k2 ^ t)] = v[k2];
     __syncwarp();
 #pragma unroll
     for (int tt = 0; tt < R; ++tt) v[tt] = sm[tt * R + (t ^ tt)];
     __syncwarp();
-    dft<R, false>(v);
   } else {
-    dft<R, true>(v);
 #pragma unroll
-    for (int tt = 1; tt < R; ++tt) v[tt] = cmulc(v[tt], tw[(tt * t) & (N - 1)]);
+    for (int tt = 1; tt < R; ++tt) v[tt] = cmul4(v[tt], tw[N - tt * t]);
 #pragma unroll
     for (int tt = 0; tt < R; ++tt) sm[tt * R + (t ^ tt)] = v[tt];
     __syncwarp();
 #pragma unroll
     for (int k2 = 0; k2 < R; ++k2) v[k2] = sm[t * R + (k2 ^ t)];
     __syncwarp();
-    dft<R, true>(v);
   }
+  dft<R, INV>(v);
 }
 
-// One group's staging: stage s = [ N float2 spectrum line | 2N floats (row pair) ]
+// One group's staging: stage s = 16 N bytes = [ N float2 spectrum line | row lo (N floats) | row hi (N floats) ]
+// or [ sensor row lo (N float2) | sensor row hi (N float2) ]
 template <int R>
 struct XStage {
   static constexpr int N = R * R;
   static constexpr int BYTES = 16 * N;          // per stage
   static constexpr int GROUPS = 128 / R;
-  static constexpr int SMEM = GROUPS * 2 * BYTES + 8 * N;   // + twiddle table
+  static constexpr int SMEM = GROUPS * 2 * BYTES + 16 * (N + 1);   // + twiddle table
   // copy `bytes` (multiple of 16*R) from global to shared with the R lanes of the group
   static __device__ __forceinline__ void copy(char* sdst, const char* gsrc, int bytes, int t) {
 #pragma unroll
     for (int o = 0; o < 8 * N; o += 16 * R)
       if (o < bytes) cp_async16(sdst + o + 16 * t, gsrc + o + 16 * t);
   }
+  static __device__ __forceinline__ const float4* load_tw(unsigned char* smraw, const float4* __restrict__ g) {
+    float4* s = reinterpret_cast<float4*>(smraw + GROUPS * 2 * BYTES);
+    for (int i = threadIdx.x; i <= N; i += 128) s[i] = g[i];
+    __syncthreads();
+    return s;
+  }
 };
+
+// row pair m of plane z -> element offset of its lower row in a real field; the upper row is Ry rows further
+__device__ __forceinline__ long long pair_row_lo(const V2Params& Q, int z, int m) {
+  const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
+  return ((long long)z * Q.Ny + ylo) * Q.Nx;
+}
 
 template <int R, bool HOMOG>
 __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
   using XS = XStage<R>;
   constexpr int N = R * R, G = XS::GROUPS;
   extern __shared__ __align__(16) unsigned char smraw[];
-  float2* tw = reinterpret_cast<float2*>(smraw + G * 2 * XS::BYTES);
-  for (int i = threadIdx.x; i < N; i += 128) tw[i] = Q.twx[i];
-  __syncthreads();
+  const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
   char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
-  const long long nbatch = (long long)Q.Nz * (Q.Ny / 2) / G;
+  const int hy = Q.Ny / 2;
+  const long long hi = (long long)Q.Ry * N;                       // offset of the pair's upper row
+  const long long nbatch = (long long)Q.Nz * hy / G;
   const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long nitems = my_iters * 3;
 
@@ -450,10 +470,12 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
     if (q < nitems) {
       const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
       const int c = (int)(q % 3);
-      const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+      const int m = (int)(pair % hy), z = (int)(pair / hy);
+      const long long r0 = pair_row_lo(Q, z, m);
       char* st = gbase + (q & 1) * XS::BYTES;
       XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + pair * N), 8 * N, t);
-      XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + ((long long)z * Q.Ny + 2 * m) * N), 8 * N, t);
+      XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0), 4 * N, t);
+      XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0 + hi), 4 * N, t);
     }
     cp_async_commit();
   };
@@ -464,30 +486,31 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
     __syncwarp();
     const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
     const int c = (int)(q % 3);
-    const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+    const int m = (int)(pair % hy), z = (int)(pair / hy);
+    const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
     float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
     const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
-    const long long r0 = ((long long)z * Q.Ny + 2 * m) * N;
+    const long long r0 = ((long long)z * Q.Ny + ylo) * N;
     float2 v[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
     __syncwarp();
     line_fft_sw<R, true>(v, tw, zb, t);
-    float* u = P.u + c * P.RS;
-    float s0, s1;
-    if (c == 1) { s0 = P.sgy[2 * m]; s1 = P.sgy[2 * m + 1]; } else { s0 = s1 = P.sgz[z]; }
+    float* u = P.u + c * P.RS + r0;
+    float2 s;
+    if (c == 1) s = make_float2(P.sgy[ylo], P.sgy[ylo + Q.Ry]); else s.x = s.y = P.sgz[z];
 #pragma unroll
     for (int j = 0; j < R; ++j) {
       const int x = t + R * j;
-      if (c == 0) s0 = s1 = P.sgx[x];
-      float d0, d1;
-      if constexpr (HOMOG) { d0 = d1 = P.dt_rho0_sg_s; }
-      else { d0 = P.dt_rho0_sg[c * P.RS + r0 + x]; d1 = P.dt_rho0_sg[c * P.RS + r0 + N + x]; }
-      const float u0 = s0 * (s0 * rb[x] - d0 * v[j].x);
-      const float u1 = s1 * (s1 * rb[N + x] - d1 * v[j].y);
-      u[r0 + x] = u0;
-      u[r0 + N + x] = u1;
-      v[j] = make_float2(u0, u1);
+      if (c == 0) s.x = s.y = P.sgx[x];
+      float2 d;
+      if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_sg_s; }
+      else { d.x = -P.dt_rho0_sg[c * P.RS + r0 + x]; d.y = -P.dt_rho0_sg[c * P.RS + r0 + hi + x]; }
+      // u = s (s u - dt/rho0 dp)
+      const float2 un = __fmul2_rn(s, __ffma2_rn(d, v[j], __fmul2_rn(s, make_float2(rb[x], rb[N + x]))));
+      u[x] = un.x;
+      u[hi + x] = un.y;
+      v[j] = un;
     }
     line_fft_sw<R, false>(v, tw, zb, t);
     float2* zo = Q.Z4 + c * Q.ZS + pair * N;
@@ -500,31 +523,45 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
 }
 
 // SRC: 0 none, 1 filtered source in Z4[3], 2 unfiltered dense slab
+// Items per row pair: [source spectrum], rho_x, rho_y, rho_z, sensor rows (pm = interleaved (p_max, p_min)
+// on the expanded grid; rows in the PML are skipped).
 template <int R, bool HOMOG, int SRC>
 __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   using XS = XStage<R>;
   constexpr int N = R * R, G = XS::GROUPS;
-  constexpr int NI = SRC == 1 ? 4 : 3;                 // items per row pair: [source], rho_x, rho_y, rho_z
+  constexpr int NI = SRC == 1 ? 5 : 4;
+  constexpr int C0 = SRC == 1 ? 1 : 0;                  // item index of rho_x
   extern __shared__ __align__(16) unsigned char smraw[];
-  float2* tw = reinterpret_cast<float2*>(smraw + G * 2 * XS::BYTES);
-  for (int i = threadIdx.x; i < N; i += 128) tw[i] = Q.twx[i];
-  __syncthreads();
+  const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
   char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
-  const long long nbatch = (long long)Q.Nz * (Q.Ny / 2) / G;
+  const int hy = Q.Ny / 2;
+  const long long hi = (long long)Q.Ry * N;
+  const long long nbatch = (long long)Q.Nz * hy / G;
   const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long nitems = my_iters * NI;
 
   auto issue = [&](long long q) {
     if (q < nitems) {
       const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
-      const int it = (int)(q % NI);
-      const int c = SRC == 1 ? it - 1 : it;              // -1: the source item
-      const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+      const int c = (int)(q % NI) - C0;                   // -1: source item, 0..2: rho, 3: sensor rows
+      const int m = (int)(pair % hy), z = (int)(pair / hy);
+      const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
+      const long long r0 = ((long long)z * Q.Ny + ylo) * N;
       char* st = gbase + (q & 1) * XS::BYTES;
-      XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + pair * N), 8 * N, t);
-      if (c >= 0)
-        XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + ((long long)z * Q.Ny + 2 * m) * N), 8 * N, t);
+      if (c < 3) {
+        XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + pair * N), 8 * N, t);
+        if (c >= 0) {
+          XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0), 4 * N, t);
+          XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0 + hi), 4 * N, t);
+        }
+      } else {
+        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        if (zin && (unsigned)(ylo - P.py) < (unsigned)P.ny)
+          XS::copy(st, reinterpret_cast<const char*>(Q.pm + r0), 8 * N, t);
+        if (zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny)
+          XS::copy(st + 8 * N, reinterpret_cast<const char*>(Q.pm + r0 + hi), 8 * N, t);
+      }
     }
     cp_async_commit();
   };
@@ -535,70 +572,86 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
     cp_async_wait<1>();
     __syncwarp();
     const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
-    const int it = (int)(q % NI);
-    const int c = SRC == 1 ? it - 1 : it;
-    const int m = (int)(pair % (Q.Ny / 2)), z = (int)(pair / (Q.Ny / 2));
+    const int c = (int)(q % NI) - C0;
+    const int m = (int)(pair % hy), z = (int)(pair / hy);
+    const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
     float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
     const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
-    const long long r0 = ((long long)z * Q.Ny + 2 * m) * N;
-    float2 v[R];
+    const long long r0 = ((long long)z * Q.Ny + ylo) * N;
+    if (c < 3) {
+      float2 v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
-    __syncwarp();
-    line_fft_sw<R, true>(v, tw, zb, t);
-    if (c < 0) {
+      for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+      __syncwarp();
+      line_fft_sw<R, true>(v, tw, zb, t);
+      if (c < 0) {
 #pragma unroll
-      for (int j = 0; j < R; ++j) src[j] = v[j];
-    } else {
-      if (SRC == 2 && c == 0) {
-        const int zr = z - Q.z0s;
-        const bool in = zr >= 0 && zr < Q.nzs;
-        const long long so = ((long long)zr * Q.Ny + 2 * m) * N;
+        for (int j = 0; j < R; ++j) src[j] = v[j];
+      } else {
+        if (SRC == 2 && c == 0) {
+          const int zr = z - Q.z0s;
+          const bool in = zr >= 0 && zr < Q.nzs;
+          const long long so = ((long long)zr * Q.Ny + ylo) * N;
 #pragma unroll
-        for (int j = 0; j < R; ++j)
-          src[j] = in ? make_float2(Q.Sslab[so + t + R * j], Q.Sslab[so + N + t + R * j]) : make_float2(0.f, 0.f);
-      }
-      float* rho = P.rho + c * P.RS;
-      float a0, a1;
-      if (c == 1) { a0 = P.pmly[2 * m]; a1 = P.pmly[2 * m + 1]; } else { a0 = a1 = P.pmlz[z]; }
-#pragma unroll
-      for (int j = 0; j < R; ++j) {
-        const int x = t + R * j;
-        if (c == 0) a0 = a1 = P.pmlx[x];
-        float d0, d1;
-        if constexpr (HOMOG) { d0 = d1 = P.dt_rho0_s; }
-        else { d0 = P.dt_rho0[r0 + x]; d1 = P.dt_rho0[r0 + N + x]; }
-        float q0 = a0 * (a0 * rb[x] - d0 * v[j].x);
-        float q1 = a1 * (a1 * rb[N + x] - d1 * v[j].y);
-        if constexpr (SRC != 0) { q0 += src[j].x; q1 += src[j].y; }
-        rho[r0 + x] = q0;
-        rho[r0 + N + x] = q1;
-        if (c == 0) sum[j] = make_float2(q0, q1);
-        else { sum[j].x += q0; sum[j].y += q1; }          // (rho_x + rho_y) + rho_z
-      }
-      if (c == 2) {
-        // equation of state, sensor reduction, forward transform of the new pressure
-        const int jz = z - P.pz, jy0 = 2 * m - P.py, jy1 = jy0 + 1;
-        const bool zin = (unsigned)jz < (unsigned)P.nz;
-        const bool in0 = zin && (unsigned)jy0 < (unsigned)P.ny, in1 = zin && (unsigned)jy1 < (unsigned)P.ny;
-        const long long s0 = ((long long)jz * P.ny + jy0) * P.nx - P.px, s1 = s0 + P.nx;
+          for (int j = 0; j < R; ++j)
+            src[j] = in ? make_float2(Q.Sslab[so + t + R * j], Q.Sslab[so + hi + t + R * j]) : make_float2(0.f, 0.f);
+        }
+        float* rho = P.rho + c * P.RS + r0;
+        float2 a;
+        if (c == 1) a = make_float2(P.pmly[ylo], P.pmly[ylo + Q.Ry]); else a.x = a.y = P.pmlz[z];
 #pragma unroll
         for (int j = 0; j < R; ++j) {
           const int x = t + R * j;
-          float c0, c1;
-          if constexpr (HOMOG) { c0 = c1 = P.c2_s; } else { c0 = P.c2[r0 + x]; c1 = P.c2[r0 + N + x]; }
-          const float p0 = c0 * sum[j].x, p1 = c1 * sum[j].y;
-          sum[j] = make_float2(p0, p1);
-          if (Q.store_p) { P.p[r0 + x] = p0; P.p[r0 + N + x] = p1; }
-          const bool xin = (unsigned)(x - P.px) < (unsigned)P.nx;
-          if (xin && in0) { P.pmax[s0 + x] = fmaxf(P.pmax[s0 + x], p0); P.pmin[s0 + x] = fminf(P.pmin[s0 + x], p0); }
-          if (xin && in1) { P.pmax[s1 + x] = fmaxf(P.pmax[s1 + x], p1); P.pmin[s1 + x] = fminf(P.pmin[s1 + x], p1); }
+          if (c == 0) a.x = a.y = P.pmlx[x];
+          float2 d;
+          if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_s; }
+          else { d.x = -P.dt_rho0[r0 + x]; d.y = -P.dt_rho0[r0 + hi + x]; }
+          // rho = a (a rho - dt rho0 du) [+ S]
+          float2 rn = __fmul2_rn(a, __ffma2_rn(d, v[j], __fmul2_rn(a, make_float2(rb[x], rb[N + x]))));
+          if constexpr (SRC != 0) rn = cadd(rn, src[j]);
+          rho[x] = rn.x;
+          rho[hi + x] = rn.y;
+          sum[j] = c == 0 ? rn : cadd(sum[j], rn);           // (rho_x + rho_y) + rho_z
         }
-        line_fft_sw<R, false>(sum, tw, zb, t);
-        float2* zo = Q.ZP + pair * N;
+        if (c == 2) {
+          // equation of state; the sensor item that follows consumes p from `sum`
 #pragma unroll
-        for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
+          for (int j = 0; j < R; ++j) {
+            const int x = t + R * j;
+            float2 c2;
+            if constexpr (HOMOG) { c2.x = c2.y = P.c2_s; } else { c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
+            sum[j] = __fmul2_rn(c2, sum[j]);
+            if (Q.store_p) { P.p[r0 + x] = sum[j].x; P.p[r0 + hi + x] = sum[j].y; }
+          }
+        }
       }
+    } else {
+      // running max / min on the two sensor rows, then the forward transform of the new pressure
+      const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+      const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
+      const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
+      float2* pmg = Q.pm + r0;
+      if (in0) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int x = t + R * j;
+          const float2 o = zb[x];
+          pmg[x] = make_float2(fmaxf(o.x, sum[j].x), fminf(o.y, sum[j].x));
+        }
+      }
+      if (in1) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int x = t + R * j;
+          const float2 o = zb[N + x];
+          pmg[hi + x] = make_float2(fmaxf(o.x, sum[j].y), fminf(o.y, sum[j].y));
+        }
+      }
+      __syncwarp();
+      line_fft_sw<R, false>(sum, tw, zb, t);
+      float2* zo = Q.ZP + pair * N;
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
     }
     __syncwarp();
     issue(q + 2);
@@ -607,22 +660,27 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.step = *P.step + 1;
 }
 
-// x forward of the dense source slab (row pairs).  grid = nzs*(Ny/2)/G
+// x forward of the dense source slab (row pairs).  grid = ceil(nzs*(Ny/2)/G), G = 256/R
 template <int R>
 __global__ void __launch_bounds__(256) k2_x_src(StepParams P, V2Params Q) {
-  extern __shared__ float2 smem[];
-  constexpr int G = 256 / R;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int G = 256 / R, N = R * R;
+  float4* tws = reinterpret_cast<float4*>(smraw + G * N * 8);
+  for (int i = threadIdx.x; i <= N; i += 256) tws[i] = Q.tw4x[i];
+  __syncthreads();
   const int g = threadIdx.x / R, t = threadIdx.x % R;
-  float2* sm = smem + g * R * (R + 1);
+  float2* sm = reinterpret_cast<float2*>(smraw) + g * N;
+  const int hy = Q.Ny / 2;
   const long long pair = (long long)blockIdx.x * G + g;          // zr*(Ny/2) + m
-  if (pair >= (long long)Q.nzs * (Q.Ny / 2)) return;
-  const long long r0 = pair * 2 * Q.Nx;
+  if (pair >= (long long)Q.nzs * hy) return;
+  const int m = (int)(pair % hy), zr = (int)(pair / hy);
+  const long long r0 = pair_row_lo(Q, zr, m), hi = (long long)Q.Ry * N;
   float2 v[R];
 #pragma unroll
-  for (int j = 0; j < R; ++j) v[j] = make_float2(Q.Sslab[r0 + t + R * j], Q.Sslab[r0 + Q.Nx + t + R * j]);
-  line_fft<R, false>(v, Q.twx, sm, t);
+  for (int j = 0; j < R; ++j) v[j] = make_float2(Q.Sslab[r0 + t + R * j], Q.Sslab[r0 + hi + t + R * j]);
+  line_fft_sw<R, false>(v, tws, sm, t);
 #pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) Q.ZSslab[pair * Q.Nx + t + R * k1] = v[k1];
+  for (int k1 = 0; k1 < R; ++k1) Q.ZSslab[pair * N + t + R * k1] = v[k1];
 }
 
 // Source scatter into the dense slab (same arithmetic as k_source_scatter of v1).
@@ -638,6 +696,23 @@ __global__ void __launch_bounds__(128) k2_source_scatter(StepParams P, V2Params 
       if (tt >= 0 && tt < S.n_base) acc = fmaf(S.w[j] * S.gain[e], S.base[tt], acc);
     }
     Q.Sslab[S.lin_exp[i] - slab0] = acc * S.scale[i];
+  }
+}
+
+// sensor field helpers: pm = interleaved (p_max, p_min) on the expanded grid
+__global__ void k2_pm_init(float2* pm, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    pm[i] = make_float2(-INFINITY, INFINITY);
+}
+__global__ void k2_pm_crop(StepParams P, V2Params Q) {
+  const long long n = (long long)P.nx * P.ny * P.nz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % P.nx);
+    const long long r = i / P.nx;
+    const int y = (int)(r % P.ny), z = (int)(r / P.ny);
+    const float2 v = Q.pm[((long long)(z + P.pz) * P.Ny + (y + P.py)) * P.Nx + (x + P.px)];
+    P.pmax[i] = v.x;
+    P.pmin[i] = v.y;
   }
 }
 

@@ -584,25 +584,49 @@ static int v2_setup(lifu_sim* s) {
   if (!s->v2_ready) {
     Q.Nx = s->N[0]; Q.Ny = s->N[1]; Q.Nz = s->N[2]; Q.Nxh = s->Nxh;
     Q.PH = (int)round_up(s->Nxh, 16);
+    Q.nxt = s->N[0] / 32;
     Q.HS = (long long)Q.Nz * Q.Ny * Q.PH;
     Q.ZS = (long long)Q.Nz * (Q.Ny / 2) * Q.Nx;
     Q.norm = (float)(1.0 / (2.0 * (double)s->V));
     for (int a = 0; a < 3; ++a) {
       s->R[a] = radix_of(s->N[a]);
       const int n = s->N[a];
-      std::vector<float2> tw(n);
-      for (int m = 0; m < n; ++m) {
-        double ang = -2.0 * M_PI * (double)m / (double)n;
-        tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      std::vector<float4> tw(n + 1);
+      for (int m = 0; m <= n; ++m) {
+        double ang = -2.0 * M_PI * (double)(m % n) / (double)n;
+        float c = (float)std::cos(ang), sn = (float)std::sin(ang);
+        tw[m] = make_float4(c, sn, -sn, c);                          // (w, i w)
       }
-      LIFU_CHECK(dev_alloc(s, (void**)&s->d_tw[a], sizeof(float2) * n));
-      LIFU_CUDA(cudaMemcpyAsync(s->d_tw[a], tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_tw[a], sizeof(float4) * (n + 1)));
+      LIFU_CUDA(cudaMemcpyAsync(s->d_tw[a], tw.data(), sizeof(float4) * (n + 1), cudaMemcpyHostToDevice, s->stream));
       LIFU_CUDA(cudaStreamSynchronize(s->stream));
     }
-    Q.twx = s->d_tw[0]; Q.twy = s->d_tw[1]; Q.twz = s->d_tw[2];
+    Q.Ry = s->R[1];
+    Q.tw4x = s->d_tw[0]; Q.tw4y = s->d_tw[1]; Q.tw4z = s->d_tw[2];
+    {
+      // derivative multipliers i k e^{+-i k d/2} of the y and z axes as (m, i m) pairs
+      const int Ny = s->N[1], Nz = s->N[2];
+      std::vector<float4> mul(2 * Ny + 2 * Nz);
+      auto fill = [&](float4* dst, int n, double d, double sign) {
+        for (int i = 0; i < n; ++i) {
+          double k = k_fft(n, d, i);
+          float re = (float)(-sign * k * std::sin(k * d / 2.0)), im = (float)(k * std::cos(k * d / 2.0));
+          dst[i] = make_float4(re, im, -im, re);
+        }
+      };
+      fill(mul.data(), Ny, s->grid.d[1], +1.0);
+      fill(mul.data() + Ny, Ny, s->grid.d[1], -1.0);
+      fill(mul.data() + 2 * Ny, Nz, s->grid.d[2], +1.0);
+      fill(mul.data() + 2 * Ny + Nz, Nz, s->grid.d[2], -1.0);
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_mul4, sizeof(float4) * mul.size()));
+      LIFU_CUDA(cudaMemcpyAsync(s->d_mul4, mul.data(), sizeof(float4) * mul.size(), cudaMemcpyHostToDevice, s->stream));
+      LIFU_CUDA(cudaStreamSynchronize(s->stream));
+      Q.dpy4 = s->d_mul4; Q.dny4 = s->d_mul4 + Ny; Q.dpz4 = s->d_mul4 + 2 * Ny; Q.dnz4 = s->d_mul4 + 2 * Ny + Nz;
+    }
     LIFU_CHECK(dev_alloc(s, (void**)&Q.ZP, sizeof(float2) * Q.ZS));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.Z4, sizeof(float2) * 4 * Q.ZS));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.H4, sizeof(float2) * 4 * Q.HS));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.pm, sizeof(float2) * s->V));
     s->v2_ready = true;
   }
   // source slab: z range of the mask (indices are sorted, x fastest, so first/last give min/max z)
@@ -628,51 +652,47 @@ static int v2_setup(lifu_sim* s) {
   return LIFU_OK;
 }
 
-#define V2_DISPATCH_R(RVAL, CALL8, CALL16) do { if ((RVAL) == 8) { CALL8; } else { CALL16; } } while (0)
-
-template <typename K> static void v2_launch_persistent(lifu_sim* s, K kernel, int max_grid, size_t sm) {
-  // persistent x kernels: 3 CTAs of 128 threads per SM, dynamic shared memory above the 48 KB default
+// launch helpers: every v2 kernel uses dynamic shared memory above the 48 KB default
+template <typename K, typename... Args>
+static void v2_launch(K kernel, dim3 grid, int threads, size_t sm, cudaStream_t st, Args... args) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  int grid = std::min(max_grid, s->n_sm * 3);
-  kernel<<<grid, 128, sm, s->stream>>>(s->P, s->Q);
+  kernel<<<grid, threads, sm, st>>>(args...);
 }
+#define V2_R(RVAL, EXPR) do { if ((RVAL) == 8) { constexpr int RR = 8; EXPR; } else { constexpr int RR = 16; EXPR; } } while (0)
+
 template <int R> static void v2_launch_x_u(lifu_sim* s, int nbatch) {
-  if (s->homogeneous) v2_launch_persistent(s, k2_x_u<R, true>, nbatch, XStage<R>::SMEM);
-  else v2_launch_persistent(s, k2_x_u<R, false>, nbatch, XStage<R>::SMEM);
+  dim3 grid(std::min(nbatch, s->n_sm * 3));
+  if (s->homogeneous) v2_launch(k2_x_u<R, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  else v2_launch(k2_x_u<R, false>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
 }
 template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int nbatch) {
-  if (s->homogeneous) v2_launch_persistent(s, k2_x_rho_p<R, true, SRC>, nbatch, XStage<R>::SMEM);
-  else v2_launch_persistent(s, k2_x_rho_p<R, false, SRC>, nbatch, XStage<R>::SMEM);
+  dim3 grid(std::min(nbatch, s->n_sm * 3));
+  if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  else v2_launch(k2_x_rho_p<R, false, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
 }
 
 static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
   const V2Params& Q = s->Q;
   cudaStream_t st = s->stream;
   const int Rx = s->R[0], Ry = s->R[1], Rz = s->R[2];
-  const int tiles = Q.PH / 16;
-  const size_t sm_y = sizeof(float2) * Ry * Ry * 16, sm_z = sizeof(float2) * Rz * Rz * 16;
-  const size_t sm_x = sizeof(float2) * 256 * (Rx + 1);
+  const unsigned tx = Q.nxt + 1;                                   // regular kx tiles + the Nyquist slot
   const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (128 / Rx));   // row-pair batches of the persistent x kernels
   int nk = 0;
   const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
   const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
+  const bool poly = s->P.poly_ok != 0;
   // (1) pressure gradient
-  V2_DISPATCH_R(Ry, (k2_y_fwd<8, 0><<<dim3(tiles, Q.Nz, 1), 128, sm_y, st>>>(s->P, Q)),
-                    (k2_y_fwd<16, 0><<<dim3(tiles, Q.Nz, 1), 256, sm_y, st>>>(s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 0>, dim3(tx, Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_p", 8);
-  if (s->P.poly_ok) V2_DISPATCH_R(Rz, (k2_z_grad<8, true><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
-                                      (k2_z_grad<16, true><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
-  else V2_DISPATCH_R(Rz, (k2_z_grad<8, false><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q)),
-                         (k2_z_grad<16, false><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q)));
+  if (poly) V2_R(Rz, (v2_launch(k2_z_grad<RR, true>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  else V2_R(Rz, (v2_launch(k2_z_grad<RR, false>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_z_grad", 12);
-  V2_DISPATCH_R(Ry, (k2_y_inv_grad<8><<<dim3(tiles, Q.Nz), 128, sm_y, st>>>(s->P, Q)),
-                    (k2_y_inv_grad<16><<<dim3(tiles, Q.Nz), 256, sm_y, st>>>(s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_inv_grad<RR>, dim3(tx, Q.Nz), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
-  V2_DISPATCH_R(Rx, (v2_launch_x_u<8>(s, gx)), (v2_launch_x_u<16>(s, gx)));
+  V2_R(Rx, (v2_launch_x_u<RR>(s, gx)));
   ++nk; mark("k2_x_u", s->homogeneous ? 48 : 60);
-  V2_DISPATCH_R(Ry, (k2_y_fwd<8, 1><<<dim3(tiles, Q.Nz, 3), 128, sm_y, st>>>(s->P, Q)),
-                    (k2_y_fwd<16, 1><<<dim3(tiles, Q.Nz, 3), 256, sm_y, st>>>(s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 1>, dim3(tx, Q.Nz, 3), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_u", 24);
   // (3) source field on its slab
   if (src != 0) {
@@ -680,30 +700,26 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
     ++nk; mark("k2_source_scatter", 0);
     if (src == 1) {
       const int gs = (int)(((long long)Q.nzs * (Q.Ny / 2) + (256 / Rx) - 1) / (256 / Rx));
-      V2_DISPATCH_R(Rx, (k2_x_src<8><<<gs, 256, sm_x, st>>>(s->P, Q)), (k2_x_src<16><<<gs, 256, sm_x, st>>>(s->P, Q)));
+      V2_R(Rx, (v2_launch(k2_x_src<RR>, dim3(gs), 256, (size_t)(256 / RR) * RR * RR * 8 + 16 * (RR * RR + 1), st, s->P, Q)));
       ++nk; mark("k2_x_src", 8 * srcf);
-      V2_DISPATCH_R(Ry, (k2_y_fwd<8, 2><<<dim3(tiles, Q.nzs, 1), 128, sm_y, st>>>(s->P, Q)),
-                        (k2_y_fwd<16, 2><<<dim3(tiles, Q.nzs, 1), 256, sm_y, st>>>(s->P, Q)));
+      V2_R(Ry, (v2_launch(k2_y_fwd<RR, 2>, dim3(tx, Q.nzs, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
       ++nk; mark("k2_y_fwd_src", 8 * srcf);
     }
   }
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src == 1 ? 4 : 3;
-  if (s->P.poly_ok) V2_DISPATCH_R(Rz, (k2_z_div<8, true><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q, ncomp)),
-                                      (k2_z_div<16, true><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q, ncomp)));
-  else V2_DISPATCH_R(Rz, (k2_z_div<8, false><<<dim3(tiles, Q.Ny), 128, sm_z, st>>>(s->P, Q, ncomp)),
-                         (k2_z_div<16, false><<<dim3(tiles, Q.Ny), 256, sm_z, st>>>(s->P, Q, ncomp)));
+  if (poly) V2_R(Rz, (v2_launch(k2_z_div<RR, true>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
+  else V2_R(Rz, (v2_launch(k2_z_div<RR, false>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
   ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
-  V2_DISPATCH_R(Ry, (k2_y_inv<8><<<dim3(tiles, Q.Nz, ncomp), 128, sm_y, st>>>(s->P, Q)),
-                    (k2_y_inv<16><<<dim3(tiles, Q.Nz, ncomp), 256, sm_y, st>>>(s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, ncomp), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
-  if (src == 0) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 0>(s, gx)), (v2_launch_x_rho_p<16, 0>(s, gx)));
-  else if (src == 1) V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 1>(s, gx)), (v2_launch_x_rho_p<16, 1>(s, gx)));
-  else V2_DISPATCH_R(Rx, (v2_launch_x_rho_p<8, 2>(s, gx)), (v2_launch_x_rho_p<16, 2>(s, gx)));
+  if (src == 0) V2_R(Rx, (v2_launch_x_rho_p<RR, 0>(s, gx)));
+  else if (src == 1) V2_R(Rx, (v2_launch_x_rho_p<RR, 1>(s, gx)));
+  else V2_R(Rx, (v2_launch_x_rho_p<RR, 2>(s, gx)));
   ++nk;
-  const double inner = (double)s->Vin / (double)s->V;
-  mark("k2_x_rho_p", 12 + 24 + 16 * inner + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+  const double sens = (double)s->n[1] * s->n[2] / ((double)s->N[1] * s->N[2]);   // sensor rows are full x lines
+  mark("k2_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
   return LIFU_OK;
@@ -870,6 +886,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   if (s->last_used_v2) {
     LIFU_CUDA(cudaMemsetAsync(s->Q.ZP, 0, sizeof(float2) * s->Q.ZS, st));
     LIFU_CUDA(cudaMemsetAsync(s->Q.Sslab, 0, sizeof(float) * (size_t)s->Q.nzs * s->N[1] * s->N[0], st));
+    k2_pm_init<<<grid_blocks(s, s->V, 256), 256, 0, st>>>(s->Q.pm, s->V);
   }
   k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmax, s->Vin, -INFINITY);
   k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmin, s->Vin, INFINITY);
@@ -915,6 +932,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     }
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  if (rc == LIFU_OK && s->last_used_v2) k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
   if (rc == LIFU_OK && p_max) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && p_min) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   cudaError_t se = cudaStreamSynchronize(st);

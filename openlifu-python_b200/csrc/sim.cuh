@@ -65,7 +65,8 @@ struct lifu_sim {
   bool v2_ready = false;
   int R[3] = {0, 0, 0};        // radix per axis (N = R*R)
   lifu::V2Params Q{};
-  float2* d_tw[3] = {nullptr, nullptr, nullptr};
+  float4* d_tw[3] = {nullptr, nullptr, nullptr};
+  float4* d_mul4 = nullptr;    // dpy4, dny4, dpz4, dnz4 packed
   long long slab_planes_alloc = 0;
   bool last_used_v2 = false;
 
