@@ -103,6 +103,7 @@ struct V2Params {
   int Nx, Ny, Nz, Nxh, PH;          // PH = row pitch of the H layout (multiple of 16)
   int nxt;                          // regular 16-lane kx tiles of the strided passes (Nx/32); tile nxt = Nyquist column
   int Ry;                           // radix of the y axis: rows y and y+Ry form a packed row pair
+  int ry_sh, hy_sh;                 // log2(Ry), log2(Ny/2)
   long long HS;                     // stride between batched H fields  (Nz*Ny*PH)
   long long ZS;                     // stride between batched Z fields  (Nz*(Ny/2)*Nx)
   const float4 *tw4x, *tw4y, *tw4z; // (w, i w), w = exp(-2 pi i m / N), m = 0..N (entry N = entry 0), per axis

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
 
 // z pass of the pressure gradient: H4[0] -> H4[0] (kappa p^) and H4[1] (i kz e^{+i kz dz/2} kappa p^),
 // both already inverse transformed along z.  grid (nxt+1, Ny)
-template <int R, bool POLY>
+template <int R, int POLY>
 __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_grad(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
   using S = Strided<R>;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_grad(StepParams 
   for (int k1 = 0; k1 < R; ++k1) {
     const int kz = t + R * k1;
     const float a2 = axy + P.az2[kz];
-    const float kap = (POLY ? sinc_sqrt_poly(a2) : kappa_of(a2)) * Q.norm;
+    const float kap = kappa_sel<POLY>(a2) * Q.norm;
     v[k1] = cscale(v[k1], kap);
     w[k1] = cmul4(v[k1], Q.dpz4[kz]);
   }
@@ -306,11 +306,12 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_y_inv_grad(StepPar
 }
 
 // z pass of the velocity divergence (comp 0..2, in place) and of the source field (comp 3).
-// grid (nxt+1, Ny); the CTA walks the components so that kappa is evaluated once per (kx,ky,kz).
-// comp 2 additionally gets i kz e^{-i kz dz/2}; comp 3 reads the slab planes only and is filtered with
-// cos(c_ref k dt/2).
-template <int R, bool POLY>
-__global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_z_div(StepParams P, V2Params Q, int ncomp) {
+// grid (nxt+1, Ny); the CTA walks the components with the loads of component c+1 in flight while component
+// c is transformed (register double buffer), so HBM stays busy through the FFT phases; kappa is evaluated
+// once per (kx,ky,kz).  comp 2 additionally gets i kz e^{-i kz dz/2}; comp 3 reads the slab planes only and
+// is filtered with cos(c_ref k dt/2).
+template <int R, int POLY>
+__global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P, V2Params Q, int ncomp) {
   extern __shared__ __align__(16) unsigned char smraw[];
   using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
@@ -320,27 +321,27 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_z_div(StepParams P
   float2* xa = reinterpret_cast<float2*>(smraw);
   float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
   const int zs = Q.Ny * Q.PH, jstep = R * zs;
-  const long long off = (long long)t * zs + ky * Q.PH + kx;
+  float2* hp = Q.H4 + (long long)t * zs + ky * Q.PH + kx;
+  const float2* sp = Q.HSslab + (long long)(t - Q.z0s) * zs + ky * Q.PH + kx;
+  float2 v[R], nx[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
   const float axy = P.ax2[kx] + P.ay2[ky];
   float kap[R];
 #pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) {
-    const float a2 = axy + P.az2[t + R * k1];
-    kap[k1] = (POLY ? sinc_sqrt_poly(a2) : kappa_of(a2)) * Q.norm;
-  }
+  for (int k1 = 0; k1 < R; ++k1) kap[k1] = kappa_sel<POLY>(axy + P.az2[t + R * k1]) * Q.norm;
 #pragma unroll 1
   for (int comp = 0; comp < ncomp; ++comp) {
-    float2* hp = Q.H4 + comp * Q.HS + off;
-    float2 v[R];
-    if (comp < 3) {
+    // prefetch the next component
+    if (comp + 1 < 3) {
+      const float2* np = hp + (comp + 1) * Q.HS;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
-    } else {
-      const float2* sp = Q.HSslab + (long long)(t - Q.z0s) * zs + ky * Q.PH + kx;
+      for (int j = 0; j < R; ++j) nx[j] = np[j * jstep];
+    } else if (comp + 1 < ncomp) {
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         const int zr = t + R * j - Q.z0s;
-        v[j] = (zr >= 0 && zr < Q.nzs) ? sp[j * jstep] : make_float2(0.f, 0.f);
+        nx[j] = (zr >= 0 && zr < Q.nzs) ? sp[j * jstep] : make_float2(0.f, 0.f);
       }
     }
     strided_fft<R, false>(v, tw, xa, l, t);
@@ -352,14 +353,14 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_z_div(StepParams P
       for (int k1 = 0; k1 < R; ++k1) v[k1] = cmul4(cscale(v[k1], kap[k1]), Q.dnz4[t + R * k1]);
     } else {
 #pragma unroll
-      for (int k1 = 0; k1 < R; ++k1) {
-        const float a2 = axy + P.az2[t + R * k1];
-        v[k1] = cscale(v[k1], (POLY ? cos_sqrt_poly(a2) : cosf(sqrtf(a2))) * Q.norm);
-      }
+      for (int k1 = 0; k1 < R; ++k1) v[k1] = cscale(v[k1], cosk_sel<POLY>(axy + P.az2[t + R * k1]) * Q.norm);
     }
     strided_fft<R, true>(v, tw, xb, l, t);
+    float2* op = hp + comp * Q.HS;
 #pragma unroll
-    for (int j = 0; j < R; ++j) hp[j * jstep] = v[j];
+    for (int j = 0; j < R; ++j) op[j * jstep] = v[j];
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = nx[j];
   }
 }
 
@@ -446,12 +447,19 @@ struct XStage {
   }
 };
 
-// row pair m of plane z -> element offset of its lower row in a real field; the upper row is Ry rows further
+// row pair index (z*Ny/2 + m) -> z and the lower row y_lo of the pair (Ny/2 and Ry are powers of two)
+__device__ __forceinline__ void pair_rows(const V2Params& Q, int pair, int& z, int& ylo) {
+  const int m = pair & ((Q.Ny >> 1) - 1);
+  z = pair >> Q.hy_sh;
+  ylo = ((m >> Q.ry_sh) << (Q.ry_sh + 1)) | (m & (Q.Ry - 1));
+}
 __device__ __forceinline__ long long pair_row_lo(const V2Params& Q, int z, int m) {
-  const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
+  const int ylo = ((m >> Q.ry_sh) << (Q.ry_sh + 1)) | (m & (Q.Ry - 1));
   return ((long long)z * Q.Ny + ylo) * Q.Nx;
 }
 
+// Work of one persistent CTA: row-pair batches blockIdx.x, blockIdx.x + gridDim.x, ...; inside a batch the
+// items of a pair are unrolled at compile time, so the per-item index arithmetic folds away.
 template <int R, bool HOMOG>
 __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
   using XS = XStage<R>;
@@ -460,64 +468,68 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
   char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
-  const int hy = Q.Ny / 2;
   const long long hi = (long long)Q.Ry * N;                       // offset of the pair's upper row
-  const long long nbatch = (long long)Q.Nz * hy / G;
-  const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long nitems = my_iters * 3;
+  const int nbatch = Q.Nz * (Q.Ny / 2) / G;
+  const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int pstep = gridDim.x * G;
 
-  auto issue = [&](long long q) {
-    if (q < nitems) {
-      const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
-      const int c = (int)(q % 3);
-      const int m = (int)(pair % hy), z = (int)(pair / hy);
-      const long long r0 = pair_row_lo(Q, z, m);
-      char* st = gbase + (q & 1) * XS::BYTES;
-      XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + pair * N), 8 * N, t);
+  auto issue = [&](int pair, int c, int stage, bool valid) {
+    if (valid) {
+      int z, ylo;
+      pair_rows(Q, pair, z, ylo);
+      const long long r0 = ((long long)z * Q.Ny + ylo) * N;
+      char* st = gbase + stage * XS::BYTES;
+      XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + (long long)pair * N), 8 * N, t);
       XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0), 4 * N, t);
       XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0 + hi), 4 * N, t);
     }
     cp_async_commit();
   };
-  issue(0);
-  issue(1);
-  for (long long q = 0; q < nitems; ++q) {
-    cp_async_wait<1>();
-    __syncwarp();
-    const long long pair = (blockIdx.x + (q / 3) * gridDim.x) * G + g;
-    const int c = (int)(q % 3);
-    const int m = (int)(pair % hy), z = (int)(pair / hy);
-    const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
-    float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
-    const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
+  int pair = blockIdx.x * G + g;
+  issue(pair, 0, 0, iters > 0);
+  issue(pair, 1, 1, iters > 0);
+  for (int it = 0; it < iters; ++it, pair += pstep) {
+    int z, ylo;
+    pair_rows(Q, pair, z, ylo);
     const long long r0 = ((long long)z * Q.Ny + ylo) * N;
-    float2 v[R];
+    const int par = it & 1;                               // item index = 3*it + c
 #pragma unroll
-    for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
-    __syncwarp();
-    line_fft_sw<R, true>(v, tw, zb, t);
-    float* u = P.u + c * P.RS + r0;
-    float2 s;
-    if (c == 1) s = make_float2(P.sgy[ylo], P.sgy[ylo + Q.Ry]); else s.x = s.y = P.sgz[z];
+    for (int c = 0; c < 3; ++c) {
+      cp_async_wait<1>();
+      __syncwarp();
+      const int stage = (par + c) & 1;
+      float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
+      const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
+      float2 v[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-      const int x = t + R * j;
-      if (c == 0) s.x = s.y = P.sgx[x];
-      float2 d;
-      if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_sg_s; }
-      else { d.x = -P.dt_rho0_sg[c * P.RS + r0 + x]; d.y = -P.dt_rho0_sg[c * P.RS + r0 + hi + x]; }
-      // u = s (s u - dt/rho0 dp)
-      const float2 un = __fmul2_rn(s, __ffma2_rn(d, v[j], __fmul2_rn(s, make_float2(rb[x], rb[N + x]))));
-      u[x] = un.x;
-      u[hi + x] = un.y;
-      v[j] = un;
+      for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+      __syncwarp();
+      line_fft_sw<R, true>(v, tw, zb, t);
+      float* u = P.u + c * P.RS + r0;
+      float2 s;
+      if (c == 1) s = make_float2(P.sgy[ylo], P.sgy[ylo + Q.Ry]);
+      else if (c == 2) s.x = s.y = P.sgz[z];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const int x = t + R * j;
+        if (c == 0) s.x = s.y = P.sgx[x];
+        float2 d;
+        if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_sg_s; }
+        else { d.x = -P.dt_rho0_sg[c * P.RS + r0 + x]; d.y = -P.dt_rho0_sg[c * P.RS + r0 + hi + x]; }
+        // u = s (s u - dt/rho0 dp)
+        const float2 un = __fmul2_rn(s, __ffma2_rn(d, v[j], __fmul2_rn(s, make_float2(rb[x], rb[N + x]))));
+        u[x] = un.x;
+        u[hi + x] = un.y;
+        v[j] = un;
+      }
+      line_fft_sw<R, false>(v, tw, zb, t);
+      float2* zo = Q.Z4 + c * Q.ZS + (long long)pair * N;
+#pragma unroll
+      for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = v[k1];
+      __syncwarp();
+      if (c == 0) issue(pair, 2, stage, true);
+      else issue(pair + pstep, c - 1, stage, it + 1 < iters);
     }
-    line_fft_sw<R, false>(v, tw, zb, t);
-    float2* zo = Q.Z4 + c * Q.ZS + pair * N;
-#pragma unroll
-    for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = v[k1];
-    __syncwarp();
-    issue(q + 2);
   }
   cp_async_wait<0>();
 }
@@ -535,22 +547,20 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
   char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
-  const int hy = Q.Ny / 2;
   const long long hi = (long long)Q.Ry * N;
-  const long long nbatch = (long long)Q.Nz * hy / G;
-  const long long my_iters = blockIdx.x < nbatch ? (nbatch - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long nitems = my_iters * NI;
+  const int nbatch = Q.Nz * (Q.Ny / 2) / G;
+  const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int pstep = gridDim.x * G;
 
-  auto issue = [&](long long q) {
-    if (q < nitems) {
-      const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
-      const int c = (int)(q % NI) - C0;                   // -1: source item, 0..2: rho, 3: sensor rows
-      const int m = (int)(pair % hy), z = (int)(pair / hy);
-      const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
+  // c: -1 source item, 0..2 rho_x, rho_y, rho_z, 3 sensor rows
+  auto issue = [&](int pair, int c, int stage, bool valid) {
+    if (valid) {
+      int z, ylo;
+      pair_rows(Q, pair, z, ylo);
       const long long r0 = ((long long)z * Q.Ny + ylo) * N;
-      char* st = gbase + (q & 1) * XS::BYTES;
+      char* st = gbase + stage * XS::BYTES;
       if (c < 3) {
-        XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + pair * N), 8 * N, t);
+        XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + (long long)pair * N), 8 * N, t);
         if (c >= 0) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0 + hi), 4 * N, t);
@@ -565,96 +575,103 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
     }
     cp_async_commit();
   };
-  issue(0);
-  issue(1);
+  int pair = blockIdx.x * G + g;
+  issue(pair, 0 - C0, 0, iters > 0);
+  issue(pair, 1 - C0, 1, iters > 0);
   float2 src[R], sum[R];
-  for (long long q = 0; q < nitems; ++q) {
-    cp_async_wait<1>();
-    __syncwarp();
-    const long long pair = (blockIdx.x + (q / NI) * gridDim.x) * G + g;
-    const int c = (int)(q % NI) - C0;
-    const int m = (int)(pair % hy), z = (int)(pair / hy);
-    const int ylo = (m / Q.Ry) * 2 * Q.Ry + (m % Q.Ry);
-    float2* zb = reinterpret_cast<float2*>(gbase + (q & 1) * XS::BYTES);
-    const float* rb = reinterpret_cast<const float*>(gbase + (q & 1) * XS::BYTES + 8 * N);
+  for (int it = 0; it < iters; ++it, pair += pstep) {
+    int z, ylo;
+    pair_rows(Q, pair, z, ylo);
     const long long r0 = ((long long)z * Q.Ny + ylo) * N;
-    if (c < 3) {
-      float2 v[R];
+    const int par = (it * NI) & 1;
 #pragma unroll
-      for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+    for (int ci = 0; ci < NI; ++ci) {
+      const int c = ci - C0;
+      cp_async_wait<1>();
       __syncwarp();
-      line_fft_sw<R, true>(v, tw, zb, t);
-      if (c < 0) {
+      const int stage = (par + ci) & 1;
+      float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
+      const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
+      if (c < 3) {
+        float2 v[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) src[j] = v[j];
-      } else {
-        if (SRC == 2 && c == 0) {
-          const int zr = z - Q.z0s;
-          const bool in = zr >= 0 && zr < Q.nzs;
-          const long long so = ((long long)zr * Q.Ny + ylo) * N;
+        for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+        __syncwarp();
+        line_fft_sw<R, true>(v, tw, zb, t);
+        if (c < 0) {
 #pragma unroll
-          for (int j = 0; j < R; ++j)
-            src[j] = in ? make_float2(Q.Sslab[so + t + R * j], Q.Sslab[so + hi + t + R * j]) : make_float2(0.f, 0.f);
-        }
-        float* rho = P.rho + c * P.RS + r0;
-        float2 a;
-        if (c == 1) a = make_float2(P.pmly[ylo], P.pmly[ylo + Q.Ry]); else a.x = a.y = P.pmlz[z];
+          for (int j = 0; j < R; ++j) src[j] = v[j];
+        } else {
+          if (SRC == 2 && c == 0) {
+            const int zr = z - Q.z0s;
+            const bool in = zr >= 0 && zr < Q.nzs;
+            const long long so = ((long long)zr * Q.Ny + ylo) * N;
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int x = t + R * j;
-          if (c == 0) a.x = a.y = P.pmlx[x];
-          float2 d;
-          if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_s; }
-          else { d.x = -P.dt_rho0[r0 + x]; d.y = -P.dt_rho0[r0 + hi + x]; }
-          // rho = a (a rho - dt rho0 du) [+ S]
-          float2 rn = __fmul2_rn(a, __ffma2_rn(d, v[j], __fmul2_rn(a, make_float2(rb[x], rb[N + x]))));
-          if constexpr (SRC != 0) rn = cadd(rn, src[j]);
-          rho[x] = rn.x;
-          rho[hi + x] = rn.y;
-          sum[j] = c == 0 ? rn : cadd(sum[j], rn);           // (rho_x + rho_y) + rho_z
-        }
-        if (c == 2) {
-          // equation of state; the sensor item that follows consumes p from `sum`
+            for (int j = 0; j < R; ++j)
+              src[j] = in ? make_float2(Q.Sslab[so + t + R * j], Q.Sslab[so + hi + t + R * j]) : make_float2(0.f, 0.f);
+          }
+          float* rho = P.rho + c * P.RS + r0;
+          float2 a;
+          if (c == 1) a = make_float2(P.pmly[ylo], P.pmly[ylo + Q.Ry]);
+          else if (c == 2) a.x = a.y = P.pmlz[z];
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int x = t + R * j;
-            float2 c2;
-            if constexpr (HOMOG) { c2.x = c2.y = P.c2_s; } else { c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
-            sum[j] = __fmul2_rn(c2, sum[j]);
-            if (Q.store_p) { P.p[r0 + x] = sum[j].x; P.p[r0 + hi + x] = sum[j].y; }
+            if (c == 0) a.x = a.y = P.pmlx[x];
+            float2 d;
+            if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_s; }
+            else { d.x = -P.dt_rho0[r0 + x]; d.y = -P.dt_rho0[r0 + hi + x]; }
+            // rho = a (a rho - dt rho0 du) [+ S]
+            float2 rn = __fmul2_rn(a, __ffma2_rn(d, v[j], __fmul2_rn(a, make_float2(rb[x], rb[N + x]))));
+            if constexpr (SRC != 0) rn = cadd(rn, src[j]);
+            rho[x] = rn.x;
+            rho[hi + x] = rn.y;
+            sum[j] = c == 0 ? rn : cadd(sum[j], rn);           // (rho_x + rho_y) + rho_z
+          }
+          if (c == 2) {
+            // equation of state; the sensor item that follows consumes p from `sum`
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+              const int x = t + R * j;
+              float2 c2;
+              if constexpr (HOMOG) { c2.x = c2.y = P.c2_s; } else { c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
+              sum[j] = __fmul2_rn(c2, sum[j]);
+              if (Q.store_p) { P.p[r0 + x] = sum[j].x; P.p[r0 + hi + x] = sum[j].y; }
+            }
           }
         }
-      }
-    } else {
-      // running max / min on the two sensor rows, then the forward transform of the new pressure
-      const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
-      const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
-      const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
-      float2* pmg = Q.pm + r0;
-      if (in0) {
+      } else {
+        // running max / min on the two sensor rows, then the forward transform of the new pressure
+        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
+        const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
+        float2* pmg = Q.pm + r0;
+        if (in0) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int x = t + R * j;
-          const float2 o = zb[x];
-          pmg[x] = make_float2(fmaxf(o.x, sum[j].x), fminf(o.y, sum[j].x));
+          for (int j = 0; j < R; ++j) {
+            const int x = t + R * j;
+            const float2 o = zb[x];
+            pmg[x] = make_float2(fmaxf(o.x, sum[j].x), fminf(o.y, sum[j].x));
+          }
         }
-      }
-      if (in1) {
+        if (in1) {
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          const int x = t + R * j;
-          const float2 o = zb[N + x];
-          pmg[hi + x] = make_float2(fmaxf(o.x, sum[j].y), fminf(o.y, sum[j].y));
+          for (int j = 0; j < R; ++j) {
+            const int x = t + R * j;
+            const float2 o = zb[N + x];
+            pmg[hi + x] = make_float2(fmaxf(o.x, sum[j].y), fminf(o.y, sum[j].y));
+          }
         }
+        __syncwarp();
+        line_fft_sw<R, false>(sum, tw, zb, t);
+        float2* zo = Q.ZP + (long long)pair * N;
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
       }
       __syncwarp();
-      line_fft_sw<R, false>(sum, tw, zb, t);
-      float2* zo = Q.ZP + pair * N;
-#pragma unroll
-      for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
+      if (ci + 2 < NI) issue(pair, ci + 2 - C0, stage, true);
+      else issue(pair + pstep, ci + 2 - NI - C0, stage, it + 1 < iters);
     }
-    __syncwarp();
-    issue(q + 2);
   }
   cp_async_wait<0>();
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.step = *P.step + 1;
@@ -673,7 +690,7 @@ __global__ void __launch_bounds__(256) k2_x_src(StepParams P, V2Params Q) {
   const int hy = Q.Ny / 2;
   const long long pair = (long long)blockIdx.x * G + g;          // zr*(Ny/2) + m
   if (pair >= (long long)Q.nzs * hy) return;
-  const int m = (int)(pair % hy), zr = (int)(pair / hy);
+  const int m = (int)(pair & (hy - 1)), zr = (int)(pair >> Q.hy_sh);
   const long long r0 = pair_row_lo(Q, zr, m), hi = (long long)Q.Ry * N;
   float2 v[R];
 #pragma unroll

@@ -129,7 +129,7 @@ static int build_tables(lifu_sim* s) {
   {
     double smax = 0;
     for (int a = 0; a < 3; ++a) { double arg = c * (M_PI / d[a]) * dt / 2.0; smax += arg * arg; }
-    P.poly_ok = smax <= 9.8 ? 1 : 0;
+    P.poly_ok = smax <= 2.0 ? 2 : (smax <= 9.8 ? 1 : 0);
   }
   s->tables_ready = true;
   return LIFU_OK;
@@ -602,6 +602,9 @@ static int v2_setup(lifu_sim* s) {
       LIFU_CUDA(cudaStreamSynchronize(s->stream));
     }
     Q.Ry = s->R[1];
+    Q.ry_sh = Q.Ry == 8 ? 3 : 4;
+    Q.hy_sh = 0;
+    while ((1 << Q.hy_sh) < Q.Ny / 2) ++Q.hy_sh;
     Q.tw4x = s->d_tw[0]; Q.tw4y = s->d_tw[1]; Q.tw4z = s->d_tw[2];
     {
       // derivative multipliers i k e^{+-i k d/2} of the y and z axes as (m, i m) pairs
@@ -680,12 +683,13 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   int nk = 0;
   const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
   const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
-  const bool poly = s->P.poly_ok != 0;
+  const int poly = s->P.poly_ok;
   // (1) pressure gradient
   V2_R(Ry, (v2_launch(k2_y_fwd<RR, 0>, dim3(tx, Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_p", 8);
-  if (poly) V2_R(Rz, (v2_launch(k2_z_grad<RR, true>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
-  else V2_R(Rz, (v2_launch(k2_z_grad<RR, false>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_grad<RR, 2>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_grad<RR, 1>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  else V2_R(Rz, (v2_launch(k2_z_grad<RR, 0>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_z_grad", 12);
   V2_R(Ry, (v2_launch(k2_y_inv_grad<RR>, dim3(tx, Q.Nz), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_y_inv_grad", 20);
@@ -708,8 +712,9 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   }
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src == 1 ? 4 : 3;
-  if (poly) V2_R(Rz, (v2_launch(k2_z_div<RR, true>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
-  else V2_R(Rz, (v2_launch(k2_z_div<RR, false>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
+  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_div<RR, 2>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
+  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_div<RR, 1>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
+  else V2_R(Rz, (v2_launch(k2_z_div<RR, 0>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
   ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
   V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, ncomp), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_inv", 8 * ncomp);

@@ -59,10 +59,46 @@ __device__ __forceinline__ float cos_sqrt_poly(float s) {
   return r;
 }
 
+// Short forms for s <= 2 (the usual CFL <= 0.5 case): 8 terms, truncation error < 2e-11.
+__device__ __forceinline__ float sinc_sqrt_poly8(float s) {
+  float r = -7.647163732e-13f;
+  r = fmaf(r, s, 1.605904384e-10f);
+  r = fmaf(r, s, -2.505210839e-08f);
+  r = fmaf(r, s, 2.755731922e-06f);
+  r = fmaf(r, s, -1.984126984e-04f);
+  r = fmaf(r, s, 8.333333333e-03f);
+  r = fmaf(r, s, -1.666666667e-01f);
+  r = fmaf(r, s, 1.000000000e+00f);
+  return r;
+}
+__device__ __forceinline__ float cos_sqrt_poly8(float s) {
+  float r = -1.147074560e-11f;
+  r = fmaf(r, s, 2.087675699e-09f);
+  r = fmaf(r, s, -2.755731922e-07f);
+  r = fmaf(r, s, 2.480158730e-05f);
+  r = fmaf(r, s, -1.388888889e-03f);
+  r = fmaf(r, s, 4.166666667e-02f);
+  r = fmaf(r, s, -5.000000000e-01f);
+  r = fmaf(r, s, 1.000000000e+00f);
+  return r;
+}
+
 __device__ __forceinline__ float kappa_of(float a2) {
   // kappa = sinc(c_ref k dt / 2); a2 = (c_ref k dt / 2)^2 <= (cfl*pi*sqrt(3)/2)^2, no range issues
   float a = sqrtf(a2);
   return a > 0.f ? sinf(a) / a : 1.f;
+}
+
+// POLY: 0 exact sinf/cosf, 1 long polynomials (s <= 9.8), 2 short polynomials (s <= 2)
+template <int POLY> __device__ __forceinline__ float kappa_sel(float a2) {
+  if constexpr (POLY == 2) return sinc_sqrt_poly8(a2);
+  else if constexpr (POLY == 1) return sinc_sqrt_poly(a2);
+  else return kappa_of(a2);
+}
+template <int POLY> __device__ __forceinline__ float cosk_sel(float a2) {
+  if constexpr (POLY == 2) return cos_sqrt_poly8(a2);
+  else if constexpr (POLY == 1) return cos_sqrt_poly(a2);
+  else return cosf(sqrtf(a2));
 }
 
 // ------------------------------------------------------------------ K1
