@@ -61,6 +61,55 @@ def _visible_devices() -> int:
     return max(1, min(n, cap) if cap > 0 else n)
 
 
+def _dist_world() -> Tuple[int, int]:
+    """(world_size, rank) of the torch.distributed job this process belongs to, (1, 0) outside one."""
+    try:
+        import torch.distributed as dist
+    except Exception:  # noqa: BLE001
+        return 1, 0
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1, 0
+    return dist.get_world_size(), dist.get_rank()
+
+
+def _gather_foci(mine: Dict[int, Any], n_foci: int, world: int, coords) -> list:
+    """All-gather the per-focus Datasets of a rank-sharded sweep (focus i lives on rank i mod world).
+    Every variable is exchanged in its own dtype (p_max/p_min float32, intensity float64), in slots
+    of ceil(n_foci / world) foci per rank; the only collective of the sweep, outside the solver."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    template = next(iter(mine.values())) if mine else None
+    meta = [None]
+    if rank == 0:                       # rank 0 always owns focus 0
+        meta = [[(k, template[k].data.dtype.str, tuple(template[k].data.shape), tuple(template[k].dims),
+                  dict(template[k].attrs), template[k].name) for k in template.data_vars]]
+    dist.broadcast_object_list(meta, src=0)
+    slots = (n_foci + world - 1) // world
+    on_gpu = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    gathered = {}
+    for name, dtype, shape, _, _, _ in meta[0]:
+        local = np.zeros((slots,) + shape, dtype=np.dtype(dtype))
+        for i, ds in mine.items():
+            local[i // world] = ds[name].data
+        send = torch.from_numpy(local).to(dev)
+        recv = torch.empty((world * slots,) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
+        dist.all_gather_into_tensor(recv, send)                               # rank-major concatenation
+        gathered[name] = recv.cpu().numpy().reshape((world, slots) + shape)
+    out = []
+    for i in range(n_foci):
+        if i in mine:
+            out.append(mine[i])
+            continue
+        vars_ = {}
+        for name, _, _, dims, attrs, da_name in meta[0]:
+            data = np.array(gathered[name][i % world, i // world])          # writable copy (Solution.scale works in place)
+            vars_[name] = xa.DataArray(data, coords=coords, dims=dims, name=da_name, attrs=dict(attrs))
+        out.append(xa.Dataset(vars_))
+    return out
+
+
 @dataclass
 class Protocol:
     id: str = "protocol"
@@ -200,6 +249,12 @@ class Protocol:
                                    amplitude=self.pulse.amplitude * voltage, gpu=use_gpu)
             return ds
 
+        world, rank = _dist_world()
+        if world > 1 and len(beams) > 1:
+            # one process per GPU (torchrun): rank r simulates foci r, r + world, ...; the fields are
+            # all-gathered so that every rank holds the full stack, as the reference's serial loop would
+            mine = {i: one(i) for i in range(rank, len(beams), world)}
+            return _gather_foci(mine, len(beams), world, params.coords)
         n_dev = _visible_devices() if (use_gpu and run_simulation is kwave_if.run_simulation and len(beams) > 1) else 1
         if n_dev <= 1:
             return [one(i) for i in range(len(beams))]

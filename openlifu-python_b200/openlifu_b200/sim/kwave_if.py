@@ -183,13 +183,18 @@ def run_simulation(arr,
     output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
               "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
 
+    return package_fields(params, output["p_max"], output["p_min"]), output
+
+
+def package_fields(params, p_max_flat, p_min_flat):
+    """Flat x-fastest float32 sensor vectors -> the Dataset of kwave_if.py:131-146 (p_min sign flip,
+    float64 intensity named 'I' under the key 'intensity')."""
     sz = list(params.coords.sizes.values())
-    p_max = xa.DataArray(output["p_max"].reshape(sz, order="F"), coords=params.coords, name="p_max",
+    p_max = xa.DataArray(p_max_flat.reshape(sz, order="F"), coords=params.coords, name="p_max",
                          attrs={"units": "Pa", "long_name": "PPP"})
-    p_min = xa.DataArray(-1 * output["p_min"].reshape(sz, order="F"), coords=params.coords, name="p_min",
+    p_min = xa.DataArray(-1 * p_min_flat.reshape(sz, order="F"), coords=params.coords, name="p_min",
                          attrs={"units": "Pa", "long_name": "PNP"})
     Z = params["density"].data * params["sound_speed"].data
-    intensity = xa.DataArray(1e-4 * output["p_min"].reshape(sz, order="F") ** 2 / (2 * Z), coords=params.coords,
+    intensity = xa.DataArray(1e-4 * p_min_flat.reshape(sz, order="F") ** 2 / (2 * Z), coords=params.coords,
                              name="I", attrs={"units": "W/cm^2", "long_name": "Intensity"})
-    ds = xa.Dataset({"p_max": p_max, "p_min": p_min, "intensity": intensity})
-    return ds, output
+    return xa.Dataset({"p_max": p_max, "p_min": p_min, "intensity": intensity})
