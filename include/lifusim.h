@@ -139,8 +139,50 @@ int lifu_set_drive(lifu_sim* sim, const float* base_signal, int32_t n_base,
  * the raw minimum (the adapter negates it, kwave_if.py:136).  stats may be NULL. */
 int lifu_run(lifu_sim* sim, float* p_max, float* p_min, lifu_stats* stats);
 
+/* ---- one oversized grid over several GPUs (BASELINE.json config C5) ----
+ * k-Wave's binaries are single-device, so nothing in the reference binds these; they extend the
+ * kspaceFirstOrder3D replacement (kwave_if.py:117-129) to grids that do not fit one GPU.  One process
+ * per GPU of one NVSwitch node; rank r holds the expanded planes [r*Nz/G, (r+1)*Nz/G) of every field.
+ * The expanded Ny and Nz must be multiples of G.  3-D transforms = local 2-D (x,y) transforms + one
+ * exchange over NVLink + local 1-D z transforms.
+ *   lifu_slab_unique_id   rank 0 calls it and broadcasts the 128 bytes (ncclUniqueId) to every rank
+ *   lifu_create_slab      collective: builds the NCCL communicator and maps the peers' exchange buffers
+ *   lifu_slab_layout      which planes this rank owns / must be given
+ * On a slab handle:
+ *   lifu_set_medium_planes  maps cover the inner planes [plane0, plane0+n_planes) of the INNER grid and
+ *                           must include [medium_z0, medium_z0+medium_nz); lifu_set_medium = all planes.
+ *                           Collective (c_ref = global max c0).
+ *   lifu_set_elements / lifu_set_source_geometry  take the FULL geometry on every rank (each keeps its part)
+ *   lifu_run              collective; p_max/p_min receive this rank's inner planes
+ *                         [sensor_z0, sensor_z0+sensor_nz), x fastest.
+ *   lifu_destroy          collective. */
+#define LIFU_NCCL_ID_BYTES 128
+typedef enum lifu_exchange {
+  LIFU_EXCHANGE_AUTO = 0,  /* peer stores when CUDA IPC mapping works on every rank, else NCCL */
+  LIFU_EXCHANGE_NCCL = 1,  /* pack + grouped ncclSend/ncclRecv + unpack */
+  LIFU_EXCHANGE_PEER = 2   /* kernels store straight into the destination rank's buffer over NVLink */
+} lifu_exchange;
+typedef struct lifu_slab_desc {
+  int32_t rank, nranks;
+  int32_t exchange;                      /* lifu_exchange */
+  unsigned char nccl_id[LIFU_NCCL_ID_BYTES];
+} lifu_slab_desc;
+typedef struct lifu_slab_layout {
+  int32_t rank, nranks, exchange;        /* exchange: the mode in use (1 or 2) */
+  int32_t z0, nz;                        /* expanded planes held by this rank */
+  int32_t sensor_z0, sensor_nz;          /* inner planes of p_max/p_min written by lifu_run (nz may be 0) */
+  int32_t medium_z0, medium_nz;          /* inner planes of the medium maps this rank reads */
+} lifu_slab_layout;
+int lifu_slab_unique_id(unsigned char id[LIFU_NCCL_ID_BYTES]);
+int lifu_create_slab(const lifu_grid* grid, int device, void* cuda_stream, const lifu_slab_desc* slab,
+                     lifu_sim** out);
+int lifu_slab_layout_of(lifu_sim* sim, lifu_slab_layout* out);
+int lifu_set_medium_planes(lifu_sim* sim, const float* c0, const float* rho0, const float* alpha_db,
+                           float alpha_power, int alpha_mode, int homogeneous, int32_t plane0,
+                           int32_t n_planes);
+
 /* Debug / test access to the state after lifu_run: which = 0 p, 1..3 u_x,u_y,u_z,
- * 4..6 rho_x,rho_y,rho_z; out: float32 on the EXPANDED grid, x fastest. */
+ * 4..6 rho_x,rho_y,rho_z; out: float32 on the EXPANDED grid (a slab handle: its own planes), x fastest. */
 int lifu_get_field(lifu_sim* sim, int which, float* out);
 int lifu_get_info(lifu_sim* sim, lifu_stats* stats);
 

@@ -49,6 +49,8 @@ struct StepParams {
   int Nx, Ny, Nz, Nxh;        // expanded grid, half-spectrum length along x
   int nx, ny, nz;             // inner grid
   int px, py, pz;             // PML thickness
+  int z0, NzG;                // slab decomposition: first expanded plane held here and the global Nz (0, Nz otherwise)
+  int jz0;                    // first inner plane of the local sensor buffers (0 without a slab decomposition)
   long long V;                // Nx*Ny*Nz
   long long Vh;               // Nxh*Ny*Nz
   long long RS, CS;           // strides between batched real / complex fields

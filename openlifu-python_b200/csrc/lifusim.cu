@@ -10,6 +10,7 @@
 #include "sim.cuh"
 #include "step_kernels.cuh"
 #include "fft_v2.cuh"
+#include "slab.cuh"
 
 namespace lifu {
 
@@ -126,6 +127,7 @@ static int build_tables(lifu_sim* s) {
   P.kx2 = T + off_k2[0]; P.ky2 = T + off_k2[1]; P.kz2 = T + off_k2[2];
   P.pmlx = T + off_pml[0]; P.pmly = T + off_pml[1]; P.pmlz = T + off_pml[2];
   P.sgx = T + off_sg[0]; P.sgy = T + off_sg[1]; P.sgz = T + off_sg[2];
+  if (s->sl.on) { P.pmlz += s->sl.z0; P.sgz += s->sl.z0; }   // real-space kernels index z by the local plane
   {
     double smax = 0;
     for (int a = 0; a < 3; ++a) { double arg = c * (M_PI / d[a]) * dt / 2.0; smax += arg * arg; }
@@ -176,11 +178,23 @@ int upload_source_points(lifu_sim* s) {
   if (!s->geometry_set || !s->medium_set) return LIFU_OK;
   if (s->d_lin_exp) { cudaFree(s->d_lin_exp); s->d_lin_exp = nullptr; }
   if (s->d_scale) { cudaFree(s->d_scale); s->d_scale = nullptr; }
-  LIFU_CUDA(cudaMalloc(&s->d_lin_exp, sizeof(long long) * std::max<long long>(s->n_src, 1)));
-  LIFU_CUDA(cudaMalloc(&s->d_scale, sizeof(float) * std::max<long long>(s->n_src, 1)));
-  if (s->n_src > 0) {
-    k_source_points<<<grid_blocks(s, s->n_src, 128), 128, 0, s->stream>>>(
-        s->d_idx, s->n_src, s->P, s->homogeneous ? nullptr : s->d_c0e, s->c0_s, s->grid.dt, s->grid.d[0],
+  long long i0 = 0, i1 = s->n_src;
+  if (s->sl.on && s->n_src > 0) {
+    // the points are sorted x fastest / z slowest: this rank's planes are one contiguous range
+    std::vector<long long> h(s->n_src);
+    LIFU_CUDA(cudaMemcpyAsync(h.data(), s->d_idx, sizeof(long long) * s->n_src, cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaStreamSynchronize(s->stream));
+    const long long plane = (long long)s->n[0] * s->n[1];
+    i0 = std::lower_bound(h.begin(), h.end(), (long long)s->sl.jz_lo * plane) - h.begin();
+    i1 = std::lower_bound(h.begin(), h.end(), (long long)(s->sl.jz_lo + s->sl.jz_n) * plane) - h.begin();
+  }
+  s->sl.src_i0 = i0; s->sl.src_i1 = i1;
+  const long long cnt = i1 - i0;
+  LIFU_CUDA(cudaMalloc(&s->d_lin_exp, sizeof(long long) * std::max<long long>(cnt, 1)));
+  LIFU_CUDA(cudaMalloc(&s->d_scale, sizeof(float) * std::max<long long>(cnt, 1)));
+  if (cnt > 0) {
+    k_source_points<<<grid_blocks(s, cnt, 128), 128, 0, s->stream>>>(
+        s->d_idx + i0, cnt, s->P, s->homogeneous ? nullptr : s->d_c0e, s->c0_s, s->grid.dt, s->grid.d[0],
         s->d_lin_exp, s->d_scale);
     LIFU_CUDA(cudaGetLastError());
   }
@@ -273,7 +287,7 @@ int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]) {
   return LIFU_OK;
 }
 
-int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** out) {
+static int create_impl(const lifu_grid* g, int device, void* cuda_stream, const lifu_slab_desc* slab, lifu_sim** out) {
   if (!g || !out) { set_error("lifu_create: null argument"); return LIFU_ERR_INVALID; }
   *out = nullptr;
   for (int a = 0; a < 3; ++a) {
@@ -308,22 +322,46 @@ int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** ou
     s->N[a] = s->n[a] + 2 * s->pml[a];
     s->grid.pml[a] = s->pml[a];
   }
-  s->Nxh = s->N[0] / 2 + 1;
-  s->V = (long long)s->N[0] * s->N[1] * s->N[2];
-  s->Vh = (long long)s->Nxh * s->N[1] * s->N[2];
-  s->Vin = (long long)s->n[0] * s->n[1] * s->n[2];
-  s->RS = round_up(s->V, 128);
-  s->CS = round_up(s->Vh, 64);
   const char* ng = getenv("LIFU_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
   const char* pl = getenv("LIFU_PIPELINE");
   s->pipeline = (pl && !strcmp(pl, "v1")) ? 1 : ((pl && !strcmp(pl, "v2")) ? 2 : 0);
+  s->Nxh = s->N[0] / 2 + 1;
+  s->V = (long long)s->N[0] * s->N[1] * s->N[2];
+  s->Vin = (long long)s->n[0] * s->n[1] * s->n[2];
+  int nz_loc = s->N[2];
+  if (slab) {
+    if (slab->nranks < 1 || slab->rank < 0 || slab->rank >= slab->nranks || slab->exchange < 0 || slab->exchange > 2) {
+      set_error("lifu_create_slab: bad rank %d / nranks %d / exchange %d", slab->rank, slab->nranks, slab->exchange);
+      delete s; return LIFU_ERR_INVALID;
+    }
+    if (s->N[2] % slab->nranks || s->N[1] % slab->nranks) {
+      set_error("lifu_create_slab: expanded grid %dx%dx%d: Ny and Nz must be multiples of the %d ranks",
+                s->N[0], s->N[1], s->N[2], slab->nranks);
+      delete s; return LIFU_ERR_INVALID;
+    }
+    if (!s->stream) {   // collectives and kernels share one real stream for the handle's lifetime
+      if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("cudaStreamCreate failed"); delete s; return LIFU_ERR_CUDA; }
+      s->stream = s->own_stream;
+    }
+    int rcs = slab_init(s, slab);
+    if (rcs != LIFU_OK) { lifu_destroy(s); return rcs; }
+    nz_loc = s->sl.Nzl;
+    s->pipeline = 1;
+    s->use_graph = false;
+  }
+  s->Vloc = (long long)s->N[0] * s->N[1] * nz_loc;
+  s->Vsens = slab ? (long long)s->n[0] * s->n[1] * s->sl.jz_n : s->Vin;
+  s->Vh = (long long)s->Nxh * s->N[1] * nz_loc;
+  s->RS = round_up(s->Vloc, 128);
+  s->CS = round_up(s->Vh, 64);
 
   StepParams& P = s->P;
-  P.Nx = s->N[0]; P.Ny = s->N[1]; P.Nz = s->N[2]; P.Nxh = s->Nxh;
+  P.Nx = s->N[0]; P.Ny = s->N[1]; P.Nz = nz_loc; P.Nxh = s->Nxh;
   P.nx = s->n[0]; P.ny = s->n[1]; P.nz = s->n[2];
   P.px = s->pml[0]; P.py = s->pml[1]; P.pz = s->pml[2];
-  P.V = s->V; P.Vh = s->Vh; P.RS = s->RS; P.CS = s->CS;
+  P.z0 = slab ? s->sl.z0 : 0; P.NzG = s->N[2]; P.jz0 = slab ? s->sl.jz_lo : 0;
+  P.V = s->Vloc; P.Vh = s->Vh; P.RS = s->RS; P.CS = s->CS;
   P.invN = (float)(1.0 / (double)s->V);
 
   int rc = LIFU_OK;
@@ -331,8 +369,8 @@ int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** ou
   const size_t R = sizeof(float) * s->RS, C = sizeof(float2) * s->CS;
   A((void**)&P.p, R); A((void**)&P.u, 3 * R); A((void**)&P.rho, 3 * R); A((void**)&P.r3, 3 * R);
   A((void**)&P.r1, R); A((void**)&P.S, R); A((void**)&P.Sf, R);
-  A((void**)&P.c1, C); A((void**)&P.c3, 3 * C);
-  A((void**)&P.pmax, sizeof(float) * s->Vin); A((void**)&P.pmin, sizeof(float) * s->Vin);
+  if (!slab) { A((void**)&P.c1, C); A((void**)&P.c3, 3 * C); }
+  A((void**)&P.pmax, sizeof(float) * s->Vsens); A((void**)&P.pmin, sizeof(float) * s->Vsens);
   A((void**)&P.step, sizeof(int) * 4);
   if (rc == LIFU_OK) for (int i = 0; i < 3 && rc == LIFU_OK; ++i)
     if (cudaEventCreate(&s->ev[i]) != cudaSuccess) { set_error("cudaEventCreate failed"); rc = LIFU_ERR_CUDA; }
@@ -342,7 +380,38 @@ int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** ou
     rc = build_tables(s);
     if (rc != LIFU_OK) { lifu_destroy(s); return rc; }
   }
+  if (slab) s->sl.ready = true;
   *out = s;
+  return LIFU_OK;
+}
+
+int lifu_create(const lifu_grid* g, int device, void* cuda_stream, lifu_sim** out) {
+  return create_impl(g, device, cuda_stream, nullptr, out);
+}
+
+int lifu_slab_unique_id(unsigned char id[LIFU_NCCL_ID_BYTES]) {
+  if (!id) { set_error("lifu_slab_unique_id: null argument"); return LIFU_ERR_INVALID; }
+  NcclApi* N = nccl_api();
+  if (!N) return LIFU_ERR_STATE;
+  ncclUniqueId u;
+  LIFU_NCCL(N->GetUniqueId(&u));
+  memcpy(id, u.internal, LIFU_NCCL_ID_BYTES);
+  return LIFU_OK;
+}
+
+int lifu_create_slab(const lifu_grid* g, int device, void* cuda_stream, const lifu_slab_desc* slab, lifu_sim** out) {
+  if (!slab) { set_error("lifu_create_slab: null slab descriptor"); return LIFU_ERR_INVALID; }
+  return create_impl(g, device, cuda_stream, slab, out);
+}
+
+int lifu_slab_layout_of(lifu_sim* s, lifu_slab_layout* o) {
+  if (!s || !o) { set_error("lifu_slab_layout_of: null argument"); return LIFU_ERR_INVALID; }
+  if (!s->sl.on) { set_error("lifu_slab_layout_of: not a slab handle"); return LIFU_ERR_STATE; }
+  const SlabCtx& L = s->sl;
+  o->rank = L.rank; o->nranks = L.G; o->exchange = L.exchange;
+  o->z0 = L.z0; o->nz = L.Nzl;
+  o->sensor_z0 = L.jz_lo; o->sensor_nz = L.jz_n;
+  o->medium_z0 = L.med_lo; o->medium_nz = L.med_n;
   return LIFU_OK;
 }
 
@@ -350,6 +419,7 @@ int lifu_destroy(lifu_sim* s) {
   if (!s) return LIFU_OK;
   cudaSetDevice(s->device);
   cudaStreamSynchronize(s->stream);
+  slab_destroy(s);
   for (int i = 0; i < 2; ++i) if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
   cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
   if (s->plans_ready || s->r2c1) for (cufftHandle h : hs) if (h) cufftDestroy(h);
@@ -358,12 +428,13 @@ int lifu_destroy(lifu_sim* s) {
   cudaFree(s->d_w); cudaFree(s->d_scale); cudaFree(s->d_base); cudaFree(s->d_delay); cudaFree(s->d_gain);
   for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
+  if (s->own_stream) cudaStreamDestroy(s->own_stream);
   delete s;
   return LIFU_OK;
 }
 
-int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
-                    float alpha_power, int alpha_mode, int homogeneous) {
+static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
+                           float alpha_power, int alpha_mode, int homogeneous, int plane0, int n_planes) {
   if (!s || !c0 || !rho0) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
   if (alpha_mode < 0 || alpha_mode > 2) { set_error("lifu_set_medium: alpha_mode %d unknown", alpha_mode); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(s->device));
@@ -399,26 +470,37 @@ int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float
     P.eta_s = (float)(2.0 * a_np * std::pow((double)hc, y) * tan_term);
     c_max = hc;
   } else {
+    // planes of the inner grid this handle reads: all of them, or a slab's own range plus the halo
+    const int need_lo = s->sl.on ? s->sl.med_lo : 0, need_n = s->sl.on ? s->sl.med_n : s->n[2];
+    if (plane0 > need_lo || plane0 + n_planes < need_lo + need_n) {
+      set_error("lifu_set_medium: maps cover inner planes [%d,%d) but [%d,%d) are needed", plane0, plane0 + n_planes,
+                need_lo, need_lo + need_n);
+      return LIFU_ERR_INVALID;
+    }
     P.homogeneous = 0;
     const size_t R = sizeof(float) * s->RS;
+    const int n_exp = s->sl.on ? s->sl.Nzl + 1 : s->N[2];            // a slab keeps one halo plane (staggered density)
+    const long long Ve = (long long)s->N[0] * s->N[1] * n_exp;
     if (!s->d_c0e) {
-      LIFU_CHECK(dev_alloc(s, (void**)&s->d_c0e, R));
-      LIFU_CHECK(dev_alloc(s, (void**)&s->d_rho0e, R));
-      LIFU_CHECK(dev_alloc(s, (void**)&s->d_alphae, R));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_c0e, sizeof(float) * Ve));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_rho0e, sizeof(float) * Ve));
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_alphae, sizeof(float) * Ve));
       LIFU_CHECK(dev_alloc(s, (void**)&s->d_med, 7 * R));
     }
-    // stage the inner-grid maps through the (currently idle) scratch field r3
+    // stage the needed inner planes through the (currently idle) scratch field r3
     float* stage = P.r3;
-    const size_t inb = sizeof(float) * s->Vin;
-    const int gb = grid_blocks(s, s->V, 256);
+    const long long plane = (long long)s->n[0] * s->n[1];
+    const size_t inb = sizeof(float) * plane * need_n;
+    const int gbe = grid_blocks(s, Ve, 256);
+    const int gb = grid_blocks(s, s->Vloc, 256);
     const float* src[3] = {c0, rho0, alpha_db};
     float* dst[3] = {s->d_c0e, s->d_rho0e, s->d_alphae};
     for (int m = 0; m < 3; ++m) {
       if (src[m]) {
-        LIFU_CUDA(cudaMemcpyAsync(stage, src[m], inb, cudaMemcpyDefault, st));
-        k_expand_edge<<<gb, 256, 0, st>>>(stage, dst[m], P);
+        LIFU_CUDA(cudaMemcpyAsync(stage, src[m] + (long long)(need_lo - plane0) * plane, inb, cudaMemcpyDefault, st));
+        k_expand_edge<<<gbe, 256, 0, st>>>(stage, dst[m], P, need_lo, n_exp);
       } else {
-        k_fill<<<gb, 256, 0, st>>>(dst[m], s->V, 0.f);
+        k_fill<<<gbe, 256, 0, st>>>(dst[m], Ve, 0.f);
       }
     }
     LIFU_CUDA(cudaGetLastError());
@@ -434,8 +516,13 @@ int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float
     P.rho0 = s->d_rho0e;
     // c_ref = max(c0) and absorbing = any(alpha != 0) come from device reductions
     float cmax = 0, amax = 0, cmin = 0, amin = 0;
-    LIFU_CHECK(reduce_minmax(s, s->d_c0e, s->V, &cmin, &cmax));
-    LIFU_CHECK(reduce_minmax(s, s->d_alphae, s->V, &amin, &amax));
+    LIFU_CHECK(reduce_minmax(s, s->d_c0e, s->Vloc, &cmin, &cmax));
+    LIFU_CHECK(reduce_minmax(s, s->d_alphae, s->Vloc, &amin, &amax));
+    if (s->sl.on) {
+      float v[4] = {cmax, -cmin, amax, -amin};
+      LIFU_CHECK(slab_allreduce_max(s, v, 4));
+      cmax = v[0]; cmin = -v[1]; amax = v[2]; amin = -v[3];
+    }
     if (!(cmin > 0)) { set_error("lifu_set_medium: sound speed must be positive everywhere"); return LIFU_ERR_INVALID; }
     if (amin < 0) { set_error("lifu_set_medium: attenuation must be non-negative"); return LIFU_ERR_INVALID; }
     s->absorbing = amax != 0.f;
@@ -447,6 +534,20 @@ int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float
   }
   s->medium_set = true;
   return upload_source_points(s);
+}
+
+int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
+                    float alpha_power, int alpha_mode, int homogeneous) {
+  return set_medium_impl(s, c0, rho0, alpha_db, alpha_power, alpha_mode, homogeneous, 0, s ? s->n[2] : 0);
+}
+
+int lifu_set_medium_planes(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
+                           float alpha_power, int alpha_mode, int homogeneous, int32_t plane0, int32_t n_planes) {
+  if (s && !homogeneous && (plane0 < 0 || n_planes <= 0 || plane0 + n_planes > s->n[2])) {
+    set_error("lifu_set_medium_planes: planes [%d,%d) outside the inner grid (nz = %d)", plane0, plane0 + n_planes, s->n[2]);
+    return LIFU_ERR_INVALID;
+  }
+  return set_medium_impl(s, c0, rho0, alpha_db, alpha_power, alpha_mode, homogeneous, plane0, n_planes);
 }
 
 int lifu_set_elements(lifu_sim* s, int32_t n_el, const double* pos_m, const double* size_m,
@@ -730,6 +831,107 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   return LIFU_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// one time step of a z-slab decomposed grid (slab.cuh): same k-Wave step order (ledger A8), every 3-D
+// transform split into local 2-D transforms, an exchange over NVLink and local 1-D transforms.
+static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts,
+                             const std::function<void(const char*, double)>& mark) {
+  StepParams& P = s->P;
+  SlabCtx& L = s->sl;
+  cudaStream_t st = s->stream;
+  LIFU_CHECK(slab_plans(s));
+  LIFU_CUFFT(cufftSetStream(L.r2c2d, st)); LIFU_CUFFT(cufftSetStream(L.c2r2d, st)); LIFU_CUFFT(cufftSetStream(L.c2c1d, st));
+  const SlabParams S = SlabHost::params(s, false);
+  float2* H = S.H; float2* T = S.T;
+  const long long Hl = L.Hl;
+  const int gbh = grid_blocks(s, Hl, 256);
+  const int gbr = grid_blocks(s, s->Vloc, 256);
+  int nk = 0, nf = 0;
+  const int xk = L.exchange == 2 ? 1 : 2;                       // kernels per exchange
+  auto fft2_r2c = [&](float* r, float2* c) { ++nf; return cufftExecR2C(L.r2c2d, r, (cufftComplex*)c); };
+  auto fft2_c2r = [&](float2* c, float* r) { ++nf; return cufftExecC2R(L.c2r2d, (cufftComplex*)c, r); };
+  auto fftz = [&](float2* c, int dir) { ++nf; return cufftExecC2C(L.c2c1d, (cufftComplex*)c, (cufftComplex*)c, dir); };
+  // (1) pressure gradient: 1 field out, 2 fields back
+  LIFU_CUFFT(fft2_r2c(P.p, H));
+  mark("cufft2d_r2c_p", 8);
+  LIFU_CHECK(slab_exchange_fwd(s, 0, 1, 0)); nk += xk;
+  mark("xchg_fwd_p", 8);
+  LIFU_CUFFT(fftz(T, CUFFT_FORWARD));
+  k_slab_grad_z<<<gbh, 256, 0, st>>>(P, S); ++nk;
+  LIFU_CUFFT(fftz(T, CUFFT_INVERSE));
+  LIFU_CUFFT(fftz(T + Hl, CUFFT_INVERSE));
+  mark("z_grad", 4 + 12 + 16);
+  LIFU_CHECK(slab_exchange_back(s, 0, 2, 3, -1));                // T0 -> H3 (kappa p^, all x/y content), T1 -> H2 (d/dz)
+  nk += xk;
+  mark("xchg_back_grad", 16);
+  k_slab_grad_xy<<<gbh, 256, 0, st>>>(P, S); ++nk;
+  mark("k_slab_grad_xy", 12);
+  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_c2r(H + c * Hl, P.r3 + c * P.RS));
+  mark("cufft2d_c2r_grad_x3", 24);
+  if (s->N[0] % 4 == 0) launch_update_u<4>(s, grid_blocks(s, s->Vloc / 4, 256));
+  else launch_update_u<1>(s, gbr);
+  ++nk;
+  mark("k_update_u", s->homogeneous ? 36 : 48);
+  // (2) source field (built before the divergence so that it can ride the same exchange)
+  int src = 0;
+  if (src_active) {
+    if (L.src_i1 > L.src_i0) {
+      k_source_scatter<<<grid_blocks(s, L.src_i1 - L.src_i0, 128), 128, 0, st>>>(P, s->S); ++nk;
+    }
+    mark("k_source_scatter", 0);
+    src = s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2;
+  }
+  // (3) velocity divergence (+ k-space filtered source): 3 (4) fields out and back
+  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_r2c(P.u + c * P.RS, H + c * Hl));
+  if (src == 1) LIFU_CUFFT(fft2_r2c(P.S, H + 3 * Hl));
+  mark("cufft2d_r2c_u", 24 + (src == 1 ? 8 : 0));
+  const int nfld = src == 1 ? 4 : 3;
+  LIFU_CHECK(slab_exchange_fwd(s, 0, nfld, 1)); nk += xk;
+  mark("xchg_fwd_u", 8 * nfld);
+  for (int c = 0; c < nfld; ++c) LIFU_CUFFT(fftz(T + c * Hl, CUFFT_FORWARD));
+  k_slab_div_z<<<gbh, 256, 0, st>>>(P, S, src == 1 ? 1 : 0); ++nk;
+  for (int c = 0; c < nfld; ++c) LIFU_CUFFT(fftz(T + c * Hl, CUFFT_INVERSE));
+  mark("z_div", 16 * nfld);
+  LIFU_CHECK(slab_exchange_back(s, 0, nfld, 0, 1)); nk += xk;
+  mark("xchg_back_div", 8 * nfld);
+  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_c2r(H + c * Hl, P.r3 + c * P.RS));
+  if (src == 1) LIFU_CUFFT(fft2_c2r(H + 3 * Hl, P.Sf));
+  mark("cufft2d_c2r_div", 24 + (src == 1 ? 8 : 0));
+  // (4) density update, source, equation of state, sensor
+  if (s->homogeneous) {
+    if (src == 0) launch_rho_p<true, 0>(s, gbr); else if (src == 1) launch_rho_p<true, 1>(s, gbr); else launch_rho_p<true, 2>(s, gbr);
+  } else {
+    if (src == 0) launch_rho_p<false, 0>(s, gbr); else if (src == 1) launch_rho_p<false, 1>(s, gbr); else launch_rho_p<false, 2>(s, gbr);
+  }
+  ++nk;
+  mark("k_update_rho_p", (s->homogeneous ? 56 : 64) + (src ? 4 : 0));
+  if (s->absorbing) {
+    LIFU_CUFFT(fft2_r2c(P.r3, H));
+    LIFU_CUFFT(fft2_r2c(P.r3 + P.RS, H + Hl));
+    mark("cufft2d_r2c_absorb", 16);
+    LIFU_CHECK(slab_exchange_fwd(s, 0, 2, 0)); nk += xk;
+    mark("xchg_fwd_absorb", 16);
+    LIFU_CUFFT(fftz(T, CUFFT_FORWARD)); LIFU_CUFFT(fftz(T + Hl, CUFFT_FORWARD));
+    k_slab_absorb_z<<<gbh, 256, 0, st>>>(P, S); ++nk;
+    LIFU_CUFFT(fftz(T, CUFFT_INVERSE)); LIFU_CUFFT(fftz(T + Hl, CUFFT_INVERSE));
+    mark("z_absorb", 32);
+    LIFU_CHECK(slab_exchange_back(s, 0, 2, 0, 1)); nk += xk;
+    mark("xchg_back_absorb", 16);
+    LIFU_CUFFT(fft2_c2r(H, P.r3));
+    LIFU_CUFFT(fft2_c2r(H + Hl, P.r3 + P.RS));
+    mark("cufft2d_c2r_absorb", 16);
+    const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
+    if (s->homogeneous) k_pressure_absorb<true><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
+    else k_pressure_absorb<false><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
+    ++nk;
+    mark("k_pressure_absorb", s->homogeneous ? 32 : 44);
+  }
+  LIFU_CUDA(cudaGetLastError());
+  if (n_kernels) *n_kernels = nk;
+  if (n_ffts) *n_ffts = nf;
+  return LIFU_OK;
+}
+
 // Enqueue one time step on the handle's stream.  Counts hand-written kernels / FFT executions.
 static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts) {
   StepParams& P = s->P;
@@ -745,6 +947,7 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
     ++s->prof_used;
   };
   mark("begin", 0);
+  if (s->sl.on) return enqueue_step_slab(s, src_active, n_kernels, n_ffts, mark);
   if (s->last_used_v2) {
     int rc2 = enqueue_step_v2(s, src_active, n_kernels, mark);
     if (n_ffts) *n_ffts = 0;
@@ -868,8 +1071,10 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
               s->N[0], s->N[1], s->N[2]);
     return LIFU_ERR_STATE;
   }
-  s->last_used_v2 = v2_eligible(s);
-  if (s->last_used_v2) {
+  s->last_used_v2 = !s->sl.on && v2_eligible(s);
+  if (s->sl.on) {
+    LIFU_CHECK(slab_plans(s));
+  } else if (s->last_used_v2) {
     LIFU_CHECK(v2_setup(s));
   } else {
     LIFU_CHECK(build_plans(s));
@@ -878,7 +1083,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   }
   StepParams& P = s->P;
   SourceParams& S = s->S;
-  S.n_src = s->n_src; S.lin_exp = s->d_lin_exp; S.row_ptr = s->d_row_ptr; S.col = s->d_col; S.w = s->d_w;
+  S.n_src = s->sl.src_i1 - s->sl.src_i0; S.lin_exp = s->d_lin_exp; S.row_ptr = s->d_row_ptr + s->sl.src_i0; S.col = s->d_col; S.w = s->d_w;
   S.scale = s->d_scale; S.base = s->d_base; S.n_base = s->n_base; S.delay = s->d_delay; S.gain = s->d_gain;
 
   LIFU_CUDA(cudaEventRecord(s->ev[0], st));
@@ -893,8 +1098,8 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     LIFU_CUDA(cudaMemsetAsync(s->Q.Sslab, 0, sizeof(float) * (size_t)s->Q.nzs * s->N[1] * s->N[0], st));
     k2_pm_init<<<grid_blocks(s, s->V, 256), 256, 0, st>>>(s->Q.pm, s->V);
   }
-  k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmax, s->Vin, -INFINITY);
-  k_fill<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(P.pmin, s->Vin, INFINITY);
+  k_fill<<<grid_blocks(s, s->Vsens, 256), 256, 0, st>>>(P.pmax, s->Vsens, -INFINITY);
+  k_fill<<<grid_blocks(s, s->Vsens, 256), 256, 0, st>>>(P.pmin, s->Vsens, INFINITY);
   LIFU_CUDA(cudaGetLastError());
 
   const int nt = s->grid.nt;
@@ -938,8 +1143,8 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && s->last_used_v2) k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
-  if (rc == LIFU_OK && p_max) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
-  if (rc == LIFU_OK && p_min) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vin, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  if (rc == LIFU_OK && p_max && s->Vsens) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  if (rc == LIFU_OK && p_min && s->Vsens) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   cudaError_t se = cudaStreamSynchronize(st);
   for (int v = 0; v < 2; ++v) if (gexec[v]) cudaGraphExecDestroy(gexec[v]);
   if (rc == LIFU_ERR_CUDA && g_err.empty()) set_error("lifu_run: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
@@ -966,7 +1171,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
 int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, char* names, int name_stride,
                         double* ms, double* bytes_per_voxel, int* n_stages) {
   if (!s || reps <= 0 || !ms || !n_stages) { set_error("lifu_profile_stages: bad argument"); return LIFU_ERR_INVALID; }
-  if (!(s->plans_ready || s->v2_ready) || !s->medium_set || !s->geometry_set || !s->drive_set) {
+  if (!(s->plans_ready || s->v2_ready || s->sl.plans) || !s->medium_set || !s->geometry_set || !s->drive_set) {
     set_error("lifu_profile_stages: call lifu_run once first");
     return LIFU_ERR_STATE;
   }
@@ -1010,7 +1215,7 @@ int lifu_get_field(lifu_sim* s, int which, float* out) {
   if (!s || !out || which < 0 || which > 6) { set_error("lifu_get_field: bad argument"); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(s->device));
   const float* src = which == 0 ? s->P.p : (which <= 3 ? s->P.u + (which - 1) * s->RS : s->P.rho + (which - 4) * s->RS);
-  LIFU_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * s->V, cudaMemcpyDefault, s->stream));
+  LIFU_CUDA(cudaMemcpyAsync(out, src, sizeof(float) * s->Vloc, cudaMemcpyDefault, s->stream));
   LIFU_CUDA(cudaStreamSynchronize(s->stream));
   return LIFU_OK;
 }

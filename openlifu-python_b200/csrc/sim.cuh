@@ -2,6 +2,31 @@
 #pragma once
 #include "common.cuh"
 
+namespace lifu {
+// One rank's share of a z-slab decomposed grid (BASELINE.json config C5).
+struct SlabCtx {
+  bool on = false;
+  bool ready = false;               // creation completed on this rank (destroy then synchronises with the peers)
+  int rank = 0, G = 1;
+  int z0 = 0, Nzl = 0;              // expanded planes [z0, z0 + Nzl) live here
+  int Nyl = 0, ky0 = 0;             // ky rows [ky0, ky0 + Nyl) of the transposed spectra live here
+  int jz_lo = 0, jz_n = 0;          // inner (sensor) planes owned
+  int med_lo = 0, med_n = 0;        // inner planes of the medium maps this rank reads (incl. the +1 halo)
+  long long Vl = 0, Hl = 0;         // local real voxels, local half-spectrum elements (= transposed elements)
+  long long src_i0 = 0, src_i1 = 0; // this rank's range of the sorted source points
+  int exchange = 0;                 // 1 NCCL send/recv, 2 peer stores over NVLink (CUDA IPC)
+  void* comm = nullptr;             // ncclComm_t
+  float2* xbuf = nullptr;           // [ H x4 | T x4 ] one allocation so one IPC handle covers both
+  float2* pack = nullptr;           // [4][Hl] staging of the NCCL exchange
+  float2** d_peer = nullptr;        // device table [G] of every rank's xbuf (own entry = local pointer)
+  std::vector<void*> opened;        // IPC mappings to close
+  float* d_bar = nullptr;           // barrier / small reductions
+  cufftHandle r2c2d = 0, c2r2d = 0, c2c1d = 0;
+  bool plans = false;
+  void* d_fftwork = nullptr;
+};
+}  // namespace lifu
+
 struct lifu_sim {
   lifu_grid grid{};
   int device = 0;
@@ -10,7 +35,10 @@ struct lifu_sim {
 
   // geometry
   int N[3]{}, n[3]{}, pml[3]{}, Nxh = 0;
-  long long V = 0, Vh = 0, Vin = 0, RS = 0, CS = 0;
+  long long V = 0, Vin = 0;            // expanded / inner voxels of the WHOLE grid
+  long long Vloc = 0, Vsens = 0;       // voxels held here (== V, Vin unless this is one slab of a decomposed grid)
+  long long Vh = 0, RS = 0, CS = 0;    // local half-spectrum elements; strides between batched real / complex fields
+  cudaStream_t own_stream = nullptr;   // created when a slab handle was given the default stream
   double c_ref = 0.0;
   bool tables_ready = false;
 
@@ -76,6 +104,9 @@ struct lifu_sim {
   std::vector<cudaEvent_t> prof_ev;
   std::vector<const char*> prof_names;
   std::vector<double> prof_bytes;
+
+  // slab decomposition over several GPUs (slab.cuh); sl.on == false for the single-GPU paths
+  lifu::SlabCtx sl{};
 
   lifu_stats last{};
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};

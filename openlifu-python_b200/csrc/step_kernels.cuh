@@ -258,9 +258,9 @@ __global__ void __launch_bounds__(256) k_update_rho_p(StepParams P) {
     } else {
       float pv = c2 * sum;
       P.p[i] = pv;
-      int jx = ix - P.px, jy = iy - P.py, jz = iz - P.pz;
+      int jx = ix - P.px, jy = iy - P.py, jz = iz + P.z0 - P.pz;
       if ((unsigned)jx < (unsigned)P.nx && (unsigned)jy < (unsigned)P.ny && (unsigned)jz < (unsigned)P.nz) {
-        long long j = ((long long)jz * P.ny + jy) * P.nx + jx;
+        long long j = ((long long)(jz - P.jz0) * P.ny + jy) * P.nx + jx;
         P.pmax[j] = fmaxf(P.pmax[j], pv);
         P.pmin[j] = fminf(P.pmin[j], pv);
       }
@@ -309,9 +309,9 @@ __global__ void __launch_bounds__(256) k_pressure_absorb(StepParams P, int use_t
     if (use_eta) acc = acc - eta * P.r3[P.RS + i];
     float pv = c2 * acc;
     P.p[i] = pv;
-    int jx = ix - P.px, jy = iy - P.py, jz = iz - P.pz;
+    int jx = ix - P.px, jy = iy - P.py, jz = iz + P.z0 - P.pz;
     if ((unsigned)jx < (unsigned)P.nx && (unsigned)jy < (unsigned)P.ny && (unsigned)jz < (unsigned)P.nz) {
-      long long j = ((long long)jz * P.ny + jy) * P.nx + jx;
+      long long j = ((long long)(jz - P.jz0) * P.ny + jy) * P.nx + jx;
       P.pmax[j] = fmaxf(P.pmax[j], pv);
       P.pmin[j] = fminf(P.pmin[j], pv);
     }
@@ -326,16 +326,20 @@ __global__ void k_fill(float* a, long long n, float v) {
 }
 
 // Expand an inner-grid map to the PML-padded grid by edge replication (ledger A11).
-__global__ void k_expand_edge(const float* __restrict__ in, float* __restrict__ out, StepParams P) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P.V;
+// `in` holds the inner planes [plane0, ...); `out` receives n_planes expanded planes starting at the
+// global plane P.z0 (a slab rank asks for one halo plane more than it owns: staggered density along z).
+__global__ void k_expand_edge(const float* __restrict__ in, float* __restrict__ out, StepParams P, int plane0,
+                              int n_planes) {
+  const long long n = (long long)P.Nx * P.Ny * n_planes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     int ix = (int)(i % P.Nx);
     long long t = i / P.Nx;
     int iy = (int)(t % P.Ny);
-    int iz = (int)(t / P.Ny);
+    int iz = min((int)(t / P.Ny) + P.z0, P.NzG - 1);
     int jx = min(max(ix - P.px, 0), P.nx - 1);
     int jy = min(max(iy - P.py, 0), P.ny - 1);
-    int jz = min(max(iz - P.pz, 0), P.nz - 1);
+    int jz = min(max(iz - P.pz, 0), P.nz - 1) - plane0;
     out[i] = in[((long long)jz * P.ny + jy) * P.nx + jx];
   }
 }
@@ -357,7 +361,7 @@ __global__ void k_derive_medium(const float* __restrict__ c0e, const float* __re
     // staggered density: linear interpolation at +d/2, last plane keeps rho0 (ledger A9)
     double rx = ix + 1 < P.Nx ? 0.5 * (r + (double)rho0e[i + 1]) : r;
     double ry = iy + 1 < P.Ny ? 0.5 * (r + (double)rho0e[i + P.Nx]) : r;
-    double rz = iz + 1 < P.Nz ? 0.5 * (r + (double)rho0e[i + (long long)P.Nx * P.Ny]) : r;
+    double rz = iz + P.z0 + 1 < P.NzG ? 0.5 * (r + (double)rho0e[i + (long long)P.Nx * P.Ny]) : r;
     dt_rho0_sg[i] = (float)((double)dt / rx);
     dt_rho0_sg[P.RS + i] = (float)((double)dt / ry);
     dt_rho0_sg[2 * P.RS + i] = (float)((double)dt / rz);
@@ -381,7 +385,7 @@ __global__ void k_source_points(const long long* __restrict__ idx_inner, long lo
     long long t = l / P.nx;
     int jy = (int)(t % P.ny);
     int jz = (int)(t / P.ny);
-    long long e = ((long long)(jz + P.pz) * P.Ny + (jy + P.py)) * P.Nx + (jx + P.px);
+    long long e = ((long long)(jz + P.pz - P.z0) * P.Ny + (jy + P.py)) * P.Nx + (jx + P.px);   // local plane index
     lin_exp[i] = e;
     double c = c0e != nullptr ? (double)c0e[e] : (double)c0_s;
     scale[i] = (float)(2.0 * dt / (3.0 * c * dx));   // additive source scaling (ledger A6)

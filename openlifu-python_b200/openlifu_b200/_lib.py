@@ -39,6 +39,16 @@ class lifu_stats(C.Structure):
         return out
 
 
+class lifu_slab_desc(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("exchange", C.c_int32), ("nccl_id", C.c_ubyte * 128)]
+
+
+class lifu_slab_layout(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("exchange", C.c_int32), ("z0", C.c_int32), ("nz", C.c_int32),
+                ("sensor_z0", C.c_int32), ("sensor_nz", C.c_int32), ("medium_z0", C.c_int32), ("medium_nz", C.c_int32)]
+
+
+EXCHANGE_MODES = {"auto": 0, "nccl": 1, "peer": 2}
 ALPHA_MODES = {"binary": 0, "no_dispersion": 1, "no_absorption": 2}
 SOURCE_MODES = {"additive": 0, "additive-no-correction": 1}
 
@@ -53,6 +63,19 @@ def load():
     if not LIB_PATH.exists():
         raise LifuError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(nvcc, sm_100a). There is no CPU fallback for the simulation path.")
+    if "LIFU_NCCL_LIB" not in os.environ:
+        # slab decomposition dlopen()s NCCL: point it at the copy PyTorch bundles (a process can hold only one
+        # libnccl.so.2, and torch cannot be imported on top of an older system NCCL)
+        try:
+            import importlib.util
+            spec = importlib.util.find_spec("nvidia.nccl")
+            for base in (spec.submodule_search_locations if spec else []):
+                cand = Path(base) / "lib" / "libnccl.so.2"
+                if cand.exists():
+                    os.environ["LIFU_NCCL_LIB"] = str(cand)
+                    break
+        except Exception:  # noqa: BLE001
+            pass
     lib = C.CDLL(str(LIB_PATH))
     vp, i32, i64, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
     sig = {
@@ -73,6 +96,10 @@ def load():
         "lifu_get_info": (C.c_int, [vp, C.POINTER(lifu_stats)]),
         "lifu_profile_stages": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(f64),
                                           C.POINTER(f64), C.POINTER(C.c_int)]),
+        "lifu_slab_unique_id": (C.c_int, [C.POINTER(C.c_ubyte)]),
+        "lifu_create_slab": (C.c_int, [C.POINTER(lifu_grid), C.c_int, vp, C.POINTER(lifu_slab_desc), C.POINTER(vp)]),
+        "lifu_slab_layout_of": (C.c_int, [vp, C.POINTER(lifu_slab_layout)]),
+        "lifu_set_medium_planes": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, i32, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -87,7 +114,8 @@ def load():
 EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
             "lifu_set_medium", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info",
-            "lifu_profile_stages"]
+            "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
+            "lifu_set_medium_planes"]
 
 
 def _check(rc):
@@ -120,10 +148,19 @@ def pml_auto(n):
     return tuple(out)
 
 
-class LifuSim:
-    """One solver handle = one (device, stream).  Thin, typed wrapper over the C ABI."""
+def slab_unique_id() -> bytes:
+    """ncclUniqueId for a slab-decomposed solve: rank 0 makes it, every rank passes it to LifuSim(slab=...)."""
+    buf = (C.c_ubyte * 128)()
+    _check(load().lifu_slab_unique_id(buf))
+    return bytes(buf)
 
-    def __init__(self, n, d, dt, nt, pml=(-1, -1, -1), device=0, stream=0, pml_alpha=0.0, c_ref=0.0):
+
+class LifuSim:
+    """One solver handle = one (device, stream).  Thin, typed wrapper over the C ABI.
+    ``slab=(rank, nranks, nccl_id, exchange)`` makes it one rank's share of a z-slab decomposed grid
+    (collective creation; exchange: "auto" | "nccl" | "peer")."""
+
+    def __init__(self, n, d, dt, nt, pml=(-1, -1, -1), device=0, stream=0, pml_alpha=0.0, c_ref=0.0, slab=None):
         self._h = C.c_void_p()
         g = lifu_grid()
         g.n[:] = [int(v) for v in n]
@@ -132,7 +169,20 @@ class LifuSim:
         g.dt, g.nt, g.pml_alpha, g.c_ref = float(dt), int(nt), float(pml_alpha), float(c_ref)
         self.n = tuple(int(v) for v in n)
         self._lib = load()
-        _check(self._lib.lifu_create(C.byref(g), int(device), C.c_void_p(int(stream) or None), C.byref(self._h)))
+        self.layout = None
+        if slab is None:
+            _check(self._lib.lifu_create(C.byref(g), int(device), C.c_void_p(int(stream) or None), C.byref(self._h)))
+        else:
+            rank, nranks, nccl_id, exchange = (tuple(slab) + ("auto",))[:4]
+            sd = lifu_slab_desc()
+            sd.rank, sd.nranks = int(rank), int(nranks)
+            sd.exchange = EXCHANGE_MODES[exchange] if isinstance(exchange, str) else int(exchange)
+            sd.nccl_id[:] = list(bytes(nccl_id))
+            _check(self._lib.lifu_create_slab(C.byref(g), int(device), C.c_void_p(int(stream) or None), C.byref(sd),
+                                              C.byref(self._h)))
+            lay = lifu_slab_layout()
+            _check(self._lib.lifu_slab_layout_of(self._h, C.byref(lay)))
+            self.layout = {k: getattr(lay, k) for k, _ in lay._fields_}
         self._keep = []
 
     def close(self):
@@ -153,9 +203,11 @@ class LifuSim:
         self.close()
 
     # ------------------------------------------------------------------ medium
-    def set_medium(self, c0, rho0, alpha_db=None, alpha_power=0.9, alpha_mode="binary", device_ptrs=False):
+    def set_medium(self, c0, rho0, alpha_db=None, alpha_power=0.9, alpha_mode="binary", device_ptrs=False, plane0=None):
         """Scalars -> homogeneous; else (Nx,Ny,Nz) maps (any layout; converted to x-fastest float32)
-        or, with ``device_ptrs=True``, raw device pointers to x-fastest float32 inner-grid maps."""
+        or, with ``device_ptrs=True``, raw device pointers to x-fastest float32 inner-grid maps.
+        ``plane0``: the maps hold only the inner z planes [plane0, plane0 + maps.shape[2]) (slab handles:
+        see ``self.layout['medium_z0'/'medium_nz']``)."""
         mode = ALPHA_MODES[alpha_mode] if isinstance(alpha_mode, str) else int(alpha_mode)
         if device_ptrs:
             _check(self._lib.lifu_set_medium(self._h, _ptr(c0), _ptr(rho0), _ptr(alpha_db), alpha_power, mode, 0))
@@ -163,13 +215,21 @@ class LifuSim:
         homog = np.ndim(c0) == 0 and np.ndim(rho0) == 0 and (alpha_db is None or np.ndim(alpha_db) == 0)
         if homog:
             arrs = [np.array([v if v is not None else 0.0], dtype=np.float32) for v in (c0, rho0, alpha_db)]
+            _check(self._lib.lifu_set_medium(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power, mode, 1))
+            return
+        shape = self.n
+        if plane0 is not None:
+            nzp = max(np.shape(v)[2] for v in (c0, rho0, alpha_db) if np.ndim(v) == 3)
+            shape = (self.n[0], self.n[1], nzp)
+        arrs = []
+        for v in (c0, rho0, 0.0 if alpha_db is None else alpha_db):
+            full = np.broadcast_to(np.asarray(v, dtype=np.float32), shape)
+            arrs.append(np.ascontiguousarray(full.transpose(2, 1, 0)))   # x fastest
+        if plane0 is None:
+            _check(self._lib.lifu_set_medium(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power, mode, 0))
         else:
-            arrs = []
-            for v in (c0, rho0, 0.0 if alpha_db is None else alpha_db):
-                full = np.broadcast_to(np.asarray(v, dtype=np.float32), self.n)
-                arrs.append(np.ascontiguousarray(full.transpose(2, 1, 0)))   # x fastest
-        _check(self._lib.lifu_set_medium(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power, mode,
-                                         1 if homog else 0))
+            _check(self._lib.lifu_set_medium_planes(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power,
+                                                    mode, 0, int(plane0), int(shape[2])))
 
     # ------------------------------------------------------------------ source geometry
     def set_elements(self, pos_m, size_m, angle_deg, bli_tolerance=0.05, upsampling_rate=5):
@@ -210,7 +270,7 @@ class LifuSim:
     def run(self, p_max=None, p_min=None):
         """Run the time loop.  ``p_max``/``p_min``: None -> new numpy arrays are returned; numpy
         float32 arrays of Nx*Ny*Nz; or raw device pointers (ints)."""
-        nvox = int(np.prod(self.n))
+        nvox = int(np.prod(self.n)) if self.layout is None else self.n[0] * self.n[1] * self.layout["sensor_nz"]
         own = p_max is None
         if own:
             p_max = np.empty(nvox, dtype=np.float32)
@@ -222,9 +282,11 @@ class LifuSim:
     def get_field(self, which):
         st = lifu_stats()
         _check(self._lib.lifu_get_info(self._h, C.byref(st)))
-        out = np.empty(int(st.voxels), dtype=np.float32)
-        _check(self._lib.lifu_get_field(self._h, int(which), _ptr(out)))
         N = list(st.n_exp)
+        if self.layout is not None:
+            N[2] = self.layout["nz"]
+        out = np.empty(int(np.prod(N)), dtype=np.float32)
+        _check(self._lib.lifu_get_field(self._h, int(which), _ptr(out)))
         return out.reshape(N[2], N[1], N[0]).transpose(2, 1, 0)
 
     def profile_stages(self, reps=5, with_source=True, max_stages=32):

@@ -107,3 +107,49 @@ def csr_to_dense(n_src, n_el, row_ptr, col, w):
     for i in range(n_src):
         W[i, col[row_ptr[i]:row_ptr[i + 1]]] = w[row_ptr[i]:row_ptr[i + 1]]
     return W
+
+
+def layered_phantom(N):
+    """Layered water / skull-like slab / tissue phantom with per-material c, rho, alpha."""
+    c0 = np.full(N, 1500.0)
+    rho0 = np.full(N, 1000.0)
+    al = np.full(N, 0.0022)
+    z = np.arange(N[2])[None, None, :] + 0 * np.arange(N[0])[:, None, None]
+    x = np.arange(N[0])[:, None, None]
+    slab = np.broadcast_to((z + (x // 6) >= 12) & (z + (x // 6) < 16), N)
+    tissue = np.broadcast_to((z + (x // 6)) >= 16, N)
+    c0[slab], rho0[slab], al[slab] = 2800.0, 1900.0, 6.0
+    c0[tissue], rho0[tissue], al[tissue] = 1540.0, 1050.0, 0.3
+    return c0, rho0, al
+
+
+def run_cuda_case_slab(case, rank, world, nccl_id, exchange="auto", alpha_mode="binary", source_mode="additive",
+                       max_steps=None, device=0, fields=()):
+    """One rank's share of the same scene on a z-slab decomposed grid (C ABI: lifu_create_slab ...).
+    Returns this rank's inner planes of p_max / p_min (x fastest) and the layout."""
+    from openlifu_b200 import _lib
+
+    sc = scene_of(case)
+    N, d, Nt, dt = osc.time_axis(sc, case["dt"], case["t_end"], 0.5)
+    if max_steps is not None:
+        Nt = min(Nt, max_steps)
+    offset = np.array([-float(np.mean(c)) * 1e-3 for c in case["coords"]])
+    t = np.arange(0, case["cycles"] / case["freq"], dt)
+    base = case["amplitude"] * np.sin(2 * np.pi * case["freq"] * t)
+    if case["sensitivity"] is not None:
+        base = base * case["sensitivity"]
+    n_delay = np.array([int(dl / dt) for dl in case["delays"]], dtype=np.int32)
+    with _lib.LifuSim(N, d, dt, Nt, device=device, slab=(rank, world, nccl_id, exchange)) as sim:
+        lay = dict(sim.layout)
+        if np.ndim(case["c0"]) == 0 and np.ndim(case["rho0"]) == 0 and np.ndim(case["alpha"]) == 0:
+            sim.set_medium(case["c0"], case["rho0"], case["alpha"], alpha_power=0.9, alpha_mode=alpha_mode)
+        else:
+            lo, n = lay["medium_z0"], lay["medium_nz"]
+            maps = [np.broadcast_to(np.asarray(m, dtype=np.float64), tuple(N))[:, :, lo:lo + n]
+                    for m in (case["c0"], case["rho0"], case["alpha"])]
+            sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode, plane0=lo)   # only the planes this rank reads
+        sim.set_elements(case["pos_m"] + offset, case["size_m"], case["angles_deg"], 0.05, 5)
+        sim.set_drive(base, n_delay, case["apod"], source_mode=source_mode)
+        p_max, p_min, stats = sim.run()
+        extra = {f"field{k}": sim.get_field(k) for k in fields}
+    return {**extra, "p_max": p_max, "p_min": p_min, "stats": stats, "layout": lay, "N": N, "Nt": Nt}
