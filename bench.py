@@ -55,6 +55,23 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `stage`, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json); None when that kernel has not been captured."""
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    if not f.exists():
+        return None
+    try:
+        ks = json.loads(f.read_text())["kernels"]
+    except Exception:  # noqa: BLE001
+        return None
+    hits = [v for k, v in ks.items() if k.split("<")[0] == stage]
+    if not hits:
+        return None
+    v = max(hits, key=lambda h: h["dram_read_MB"] + h["dram_write_MB"])
+    return (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -191,13 +208,148 @@ def workload_name(args):
             + (" -> 256^3 with PML, Nt=749" if n == 216 else ""))
 
 
+def c5_scene(n_inner):
+    """SURVEY.md config C5 at a given inner size: 0.5 mm * 216 / n spacing (0.25 mm-class at 728 -> 768^3 with
+    PML), C3 phantom scaled to the grid, the 2x64-element array at its physical size, focus (0,0,50) mm."""
+    from openlifu_b200 import configs
+    from openlifu_b200.bf import delay_methods
+    from openlifu_b200.geo import Point
+    arr = configs.openlifu_2x_array()
+    sp = 0.5 * 216.0 / n_inner if n_inner > 216 else 0.5          # mm
+    half = (n_inner - 1) * sp / 2.0
+    x = np.linspace(-half, half, n_inner)
+    z = np.linspace(-4.0, -4.0 + 2 * half, n_inner)
+    return arr, sp, x, x.copy(), z
+
+
+def c5_medium_planes(x, y, z_planes, scale):
+    """c, rho, alpha of the skull/brain phantom (configs.skull_phantom_labels + PHANTOM_MATERIALS) on a plane range."""
+    from openlifu_b200.configs import PHANTOM_MATERIALS as M
+    r = np.sqrt(x[:, None, None] ** 2 + y[None, :, None] ** 2 + (z_planes[None, None, :] - 70.0 * scale) ** 2)
+    out = []
+    for key in ("sound_speed", "density", "attenuation"):
+        w, t, k = (getattr(M[m], key) for m in ("water", "tissue", "skull"))
+        a = np.full(r.shape, w, dtype=np.float32)
+        a[r < 56.0 * scale] = t
+        a[(r >= 56.0 * scale) & (r <= 62.0 * scale)] = k
+        out.append(a)
+    return out
+
+
+def run_slab(args, rank, local_rank, world):
+    """--workload C5: ONE grid decomposed into z slabs over all ranks (strong scaling of a single simulation)."""
+    import torch
+    import torch.distributed as dist
+    from openlifu_b200 import _lib
+    from openlifu_b200.sim.kwave_if import element_geometry
+    n = args.n_inner if args.n_inner != 216 or world == 1 else 728
+    arr, sp, x, y, z = c5_scene(n)
+    d = [sp * 1e-3] * 3
+    nt_full, dt = _lib.make_time([n] * 3, d, 1500.0, 0.5)
+    nt = min(nt_full, args.time_steps)
+    ids = [_lib.slab_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(ids, src=0)
+    stream = torch.cuda.Stream()
+    sim = _lib.LifuSim([n] * 3, d, dt, nt, device=local_rank, stream=stream.cuda_stream,
+                       slab=(rank, world, ids[0], args.exchange))
+    lay = sim.layout
+    if args.homogeneous:
+        sim.set_medium(1500.0, 1000.0, 0.0, alpha_power=0.9)
+    else:
+        lo, nz = lay["medium_z0"], lay["medium_nz"]
+        maps = c5_medium_planes(x, y, z[lo:lo + nz], (n * sp) / 108.0)
+        sim.set_medium(*maps, alpha_power=0.9, plane0=lo)
+        del maps
+    offset = [-float(np.mean(c)) * 1e-3 for c in (x, y, z)]
+    pos, size, ang = element_geometry(arr, offset)
+    n_src = sim.set_elements(pos, size, ang, 0.05, 5)
+    from openlifu_b200.bf import delay_methods
+    from openlifu_b200.geo import Point
+    delays = delay_methods.Direct().calc_delays(arr, Point(position=(0, 0, 50), units="mm"))
+    freq, cycles = 400e3, 20
+    base = np.sin(2 * np.pi * freq * np.arange(0, cycles / freq, dt))
+    n_delay, gains, base_gain = arr.drive_plan(dt, delays, np.ones(arr.numelements()))
+    sim.set_drive(base * base_gain, n_delay, gains)
+    nloc = n * n * lay["sensor_nz"]
+    d_pmax = torch.empty(max(nloc, 1), dtype=torch.float32, device="cuda")
+    d_pmin = torch.empty(max(nloc, 1), dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    st = None
+    for _ in range(args.warmup):
+        st = sim.run(d_pmax.data_ptr(), d_pmin.data_ptr())[2]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = ffts = 0
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            st = sim.run(d_pmax.data_ptr(), d_pmin.data_ptr())[2]
+            launches += st["kernel_launches"]; ffts += st["fft_launches"]
+        ev1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ev0.elapsed_time(ev1), st["loop_ms"]], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total, loop_ms = float(tt[0].item()), float(tt[1].item())
+    V, Nt = st["voxels"], st["steps"]
+    value = V * Nt * args.steps / (ms_total * 1e-3) / 1e6
+    peak, peak_src = measured_peak_gbs()
+    prof = sim.profile_stages(reps=3, with_source=True)            # collective: every rank steps together
+    checksum = torch.tensor([float(d_pmax[:nloc].double().sum().item()) if nloc else 0.0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(checksum)
+    sim.close()
+    if rank != 0:
+        return
+    tot = sum(ms for _, ms, _ in prof)
+    Vl = V / world
+    own = [(nm, ms, b) for nm, ms, b in prof if nm.startswith(("k_", "xchg")) and b > 0]
+    name, ms, bpv = max(own, key=lambda r: r[1])
+    ach = bpv * Vl / (ms * 1e-3) / 1e9
+    xchg_ms = sum(ms for nm, ms, _ in prof if nm.startswith("xchg"))
+    xchg_bytes = sum(b for nm, _, b in prof if nm.startswith("xchg")) * Vl * (world - 1) / world
+    step_bps = st["bytes_per_voxel_step"] * V * Nt / (loop_ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C5: one {st['n_exp'][0]}^3 grid ({n}^3 inner) "
+                                   f"{'water' if args.homogeneous else 'skull/brain phantom (c, rho, alpha maps)'}, "
+                                   f"z-slab decomposed over {world} GPU(s), {Nt} of {nt_full} time steps per bench step",
+                       "voxels": V, "time_steps": Nt, "n_src": int(n_src), "exchange": {1: "nccl", 2: "peer stores"}[lay["exchange"]],
+                       "l2": "per-rank working set exceeds the 126 MB L2; no flush needed",
+                       "fft": "cuFFT 2-D (x,y) + exchange + cuFFT 1-D z", "checksum_p_max": float(checksum.item())},
+            "e2e": None, "gpu_launches": int(launches), "fft_launches": int(ffts), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_voxel": bpv, "kernel_ms": ms,
+                         "share_of_step": ms / tot,
+                         "step": {"algorithmic_bytes_per_voxel_step": st["bytes_per_voxel_step"],
+                                  "achieved_all_gpus": step_bps, "frac_of_n_gpus_peak": step_bps / (peak * world)},
+                         "exchange": {"ms_per_time_step": xchg_ms, "nvlink_GBps_per_gpu": (xchg_bytes / (xchg_ms * 1e-3) / 1e9) if xchg_ms > 0 else None}},
+            "cpu_baseline": None,
+            "stages": [{"stage": nm, "ms": round(ms, 4)} for nm, ms, _ in prof]}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3"])
+    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C5"])
+    ap.add_argument("--time-steps", type=int, default=40, help="C5: time steps per bench step (throughput is per step)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "peer"], help="C5: FFT transpose transport")
+    ap.add_argument("--homogeneous", action="store_true", help="C5: water instead of the skull/brain phantom")
     ap.add_argument("--n-inner", type=int, default=216)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -224,6 +376,11 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
+    if args.workload == "C5":
+        run_slab(args, rank, local_rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     from openlifu_b200 import _lib
     from openlifu_b200.sim import kwave_if
     from openlifu_b200.sim.kwave_if import element_geometry, get_kgrid
@@ -303,7 +460,9 @@ def main():
         name, ms, bpv = max(own, key=lambda r: r[1])
         ach = bpv * V / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_voxel": bpv,
+                    "traffic": ncu_traffic_bytes(name), "algorithmic_bytes": bpv * V,
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this kernel, bytes per launch)",
+                    "peak_source": peak_src, "algorithmic_bytes_per_voxel": bpv,
                     "kernel_ms": ms, "share_of_step": ms / tot,
                     "step": {"algorithmic_bytes_per_voxel_step": st["bytes_per_voxel_step"],
                              "achieved": st["bytes_per_voxel_step"] * V * Nt / (st["loop_ms"] * 1e-3) / 1e9,

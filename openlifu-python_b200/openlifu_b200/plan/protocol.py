@@ -250,6 +250,8 @@ class Protocol:
             return ds
 
         world, rank = _dist_world()
+        if world > 1 and kwave_if.multi_gpu_mode()[0] == "slab":
+            world = 1                   # the ranks share every simulation (slab decomposition): same loop on all of them
         if world > 1 and len(beams) > 1:
             # one process per GPU (torchrun): rank r simulates foci r, r + world, ...; the fields are
             # all-gathered so that every rank holds the full stack, as the reference's serial loop would

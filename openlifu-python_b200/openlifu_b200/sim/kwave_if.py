@@ -82,27 +82,74 @@ def _sample_checksum(a: np.ndarray) -> int:
     return zlib.adler32(np.ascontiguousarray(flat[::step]).tobytes()) ^ flat.size
 
 
+def multi_gpu_mode():
+    """How a torch.distributed job uses its ranks (``LIFU_MULTI_GPU``): ``"foci"`` (default) -- every
+    ``run_simulation`` call is one rank's own simulation, sweeps are sharded by ``Protocol``; ``"slab"``
+    -- every rank calls ``run_simulation`` with the SAME arguments and the grid is decomposed into z
+    slabs over the ranks (grids too large for one GPU).  Returns (mode, world, rank)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            mode = os.environ.get("LIFU_MULTI_GPU", "foci")
+            if mode not in ("foci", "slab"):
+                raise ValueError(f"LIFU_MULTI_GPU must be 'foci' or 'slab', got {mode!r}")
+            return mode, dist.get_world_size(), dist.get_rank()
+    except ImportError:
+        pass
+    return "foci", 1, 0
+
+
 class _Session:
     """Solver handle and what is cached on it."""
 
-    def __init__(self, key, kg, device):
+    def __init__(self, key, kg, device, slab=None):
         self.key = key
-        self.sim = _lib.LifuSim(kg["N"], kg["d"], kg["dt"], kg["Nt"], device=device)
+        self.sim = _lib.LifuSim(kg["N"], kg["d"], kg["dt"], kg["Nt"], device=device, slab=slab)
         self.geometry_key = None
         self.medium_key = None
         self.n_src = 0
 
 
-def _session(kg, device):
-    key = (tuple(kg["N"]), tuple(kg["d"]), kg["dt"], kg["Nt"], device)
+def _session(kg, device, slab_world=1, slab_rank=0):
+    key = (tuple(kg["N"]), tuple(kg["d"]), kg["dt"], kg["Nt"], slab_world, device)
     with _LOCK:
         s = _SESSIONS.get(key)
         if s is None:
             mine = [k for k in _SESSIONS if k[-1] == device]
             while len(mine) >= _MAX_SESSIONS:
                 _SESSIONS.pop(mine.pop(0)).sim.close()
-            s = _SESSIONS[key] = _Session(key, kg, device)
+            slab = None
+            if slab_world > 1:
+                # collective: every rank reaches this point with the same key (same arguments by contract)
+                import torch.distributed as dist
+                ids = [_lib.slab_unique_id() if slab_rank == 0 else None]
+                dist.broadcast_object_list(ids, src=0)
+                slab = (slab_rank, slab_world, ids[0], os.environ.get("LIFU_SLAB_EXCHANGE", "auto"))
+            s = _SESSIONS[key] = _Session(key, kg, device, slab=slab)
     return s
+
+
+def _gather_planes(local, layout, n, world):
+    """All-gather the ranks' inner planes of a sensor vector (ragged along z) into the full x-fastest vector."""
+    import torch
+    import torch.distributed as dist
+    plane = n[0] * n[1]
+    on_gpu = dist.get_backend() == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    meta = torch.tensor([layout["sensor_z0"], layout["sensor_nz"]], dtype=torch.int64, device=dev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta)
+    metas = [tuple(int(v) for v in m.tolist()) for m in metas]
+    cap = max(nz for _, nz in metas) * plane
+    send = torch.zeros(cap, dtype=torch.float32, device=dev)
+    send[:local.size] = torch.from_numpy(local).to(dev)
+    recv = torch.empty(world * cap, dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(recv, send)
+    recv = recv.cpu().numpy().reshape(world, cap)
+    out = np.empty(plane * n[2], dtype=np.float32)
+    for r, (z0, nz) in enumerate(metas):
+        out[z0 * plane:(z0 + nz) * plane] = recv[r, :nz * plane]
+    return out
 
 
 def clear_sessions():
@@ -148,7 +195,9 @@ def run_simulation(arr,
     scl = getunitconversion(_same_units([params[d] for d in params.dims], "dimensions"), "m")
     array_offset: List[float] = [-float(c.mean()) * scl for c in params.coords.values()]
 
-    ses = _session(kg, _device())
+    mode, world, rank = multi_gpu_mode()
+    slab = mode == "slab"
+    ses = _session(kg, _device(), world if slab else 1, rank)
     sim = ses.sim
     # medium (get_medium, kwave_if.py:49-63): alpha_power 0.9; alpha_mode='no_dispersion' is what the
     # reference asks for but the k-Wave binary only receives alpha_coeff/alpha_power (ledger A7)
@@ -164,6 +213,9 @@ def run_simulation(arr,
         if ses.medium_key != mkey:
             if all(float(m.min()) == float(m.max()) for m in maps):
                 sim.set_medium(*[float(m.flat[0]) for m in maps], alpha_power=0.9, alpha_mode=alpha_mode)
+            elif slab:
+                lo, nz = sim.layout["medium_z0"], sim.layout["medium_nz"]      # only the planes this rank reads
+                sim.set_medium(*[m[:, :, lo:lo + nz] for m in maps], alpha_power=0.9, alpha_mode=alpha_mode, plane0=lo)
             else:
                 sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode)
     ses.medium_key = mkey
@@ -179,6 +231,9 @@ def run_simulation(arr,
                   source_mode=os.environ.get("LIFU_SOURCE_MODE", "additive"))
     log.info("Running simulation")
     p_max_flat, p_min_flat, stats = sim.run()
+    if slab:
+        p_max_flat = _gather_planes(p_max_flat, sim.layout, kg["N"], world)
+        p_min_flat = _gather_planes(p_min_flat, sim.layout, kg["N"], world)
     log.info("Simulation Complete")
     output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
               "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}

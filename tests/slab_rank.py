@@ -33,6 +33,49 @@ def build_case(name, steps):
     return case
 
 
+def api_main(args, rank, world, local):
+    """Public API: every rank calls run_simulation with the same arguments; the Dataset comes back whole."""
+    import torch.distributed as dist
+    from openlifu_b200.geo import Point
+    from openlifu_b200.seg import seg_methods
+    from openlifu_b200.sim import SimSetup, kwave_if
+    from openlifu_b200.bf import delay_methods
+    from openlifu_b200.xdc import Transducer
+    from tests import cases
+    os.environ["LIFU_DEVICE"] = str(local)
+    arr = Transducer.gen_matrix_array(nx=2, ny=2, pitch=3, kerf=0.5, units="mm", sensitivity=1e5)
+    setup = SimSetup(spacing=1, x_extent=(-20, 19), y_extent=(-22, 21), z_extent=(-3, 32), dt=3e-7, t_end=args.steps * 3e-7)
+    params = setup.setup_sim_scene(seg_methods.UniformWater())
+    if args.case == "phantom":
+        c0, rho0, al = cases.layered_phantom(tuple(params["sound_speed"].data.shape))
+        params["sound_speed"].data[...] = c0
+        params["density"].data[...] = rho0
+        params["attenuation"].data[...] = al
+    delays = delay_methods.Direct().calc_delays(arr, Point(position=(0, 0, 18), units="mm"), params)
+    kw = dict(arr=arr, params=params, delays=delays, apod=np.ones(4), freq=400e3, cycles=2, dt=setup.dt, t_end=setup.t_end)
+    os.environ["LIFU_MULTI_GPU"] = "slab"
+    os.environ["LIFU_SLAB_EXCHANGE"] = args.exchange
+    ds, out = kwave_if.run_simulation(**kw)
+    ds2, _ = kwave_if.run_simulation(**kw)                       # cached handle, second collective run
+    os.environ["LIFU_MULTI_GPU"] = "foci"
+    os.environ["LIFU_PIPELINE"] = "v1"
+    one, _ = kwave_if.run_simulation(**kw)                       # this rank alone on its own GPU
+    res = {"case": args.case, "world": world, "api": True, "shape": list(ds["p_min"].data.shape),
+           "vs_single": {k: cases.rel_l2(ds[k].data, one[k].data) for k in ("p_max", "p_min", "intensity")},
+           "repeat_equal": bool(np.array_equal(ds["p_min"].data, ds2["p_min"].data)),
+           "finite": bool(np.isfinite(ds["p_max"].data).all())}
+    allres = [None] * world
+    dist.all_gather_object(allres, res)
+    kwave_if.clear_sessions()
+    if rank == 0:
+        res["all_ranks_vs_single"] = [max(r["vs_single"].values()) for r in allres]
+        print(json.dumps(res), flush=True)
+        if args.out:
+            Path(args.out).write_text(json.dumps(res))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--case", default="water")
@@ -40,6 +83,7 @@ def main():
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--out", default="")
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--api", action="store_true", help="go through openlifu_b200.sim.run_simulation (LIFU_MULTI_GPU=slab)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -48,6 +92,8 @@ def main():
     dist.init_process_group("gloo")                               # plumbing only: id broadcast + result gather
     from openlifu_b200 import _lib
     from tests import cases
+    if args.api:
+        return api_main(args, rank, world, local)
     ids = [_lib.slab_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     case = build_case(args.case, args.steps)

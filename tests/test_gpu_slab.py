@@ -80,3 +80,20 @@ def test_two_rank_slab(lifu_lib, tmp_path, case, exchange):
     for k in ("p_max", "p_min"):
         assert res["vs_single"][k] < 1e-5, res
         assert res["vs_oracle"][k] < TOL, res
+
+
+@pytest.mark.parametrize("case", ["water", "phantom"])
+def test_two_rank_run_simulation_slab_mode(lifu_lib, tmp_path, case):
+    """openlifu_b200.sim.run_simulation with LIFU_MULTI_GPU=slab: same call on every rank, whole Dataset back."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    out = tmp_path / "res.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(_free_port()), str(ROOT / "tests" / "slab_rank.py"), "--case", case,
+           "--api", "--out", str(out)]
+    r = subprocess.run(cmd, cwd=str(ROOT), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = json.loads(out.read_text())
+    assert res["finite"] and res["repeat_equal"] and res["shape"] == [40, 44, 36]
+    assert max(res["all_ranks_vs_single"]) < 1e-5, res
