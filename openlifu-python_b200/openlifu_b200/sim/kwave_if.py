@@ -107,6 +107,7 @@ class _Session:
         self.sim = _lib.LifuSim(kg["N"], kg["d"], kg["dt"], kg["Nt"], device=device, slab=slab)
         self.geometry_key = None
         self.medium_key = None
+        self.uniform = {}              # medium key -> "all three maps are constant" (decided once per maps object)
         self.n_src = 0
 
 
@@ -211,7 +212,9 @@ def run_simulation(arr,
         maps = [params[k].data for k in names]
         mkey = ("map",) + tuple((id(m), _sample_checksum(m)) for m in maps) + (alpha_mode,)
         if ses.medium_key != mkey:
-            if all(float(m.min()) == float(m.max()) for m in maps):
+            if mkey not in ses.uniform:
+                ses.uniform = {mkey: all(float(m.min()) == float(m.max()) for m in maps)}
+            if ses.uniform[mkey]:
                 sim.set_medium(*[float(m.flat[0]) for m in maps], alpha_power=0.9, alpha_mode=alpha_mode)
             elif slab:
                 lo, nz = sim.layout["medium_z0"], sim.layout["medium_nz"]      # only the planes this rank reads
@@ -241,15 +244,39 @@ def run_simulation(arr,
     return package_fields(params, output["p_max"], output["p_min"]), output
 
 
+_Z2_CACHE: dict = {}
+
+
+def _two_z_flat(params):
+    """2 * density * sound_speed (float64) flattened x fastest, cached per params maps (identity + sampled checksum)."""
+    rho, c = params["density"].data, params["sound_speed"].data
+    key = (id(rho), id(c), _sample_checksum(rho), _sample_checksum(c))
+    hit = _Z2_CACHE.get(key)
+    if hit is None:
+        if len(_Z2_CACHE) >= 4:
+            _Z2_CACHE.clear()
+        hit = _Z2_CACHE[key] = np.ascontiguousarray((2 * (rho * c)).transpose(2, 1, 0)).reshape(-1)
+    return hit
+
+
 def package_fields(params, p_max_flat, p_min_flat):
-    """Flat x-fastest float32 sensor vectors -> the Dataset of kwave_if.py:131-146 (p_min sign flip,
-    float64 intensity named 'I' under the key 'intensity')."""
+    """Flat x-fastest float32 sensor vectors -> the Dataset of kwave_if.py:131-146: p_max; p_min = -p_min;
+    intensity = 1e-4 * p_min**2 / (2 * density * sound_speed) as float64 named 'I' under the key 'intensity'.
+    Same IEEE operations in the same precisions as the reference's numpy expression (float32 square and
+    scale, float64 divide), evaluated on flat x-fastest vectors with all host threads."""
     sz = list(params.coords.sizes.values())
+    try:
+        import torch
+        tp = torch.from_numpy(p_min_flat)
+        neg = torch.neg(tp).numpy()
+        inten = ((torch.square(tp) * np.float32(1e-4)).double() / torch.from_numpy(_two_z_flat(params))).numpy()
+    except ImportError:
+        neg = -1 * p_min_flat
+        inten = (np.float32(1e-4) * p_min_flat ** 2) / _two_z_flat(params)
     p_max = xa.DataArray(p_max_flat.reshape(sz, order="F"), coords=params.coords, name="p_max",
                          attrs={"units": "Pa", "long_name": "PPP"})
-    p_min = xa.DataArray(-1 * p_min_flat.reshape(sz, order="F"), coords=params.coords, name="p_min",
+    p_min = xa.DataArray(neg.reshape(sz, order="F"), coords=params.coords, name="p_min",
                          attrs={"units": "Pa", "long_name": "PNP"})
-    Z = params["density"].data * params["sound_speed"].data
-    intensity = xa.DataArray(1e-4 * p_min_flat.reshape(sz, order="F") ** 2 / (2 * Z), coords=params.coords,
-                             name="I", attrs={"units": "W/cm^2", "long_name": "Intensity"})
+    intensity = xa.DataArray(inten.reshape(sz, order="F"), coords=params.coords, name="I",
+                             attrs={"units": "W/cm^2", "long_name": "Intensity"})
     return xa.Dataset({"p_max": p_max, "p_min": p_min, "intensity": intensity})

@@ -110,3 +110,23 @@ def test_xa_shim_surface():
     line = a.interp(x=xa.DataArray([0.5, 1.5], coords={"s": [0.0, 1.0]}), y=xa.DataArray([0.5, 0.5], coords={"s": [0.0, 1.0]}))
     assert line.dims == ("s",) and np.allclose(line.data, [1.5, 3.5])
     assert (a * xa.DataArray(np.array([1.0, 2.0]), dims=("y",))).shape == (3, 2)
+
+
+def test_package_fields_matches_reference_expression_bitwise():
+    """The packaging step (kwave_if.py:131-146) is evaluated with threaded flat-vector ops; values must equal the
+    reference's literal numpy expression bit for bit, dtypes and names included."""
+    from openlifu_b200 import configs
+    from openlifu_b200.sim import kwave_if
+    params = configs.prepare(configs.c3(24))[0]
+    sz = tuple(params.coords.sizes.values())
+    rng = np.random.default_rng(147)
+    p_max = (rng.random(int(np.prod(sz))) * 3e5).astype(np.float32)
+    p_min = (-rng.random(int(np.prod(sz))) * 3e5).astype(np.float32)
+    ds = kwave_if.package_fields(params, p_max, p_min)
+    Z = params["density"].data * params["sound_speed"].data
+    assert np.array_equal(ds["p_max"].data, p_max.reshape(sz, order="F")) and ds["p_max"].data.dtype == np.float32
+    assert np.array_equal(ds["p_min"].data, -1 * p_min.reshape(sz, order="F")) and ds["p_min"].data.dtype == np.float32
+    want = 1e-4 * p_min.reshape(sz, order="F") ** 2 / (2 * Z)
+    assert ds["intensity"].data.dtype == np.float64 and np.array_equal(ds["intensity"].data, want)
+    assert ds["p_min"].attrs == {"units": "Pa", "long_name": "PNP"} and ds["intensity"].attrs["units"] == "W/cm^2"
+    ds["p_min"].data *= 2.0          # Solution.scale works in place: the arrays must be writable
