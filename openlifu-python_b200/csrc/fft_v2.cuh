@@ -188,7 +188,7 @@ __device__ __forceinline__ void merge_store(float2* __restrict__ zp, const float
 // ------------------------------------------------------------------------------------------------
 // y forward: packed row pairs -> half spectrum.  grid (nxt+1, Nz | Nz/16.., ncomp)
 // MODE 0: pressure (no multipliers)   MODE 1: velocity (comp 0: i kx e^{-i kx dx/2}; comp 1: i ky e^{-i ky dy/2})
-// MODE 2: source slab (z index relative to the slab)
+// MODE 2: source slab (z index relative to the slab)      MODE 3: Z4[comp] without multipliers (absorption operands)
 template <int R, int MODE>
 __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
   const int zc = live ? z : nz - 1;
   const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
   float2* xa = reinterpret_cast<float2*>(smraw);
-  const float2* Zin = MODE == 0 ? Q.ZP : (MODE == 1 ? Q.Z4 + comp * Q.ZS : Q.ZSslab);
+  const float2* Zin = MODE == 0 ? Q.ZP : ((MODE == 1 || MODE == 3) ? Q.Z4 + comp * Q.ZS : Q.ZSslab);
   float2* Hout = MODE == 2 ? Q.HSslab : Q.H4 + comp * Q.HS;
   const int km = (Q.Nx - kx) & (Q.Nx - 1);
   const float2* zp = Zin + ((long long)zc * (Q.Ny / 2) + t) * Q.Nx;     // packed line m = q*R + t
@@ -354,6 +354,46 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P
     } else {
 #pragma unroll
       for (int k1 = 0; k1 < R; ++k1) v[k1] = cscale(v[k1], cosk_sel<POLY>(axy + P.az2[t + R * k1]) * Q.norm);
+    }
+    strided_fft<R, true>(v, tw, xb, l, t);
+    float2* op = hp + comp * Q.HS;
+#pragma unroll
+    for (int j = 0; j < R; ++j) op[j * jstep] = v[j];
+#pragma unroll
+    for (int j = 0; j < R; ++j) v[j] = nx[j];
+  }
+}
+
+
+// z pass of the absorption operands (in place): H4[0] <- IFFT_z[k^(y-2) FFT_z H4[0]], H4[1] <- IFFT_z[k^(y-1) FFT_z H4[1]]
+// (the fractional Laplacians of the power-law absorption / dispersion terms).  grid (nxt+1, Ny)
+template <int R>
+__global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_absorb(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
+  const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
+  int kx, ky;
+  if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
+  const int zs = Q.Ny * Q.PH, jstep = R * zs;
+  float2* hp = Q.H4 + (long long)t * zs + ky * Q.PH + kx;
+  float2 v[R], nx[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
+#pragma unroll
+  for (int j = 0; j < R; ++j) nx[j] = hp[Q.HS + j * jstep];
+  const float kxy = P.kx2[kx] + P.ky2[ky];
+#pragma unroll 1
+  for (int comp = 0; comp < 2; ++comp) {
+    strided_fft<R, false>(v, tw, xa, l, t);
+    const float e = comp == 0 ? P.y_minus2_half : P.y_minus1_half;
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) {
+      const float k2 = kxy + P.kz2[t + R * k1];
+      const float m = k2 > 0.f ? __powf(k2, e) * Q.norm : 0.f;
+      v[k1] = cscale(v[k1], m);
     }
     strided_fft<R, true>(v, tw, xb, l, t);
     float2* op = hp + comp * Q.HS;
@@ -537,11 +577,14 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
 // SRC: 0 none, 1 filtered source in Z4[3], 2 unfiltered dense slab
 // Items per row pair: [source spectrum], rho_x, rho_y, rho_z, sensor rows (pm = interleaved (p_max, p_min)
 // on the expanded grid; rows in the PML are skipped).
-template <int R, bool HOMOG, int SRC>
+// ABS (absorbing medium): no equation of state here.  The kernel forms the operands of the two fractional
+// Laplacians, rho0 * sum_xi d_xi u_xi and sum_xi rho_xi, writes their packed x-spectra to Z4[0] / Z4[1] (the lines
+// this pair has already consumed) and keeps sum rho in r1; k2_x_p finishes the step.
+template <int R, bool HOMOG, int SRC, bool ABS = false>
 __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   using XS = XStage<R>;
   constexpr int N = R * R, G = XS::GROUPS;
-  constexpr int NI = SRC == 1 ? 5 : 4;
+  constexpr int NI = (SRC == 1 ? 5 : 4) - (ABS ? 1 : 0);
   constexpr int C0 = SRC == 1 ? 1 : 0;                  // item index of rho_x
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
@@ -579,6 +622,7 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   issue(pair, 0 - C0, 0, iters > 0);
   issue(pair, 1 - C0, 1, iters > 0);
   float2 src[R], sum[R];
+  float2 dsum[ABS ? R : 1];
   for (int it = 0; it < iters; ++it, pair += pstep) {
     int z, ylo;
     pair_rows(Q, pair, z, ylo);
@@ -627,8 +671,31 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
             rho[x] = rn.x;
             rho[hi + x] = rn.y;
             sum[j] = c == 0 ? rn : cadd(sum[j], rn);           // (rho_x + rho_y) + rho_z
+            if constexpr (ABS) dsum[j] = c == 0 ? v[j] : cadd(dsum[j], v[j]);   // (dux + duy) + duz
           }
-          if (c == 2) {
+          if (ABS && c == 2) {
+            if constexpr (ABS) {
+#pragma unroll
+              for (int j = 0; j < R; ++j) {
+                const int x = t + R * j;
+                float2 r0v;
+                if constexpr (HOMOG) { r0v.x = r0v.y = P.rho0_s; } else { r0v.x = P.rho0[r0 + x]; r0v.y = P.rho0[r0 + hi + x]; }
+                dsum[j] = __fmul2_rn(r0v, dsum[j]);
+                P.r1[r0 + x] = sum[j].x;
+                P.r1[r0 + hi + x] = sum[j].y;
+              }
+              __syncwarp();
+              line_fft_sw<R, false>(dsum, tw, zb, t);
+              float2* zo = Q.Z4 + (long long)pair * N;
+#pragma unroll
+              for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = dsum[k1];
+              __syncwarp();
+              line_fft_sw<R, false>(sum, tw, zb, t);
+              zo += Q.ZS;
+#pragma unroll
+              for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
+            }
+          } else if (c == 2) {
             // equation of state; the sensor item that follows consumes p from `sum`
 #pragma unroll
             for (int j = 0; j < R; ++j) {
@@ -675,6 +742,118 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
   }
   cp_async_wait<0>();
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.step = *P.step + 1;
+}
+
+
+// Absorbing medium, last pass of the step.  Items per row pair: [Z4[0] line + the r1 rows (sum rho)],
+// [Z4[1] line], [sensor rows]:  p = c0^2 (sum rho + tau L1 - eta L2), running max/min, FFT_x of p -> ZP.
+template <int R, bool HOMOG>
+__global__ void __launch_bounds__(128, 3) k2_x_p(StepParams P, V2Params Q, int use_tau, int use_eta) {
+  using XS = XStage<R>;
+  constexpr int N = R * R, G = XS::GROUPS;
+  constexpr int NI = 3;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const float4* tw = XS::load_tw(smraw, Q.tw4x);
+  const int g = threadIdx.x / R, t = threadIdx.x % R;
+  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  const long long hi = (long long)Q.Ry * N;
+  const int nbatch = Q.Nz * (Q.Ny / 2) / G;
+  const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int pstep = gridDim.x * G;
+  auto issue = [&](int pair, int c, int stage, bool valid) {
+    if (valid) {
+      int z, ylo;
+      pair_rows(Q, pair, z, ylo);
+      const long long r0 = ((long long)z * Q.Ny + ylo) * N;
+      char* st = gbase + stage * XS::BYTES;
+      if (c < 2) {
+        XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + (long long)pair * N), 8 * N, t);
+        if (c == 0) {
+          XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.r1 + r0), 4 * N, t);
+          XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.r1 + r0 + hi), 4 * N, t);
+        }
+      } else {
+        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        if (zin && (unsigned)(ylo - P.py) < (unsigned)P.ny)
+          XS::copy(st, reinterpret_cast<const char*>(Q.pm + r0), 8 * N, t);
+        if (zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny)
+          XS::copy(st + 8 * N, reinterpret_cast<const char*>(Q.pm + r0 + hi), 8 * N, t);
+      }
+    }
+    cp_async_commit();
+  };
+  int pair = blockIdx.x * G + g;
+  issue(pair, 0, 0, iters > 0);
+  issue(pair, 1, 1, iters > 0);
+  float2 acc[R];
+  for (int it = 0; it < iters; ++it, pair += pstep) {
+    int z, ylo;
+    pair_rows(Q, pair, z, ylo);
+    const long long r0 = ((long long)z * Q.Ny + ylo) * N;
+    const int par = (it * NI) & 1;
+#pragma unroll
+    for (int c = 0; c < NI; ++c) {
+      cp_async_wait<1>();
+      __syncwarp();
+      const int stage = (par + c) & 1;
+      float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
+      const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
+      if (c < 2) {
+        float2 v[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
+        __syncwarp();
+        line_fft_sw<R, true>(v, tw, zb, t);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int x = t + R * j;
+          if (c == 0) {
+            float2 ta;
+            if constexpr (HOMOG) { ta.x = ta.y = P.tau_s; } else { ta.x = P.tau[r0 + x]; ta.y = P.tau[r0 + hi + x]; }
+            const float2 s0 = make_float2(rb[x], rb[N + x]);
+            acc[j] = use_tau ? __ffma2_rn(ta, v[j], s0) : s0;              // sum rho + tau L1
+          } else {
+            float2 et, c2;
+            if constexpr (HOMOG) { et.x = et.y = -P.eta_s; c2.x = c2.y = P.c2_s; }
+            else { et.x = -P.eta[r0 + x]; et.y = -P.eta[r0 + hi + x]; c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
+            if (use_eta) acc[j] = __ffma2_rn(et, v[j], acc[j]);            // ... - eta L2
+            acc[j] = __fmul2_rn(c2, acc[j]);
+            if (Q.store_p) { P.p[r0 + x] = acc[j].x; P.p[r0 + hi + x] = acc[j].y; }
+          }
+        }
+      } else {
+        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
+        const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
+        float2* pmg = Q.pm + r0;
+        if (in0) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int x = t + R * j;
+            const float2 o = zb[x];
+            pmg[x] = make_float2(fmaxf(o.x, acc[j].x), fminf(o.y, acc[j].x));
+          }
+        }
+        if (in1) {
+#pragma unroll
+          for (int j = 0; j < R; ++j) {
+            const int x = t + R * j;
+            const float2 o = zb[N + x];
+            pmg[hi + x] = make_float2(fmaxf(o.x, acc[j].y), fminf(o.y, acc[j].y));
+          }
+        }
+        __syncwarp();
+        line_fft_sw<R, false>(acc, tw, zb, t);
+        float2* zo = Q.ZP + (long long)pair * N;
+#pragma unroll
+        for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = acc[k1];
+      }
+      __syncwarp();
+      if (c + 2 < NI) issue(pair, c + 2, stage, true);
+      else issue(pair + pstep, c + 2 - NI, stage, it + 1 < iters);
+    }
+  }
+  cp_async_wait<0>();
 }
 
 // x forward of the dense source slab (row pairs).  grid = ceil(nzs*(Ny/2)/G), G = 256/R

@@ -675,7 +675,6 @@ static int radix_of(int n) { return n == 64 ? 8 : (n == 256 ? 16 : 0); }
 
 static bool v2_eligible(const lifu_sim* s) {
   if (s->pipeline == 1) return false;
-  if (s->absorbing) return false;
   for (int a = 0; a < 3; ++a) if (radix_of(s->N[a]) == 0) return false;
   return true;
 }
@@ -771,8 +770,19 @@ template <int R> static void v2_launch_x_u(lifu_sim* s, int nbatch) {
 }
 template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int nbatch) {
   dim3 grid(std::min(nbatch, s->n_sm * 3));
-  if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
-  else v2_launch(k2_x_rho_p<R, false, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  if (s->absorbing) {
+    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+    else v2_launch(k2_x_rho_p<R, false, SRC, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  } else {
+    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+    else v2_launch(k2_x_rho_p<R, false, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  }
+}
+template <int R> static void v2_launch_x_p(lifu_sim* s, int nbatch) {
+  dim3 grid(std::min(nbatch, s->n_sm * 3));
+  const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
+  if (s->homogeneous) v2_launch(k2_x_p<R, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
+  else v2_launch(k2_x_p<R, false>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
 }
 
 static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
@@ -825,7 +835,20 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   else V2_R(Rx, (v2_launch_x_rho_p<RR, 2>(s, gx)));
   ++nk;
   const double sens = (double)s->n[1] * s->n[2] / ((double)s->N[1] * s->N[2]);   // sensor rows are full x lines
-  mark("k2_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+  if (!s->absorbing) {
+    mark("k2_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+  } else {
+    // (6) absorbing medium: the two fractional Laplacians, then the equation of state
+    mark("k2_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+    V2_R(Ry, (v2_launch(k2_y_fwd<RR, 3>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+    ++nk; mark("k2_y_fwd_abs", 16);
+    V2_R(Rz, (v2_launch(k2_z_absorb<RR>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+    ++nk; mark("k2_z_absorb", 16);
+    V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+    ++nk; mark("k2_y_inv_abs", 16);
+    V2_R(Rx, (v2_launch_x_p<RR>(s, gx)));
+    ++nk; mark("k2_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
+  }
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
   return LIFU_OK;

@@ -216,3 +216,32 @@ def test_v2_c2_grid_short(lifu_lib):
     assert _is_v2(got)
     assert np.array_equal(got["src_idx"], want["src_idx"])
     _check_fields(got, want)
+
+
+def test_v2_homogeneous_absorbing(lifu_lib):
+    """Fused pipeline with the power-law absorption terms (two extra transform round trips per step)."""
+    case = cases.v2_small_case()
+    case["alpha"], case["c0"], case["rho0"] = 0.75, 1540.0, 1050.0
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case, fields=(0,))
+    assert _is_v2(got) and got["stats"]["absorbing"] == 1
+    _check_fields(got, want)
+    v1 = cases.run_cuda_case(case, pipeline="v1", fields=(0,))
+    assert not _is_v2(v1)
+    assert cases.rel_l2(got["field0"], v1["field0"]) < 2e-4          # final pressure field, both pipelines
+
+
+@pytest.mark.parametrize("alpha_mode", ["binary", "no_dispersion", "no_absorption"])
+def test_v2_heterogeneous_absorbing(lifu_lib, alpha_mode):
+    from oracle.solver import Assumptions
+    case = cases.v2_small_case()
+    case["c0"], case["rho0"], case["alpha"] = _phantom(tuple(case["N"]))
+    case["dt"], case["t_end"] = 1.5e-7, 100 * 1.5e-7
+    asm = Assumptions(absorb_eta=alpha_mode != "no_dispersion", absorb_tau=alpha_mode != "no_absorption")
+    want = cases.run_oracle_case(case, asm=asm)
+    got = cases.run_cuda_case(case, alpha_mode=alpha_mode)
+    assert _is_v2(got) and got["stats"]["homogeneous"] == 0 and got["stats"]["absorbing"] == 1
+    _check_fields(got, want)
+    v1 = cases.run_cuda_case(case, alpha_mode=alpha_mode, pipeline="v1")
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(got[k], v1[k]) < 2e-5
