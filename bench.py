@@ -477,6 +477,7 @@ def main():
     if not args.no_e2e:
         kwave_if.clear_sessions()
         h2d = d2h = 0
+        api_loop_ms = []
 
         def api_step(step):
             nonlocal h2d, d2h
@@ -490,6 +491,7 @@ def main():
             med = 3 * 4 if homog else 3 * 4 * n_inner_vox
             h2d = med + 4 * base.size + 8 * arr.numelements()
             d2h = 2 * 4 * n_inner_vox
+            api_loop_ms.append(out["stats"]["loop_ms"])
             return float(ds["p_min"].data.max())
 
         for w in range(max(1, min(args.warmup, 3))):
@@ -504,7 +506,8 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * V * Nt * args.steps / float(te.item()) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "foci_per_s": world * args.steps / float(te.item())}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "foci_per_s": world * args.steps / float(te.item()),
+               "wall_ms_per_step": t_e2e * 1e3 / args.steps, "solver_loop_ms_per_step": float(np.mean(api_loop_ms[-args.steps:]))}
         kwave_if.clear_sessions()
 
     # ---- CPU baseline (oracle port) on rank 0 at N=1

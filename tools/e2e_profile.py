@@ -43,7 +43,7 @@ def main():
     type(arr).drive_plan = timed("drive_plan", type(arr).drive_plan)
     for it in range(4):
         T.clear()
-        delays, apod = beams[it]
+        delays, apod = beams[it % len(beams)]
         ses = next(iter(kwave_if._SESSIONS.values()), None)
         if ses is not None:
             ses.medium_key = None
