@@ -367,6 +367,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # torchrun exports OMP_NUM_THREADS=1; the host side of the public API (packaging) uses this rank's share of the cores
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     os.environ["LIFU_DEVICE"] = str(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))

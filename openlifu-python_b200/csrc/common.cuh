@@ -55,6 +55,7 @@ struct StepParams {
   long long Vh;               // Nxh*Ny*Nz
   long long RS, CS;           // strides between batched real / complex fields
   float invN;                 // 1/(Nx*Ny*Nz): cuFFT transforms are unnormalised
+  float inv_dt;               // 1/dt
   int poly_ok;                // (c_ref k dt/2)^2 <= 9.8 everywhere: polynomial sinc/cos are valid
   // 1-D tables
   const float2 *dpx, *dpy, *dpz;   // i k exp(+i k d/2)

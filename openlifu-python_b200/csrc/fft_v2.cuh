@@ -465,14 +465,17 @@ __device__ __forceinline__ void line_fft_sw(float2 (&v)[R], const float4* __rest
   dft<R, INV>(v);
 }
 
-// One group's staging: stage s = 16 N bytes = [ N float2 spectrum line | row lo (N floats) | row hi (N floats) ]
-// or [ sensor row lo (N float2) | sensor row hi (N float2) ]
-template <int R>
+// One group's staging: a stage is SB*N bytes = [ N float2 spectrum line | row lo (N floats) | row hi (N floats) ]
+// or [ sensor row lo (N float2) | sensor row hi (N float2) ]; heterogeneous media append the two rows of the medium
+// map the item needs (SB = 24) so that they arrive with the fields instead of being loaded after the transform.
+// XB*N extra bytes per group sit behind the ring (double-buffered per-pair medium rows of k2_x_rho_p).
+template <int R, int SB = 16, int XB = 0>
 struct XStage {
   static constexpr int N = R * R;
-  static constexpr int BYTES = 16 * N;          // per stage
+  static constexpr int BYTES = SB * N;          // per stage
   static constexpr int GROUPS = 128 / R;
-  static constexpr int SMEM = GROUPS * 2 * BYTES + 16 * (N + 1);   // + twiddle table
+  static constexpr int GBYTES = 2 * BYTES + XB * N;                 // per group
+  static constexpr int SMEM = GROUPS * GBYTES + 16 * (N + 1);       // + twiddle table
   // copy `bytes` (multiple of 16*R) from global to shared with the R lanes of the group
   static __device__ __forceinline__ void copy(char* sdst, const char* gsrc, int bytes, int t) {
 #pragma unroll
@@ -480,12 +483,14 @@ struct XStage {
       if (o < bytes) cp_async16(sdst + o + 16 * t, gsrc + o + 16 * t);
   }
   static __device__ __forceinline__ const float4* load_tw(unsigned char* smraw, const float4* __restrict__ g) {
-    float4* s = reinterpret_cast<float4*>(smraw + GROUPS * 2 * BYTES);
+    float4* s = reinterpret_cast<float4*>(smraw + GROUPS * GBYTES);
     for (int i = threadIdx.x; i <= N; i += 128) s[i] = g[i];
     __syncthreads();
     return s;
   }
 };
+template <int R, bool HOMOG> using XStageU = XStage<R, HOMOG ? 16 : 24, 0>;
+template <int R, bool HOMOG> using XStageRho = XStage<R, 16, HOMOG ? 0 : 16>;
 
 // row pair index (z*Ny/2 + m) -> z and the lower row y_lo of the pair (Ny/2 and Ry are powers of two)
 __device__ __forceinline__ void pair_rows(const V2Params& Q, int pair, int& z, int& ylo) {
@@ -501,13 +506,13 @@ __device__ __forceinline__ long long pair_row_lo(const V2Params& Q, int z, int m
 // Work of one persistent CTA: row-pair batches blockIdx.x, blockIdx.x + gridDim.x, ...; inside a batch the
 // items of a pair are unrolled at compile time, so the per-item index arithmetic folds away.
 template <int R, bool HOMOG>
-__global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
-  using XS = XStage<R>;
+__global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_u(StepParams P, V2Params Q) {
+  using XS = XStageU<R, HOMOG>;
   constexpr int N = R * R, G = XS::GROUPS;
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
-  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  char* gbase = reinterpret_cast<char*>(smraw) + g * XS::GBYTES;
   const long long hi = (long long)Q.Ry * N;                       // offset of the pair's upper row
   const int nbatch = Q.Nz * (Q.Ny / 2) / G;
   const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -522,6 +527,10 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
       XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + (long long)pair * N), 8 * N, t);
       XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0), 4 * N, t);
       XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0 + hi), 4 * N, t);
+      if constexpr (!HOMOG) {
+        XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.dt_rho0_sg + c * P.RS + r0), 4 * N, t);
+        XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.dt_rho0_sg + c * P.RS + r0 + hi), 4 * N, t);
+      }
     }
     cp_async_commit();
   };
@@ -555,7 +564,7 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
         if (c == 0) s.x = s.y = P.sgx[x];
         float2 d;
         if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_sg_s; }
-        else { d.x = -P.dt_rho0_sg[c * P.RS + r0 + x]; d.y = -P.dt_rho0_sg[c * P.RS + r0 + hi + x]; }
+        else { d.x = -rb[2 * N + x]; d.y = -rb[3 * N + x]; }
         // u = s (s u - dt/rho0 dp)
         const float2 un = __fmul2_rn(s, __ffma2_rn(d, v[j], __fmul2_rn(s, make_float2(rb[x], rb[N + x]))));
         u[x] = un.x;
@@ -581,22 +590,23 @@ __global__ void __launch_bounds__(128, 3) k2_x_u(StepParams P, V2Params Q) {
 // Laplacians, rho0 * sum_xi d_xi u_xi and sum_xi rho_xi, writes their packed x-spectra to Z4[0] / Z4[1] (the lines
 // this pair has already consumed) and keeps sum rho in r1; k2_x_p finishes the step.
 template <int R, bool HOMOG, int SRC, bool ABS = false>
-__global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
-  using XS = XStage<R>;
+__global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V2Params Q) {
+  using XS = XStageRho<R, HOMOG>;
   constexpr int N = R * R, G = XS::GROUPS;
   constexpr int NI = (SRC == 1 ? 5 : 4) - (ABS ? 1 : 0);
   constexpr int C0 = SRC == 1 ? 1 : 0;                  // item index of rho_x
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
-  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  char* gbase = reinterpret_cast<char*>(smraw) + g * XS::GBYTES;
+  char* mbase = gbase + 2 * XS::BYTES;                  // heterogeneous: 2 x [dt*rho0 row lo | row hi], one slot per pair
   const long long hi = (long long)Q.Ry * N;
   const int nbatch = Q.Nz * (Q.Ny / 2) / G;
   const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int pstep = gridDim.x * G;
 
-  // c: -1 source item, 0..2 rho_x, rho_y, rho_z, 3 sensor rows
-  auto issue = [&](int pair, int c, int stage, bool valid) {
+  // c: -1 source item, 0..2 rho_x, rho_y, rho_z, 3 sensor rows; slot: parity of the pair's iteration
+  auto issue = [&](int pair, int c, int stage, bool valid, int slot) {
     if (valid) {
       int z, ylo;
       pair_rows(Q, pair, z, ylo);
@@ -607,6 +617,12 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
         if (c >= 0) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0 + hi), 4 * N, t);
+        }
+        if constexpr (!HOMOG) {
+          if (c == 0) {     // the pair's dt*rho0 rows ride with its first density item and serve all three
+            XS::copy(mbase + slot * 8 * N, reinterpret_cast<const char*>(P.dt_rho0 + r0), 4 * N, t);
+            XS::copy(mbase + slot * 8 * N + 4 * N, reinterpret_cast<const char*>(P.dt_rho0 + r0 + hi), 4 * N, t);
+          }
         }
       } else {
         const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
@@ -619,8 +635,8 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
     cp_async_commit();
   };
   int pair = blockIdx.x * G + g;
-  issue(pair, 0 - C0, 0, iters > 0);
-  issue(pair, 1 - C0, 1, iters > 0);
+  issue(pair, 0 - C0, 0, iters > 0, 0);
+  issue(pair, 1 - C0, 1, iters > 0, 0);
   float2 src[R], sum[R];
   float2 dsum[ABS ? R : 1];
   for (int it = 0; it < iters; ++it, pair += pstep) {
@@ -636,6 +652,7 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
       const int stage = (par + ci) & 1;
       float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
       const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
+      const float* mb = reinterpret_cast<const float*>(mbase + (it & 1) * 8 * N);
       if (c < 3) {
         float2 v[R];
 #pragma unroll
@@ -664,7 +681,7 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
             if (c == 0) a.x = a.y = P.pmlx[x];
             float2 d;
             if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_s; }
-            else { d.x = -P.dt_rho0[r0 + x]; d.y = -P.dt_rho0[r0 + hi + x]; }
+            else { d.x = -mb[x]; d.y = -mb[N + x]; }
             // rho = a (a rho - dt rho0 du) [+ S]
             float2 rn = __fmul2_rn(a, __ffma2_rn(d, v[j], __fmul2_rn(a, make_float2(rb[x], rb[N + x]))));
             if constexpr (SRC != 0) rn = cadd(rn, src[j]);
@@ -678,8 +695,8 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
 #pragma unroll
               for (int j = 0; j < R; ++j) {
                 const int x = t + R * j;
-                float2 r0v;
-                if constexpr (HOMOG) { r0v.x = r0v.y = P.rho0_s; } else { r0v.x = P.rho0[r0 + x]; r0v.y = P.rho0[r0 + hi + x]; }
+                float2 r0v;      // rho0 = (dt rho0) / dt: the staged row serves the tau operand too
+                if constexpr (HOMOG) { r0v.x = r0v.y = P.rho0_s; } else { r0v.x = mb[x] * P.inv_dt; r0v.y = mb[N + x] * P.inv_dt; }
                 dsum[j] = __fmul2_rn(r0v, dsum[j]);
                 P.r1[r0 + x] = sum[j].x;
                 P.r1[r0 + hi + x] = sum[j].y;
@@ -736,8 +753,8 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
         for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
       }
       __syncwarp();
-      if (ci + 2 < NI) issue(pair, ci + 2 - C0, stage, true);
-      else issue(pair + pstep, ci + 2 - NI - C0, stage, it + 1 < iters);
+      if (ci + 2 < NI) issue(pair, ci + 2 - C0, stage, true, it & 1);
+      else issue(pair + pstep, ci + 2 - NI - C0, stage, it + 1 < iters, (it + 1) & 1);
     }
   }
   cp_async_wait<0>();
@@ -748,14 +765,14 @@ __global__ void __launch_bounds__(128, 3) k2_x_rho_p(StepParams P, V2Params Q) {
 // Absorbing medium, last pass of the step.  Items per row pair: [Z4[0] line + the r1 rows (sum rho)],
 // [Z4[1] line], [sensor rows]:  p = c0^2 (sum rho + tau L1 - eta L2), running max/min, FFT_x of p -> ZP.
 template <int R, bool HOMOG>
-__global__ void __launch_bounds__(128, 3) k2_x_p(StepParams P, V2Params Q, int use_tau, int use_eta) {
-  using XS = XStage<R>;
+__global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_p(StepParams P, V2Params Q, int use_tau, int use_eta) {
+  using XS = XStageU<R, HOMOG>;
   constexpr int N = R * R, G = XS::GROUPS;
   constexpr int NI = 3;
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
-  char* gbase = reinterpret_cast<char*>(smraw) + g * 2 * XS::BYTES;
+  char* gbase = reinterpret_cast<char*>(smraw) + g * XS::GBYTES;
   const long long hi = (long long)Q.Ry * N;
   const int nbatch = Q.Nz * (Q.Ny / 2) / G;
   const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
@@ -771,6 +788,15 @@ __global__ void __launch_bounds__(128, 3) k2_x_p(StepParams P, V2Params Q, int u
         if (c == 0) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.r1 + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.r1 + r0 + hi), 4 * N, t);
+          if constexpr (!HOMOG) {
+            XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.tau + r0), 4 * N, t);
+            XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.tau + r0 + hi), 4 * N, t);
+          }
+        } else if constexpr (!HOMOG) {
+          XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.eta + r0), 4 * N, t);
+          XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.eta + r0 + hi), 4 * N, t);
+          XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.c2 + r0), 4 * N, t);
+          XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.c2 + r0 + hi), 4 * N, t);
         }
       } else {
         const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
@@ -809,13 +835,13 @@ __global__ void __launch_bounds__(128, 3) k2_x_p(StepParams P, V2Params Q, int u
           const int x = t + R * j;
           if (c == 0) {
             float2 ta;
-            if constexpr (HOMOG) { ta.x = ta.y = P.tau_s; } else { ta.x = P.tau[r0 + x]; ta.y = P.tau[r0 + hi + x]; }
+            if constexpr (HOMOG) { ta.x = ta.y = P.tau_s; } else { ta.x = rb[2 * N + x]; ta.y = rb[3 * N + x]; }
             const float2 s0 = make_float2(rb[x], rb[N + x]);
             acc[j] = use_tau ? __ffma2_rn(ta, v[j], s0) : s0;              // sum rho + tau L1
           } else {
             float2 et, c2;
             if constexpr (HOMOG) { et.x = et.y = -P.eta_s; c2.x = c2.y = P.c2_s; }
-            else { et.x = -P.eta[r0 + x]; et.y = -P.eta[r0 + hi + x]; c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
+            else { et.x = -rb[x]; et.y = -rb[N + x]; c2.x = rb[2 * N + x]; c2.y = rb[3 * N + x]; }
             if (use_eta) acc[j] = __ffma2_rn(et, v[j], acc[j]);            // ... - eta L2
             acc[j] = __fmul2_rn(c2, acc[j]);
             if (Q.store_p) { P.p[r0 + x] = acc[j].x; P.p[r0 + hi + x] = acc[j].y; }

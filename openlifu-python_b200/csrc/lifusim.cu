@@ -363,6 +363,7 @@ static int create_impl(const lifu_grid* g, int device, void* cuda_stream, const 
   P.z0 = slab ? s->sl.z0 : 0; P.NzG = s->N[2]; P.jz0 = slab ? s->sl.jz_lo : 0;
   P.V = s->Vloc; P.Vh = s->Vh; P.RS = s->RS; P.CS = s->CS;
   P.invN = (float)(1.0 / (double)s->V);
+  P.inv_dt = (float)(1.0 / g->dt);
 
   int rc = LIFU_OK;
   auto A = [&](void** p, size_t bytes) { if (rc == LIFU_OK) rc = dev_alloc(s, p, bytes); };
@@ -764,25 +765,25 @@ static void v2_launch(K kernel, dim3 grid, int threads, size_t sm, cudaStream_t 
 #define V2_R(RVAL, EXPR) do { if ((RVAL) == 8) { constexpr int RR = 8; EXPR; } else { constexpr int RR = 16; EXPR; } } while (0)
 
 template <int R> static void v2_launch_x_u(lifu_sim* s, int nbatch) {
-  dim3 grid(std::min(nbatch, s->n_sm * 3));
-  if (s->homogeneous) v2_launch(k2_x_u<R, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
-  else v2_launch(k2_x_u<R, false>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+  dim3 grid(std::min(nbatch, s->n_sm * (s->homogeneous ? 3 : 2)));
+  if (s->homogeneous) v2_launch(k2_x_u<R, true>, grid, 128, XStageU<R, true>::SMEM, s->stream, s->P, s->Q);
+  else v2_launch(k2_x_u<R, false>, grid, 128, XStageU<R, false>::SMEM, s->stream, s->P, s->Q);
 }
 template <int R, int SRC> static void v2_launch_x_rho_p(lifu_sim* s, int nbatch) {
-  dim3 grid(std::min(nbatch, s->n_sm * 3));
+  dim3 grid(std::min(nbatch, s->n_sm * (s->homogeneous ? 3 : 2)));
   if (s->absorbing) {
-    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
-    else v2_launch(k2_x_rho_p<R, false, SRC, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC, true>, grid, 128, XStageRho<R, true>::SMEM, s->stream, s->P, s->Q);
+    else v2_launch(k2_x_rho_p<R, false, SRC, true>, grid, 128, XStageRho<R, false>::SMEM, s->stream, s->P, s->Q);
   } else {
-    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
-    else v2_launch(k2_x_rho_p<R, false, SRC>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q);
+    if (s->homogeneous) v2_launch(k2_x_rho_p<R, true, SRC>, grid, 128, XStageRho<R, true>::SMEM, s->stream, s->P, s->Q);
+    else v2_launch(k2_x_rho_p<R, false, SRC>, grid, 128, XStageRho<R, false>::SMEM, s->stream, s->P, s->Q);
   }
 }
 template <int R> static void v2_launch_x_p(lifu_sim* s, int nbatch) {
-  dim3 grid(std::min(nbatch, s->n_sm * 3));
+  dim3 grid(std::min(nbatch, s->n_sm * (s->homogeneous ? 3 : 2)));
   const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
-  if (s->homogeneous) v2_launch(k2_x_p<R, true>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
-  else v2_launch(k2_x_p<R, false>, grid, 128, XStage<R>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
+  if (s->homogeneous) v2_launch(k2_x_p<R, true>, grid, 128, XStageU<R, true>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
+  else v2_launch(k2_x_p<R, false>, grid, 128, XStageU<R, false>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
 }
 
 static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
