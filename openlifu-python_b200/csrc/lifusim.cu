@@ -862,7 +862,7 @@ static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* 
                              const std::function<void(const char*, double)>& mark) {
   StepParams& P = s->P;
   SlabCtx& L = s->sl;
-  cudaStream_t st = s->stream;
+  cudaStream_t st = s->stream, xs = L.xs;
   LIFU_CHECK(slab_plans(s));
   LIFU_CUFFT(cufftSetStream(L.r2c2d, st)); LIFU_CUFFT(cufftSetStream(L.c2r2d, st)); LIFU_CUFFT(cufftSetStream(L.c2c1d, st));
   const SlabParams S = SlabHost::params(s, false);
@@ -870,33 +870,59 @@ static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* 
   const long long Hl = L.Hl;
   const int gbh = grid_blocks(s, Hl, 256);
   const int gbr = grid_blocks(s, s->Vloc, 256);
-  int nk = 0, nf = 0;
+  int nk = 0, nf = 0, ne = 0, rc = LIFU_OK;
   const int xk = L.exchange == 2 ? 1 : 2;                       // kernels per exchange
   auto fft2_r2c = [&](float* r, float2* c) { ++nf; return cufftExecR2C(L.r2c2d, r, (cufftComplex*)c); };
   auto fft2_c2r = [&](float2* c, float* r) { ++nf; return cufftExecC2R(L.c2r2d, (cufftComplex*)c, r); };
   auto fftz = [&](float2* c, int dir) { ++nf; return cufftExecC2C(L.c2c1d, (cufftComplex*)c, (cufftComplex*)c, dir); };
+  // Hand-offs between the compute stream and the exchange stream.  An exchange of field f is: wait for its producer
+  // on `st`, push + barrier on `xs`, and an event the consumer on `st` waits for right before it needs the field --
+  // so the transforms of field f+1 run while field f is on the wire.
+  auto hand = [&](cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = L.ev[ne++ & 31];
+    if (cudaEventRecord(e, from) != cudaSuccess || cudaStreamWaitEvent(to, e, 0) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  };
+  cudaEvent_t done[4];                                          // "exchange of field f finished", consumed on st
+  const bool ov = L.overlap;
+  if (!ov) xs = st;                                             // batched mode: one stream, one barrier per batch of fields
+  auto xfwd = [&](int f, int kind, bool last) {
+    if (ov) hand(st, xs);
+    if (rc == LIFU_OK) rc = slab_exchange_fwd(s, xs, f, kind, ov || last);
+    if (ov) { done[f] = L.ev[ne++ & 31]; if (cudaEventRecord(done[f], xs) != cudaSuccess) rc = LIFU_ERR_CUDA; }
+    nk += xk;
+  };
+  auto xback = [&](int f, int fd, bool last) {
+    if (ov) hand(st, xs);
+    if (rc == LIFU_OK) rc = slab_exchange_back(s, xs, f, fd, ov || last);
+    if (ov) { done[f] = L.ev[ne++ & 31]; if (cudaEventRecord(done[f], xs) != cudaSuccess) rc = LIFU_ERR_CUDA; }
+    nk += xk;
+  };
+  auto need = [&](int f) { if (ov && cudaStreamWaitEvent(st, done[f], 0) != cudaSuccess) rc = LIFU_ERR_CUDA; };
+
   // (1) pressure gradient: 1 field out, 2 fields back
   LIFU_CUFFT(fft2_r2c(P.p, H));
-  mark("cufft2d_r2c_p", 8);
-  LIFU_CHECK(slab_exchange_fwd(s, 0, 1, 0)); nk += xk;
-  mark("xchg_fwd_p", 8);
+  xfwd(0, 0, true);
+  need(0);
+  mark("r2c_p+xchg", 16);
   LIFU_CUFFT(fftz(T, CUFFT_FORWARD));
   k_slab_grad_z<<<gbh, 256, 0, st>>>(P, S); ++nk;
   LIFU_CUFFT(fftz(T, CUFFT_INVERSE));
+  xback(0, 3, false);                                              // T0 -> H3 (kappa p^: all of the x / y content)
   LIFU_CUFFT(fftz(T + Hl, CUFFT_INVERSE));
+  xback(1, 2, true);                                              // T1 -> H2 (d/dz)
   mark("z_grad", 4 + 12 + 16);
-  LIFU_CHECK(slab_exchange_back(s, 0, 2, 3, -1));                // T0 -> H3 (kappa p^, all x/y content), T1 -> H2 (d/dz)
-  nk += xk;
-  mark("xchg_back_grad", 16);
+  need(0);
   k_slab_grad_xy<<<gbh, 256, 0, st>>>(P, S); ++nk;
-  mark("k_slab_grad_xy", 12);
-  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_c2r(H + c * Hl, P.r3 + c * P.RS));
-  mark("cufft2d_c2r_grad_x3", 24);
+  LIFU_CUFFT(fft2_c2r(H, P.r3));
+  LIFU_CUFFT(fft2_c2r(H + Hl, P.r3 + P.RS));
+  need(1);
+  LIFU_CUFFT(fft2_c2r(H + 2 * Hl, P.r3 + 2 * P.RS));
+  mark("xchg_back_grad+xy+c2r", 16 + 12 + 24);
   if (s->N[0] % 4 == 0) launch_update_u<4>(s, grid_blocks(s, s->Vloc / 4, 256));
   else launch_update_u<1>(s, gbr);
   ++nk;
   mark("k_update_u", s->homogeneous ? 36 : 48);
-  // (2) source field (built before the divergence so that it can ride the same exchange)
+  // (2) source field (built before the divergence so that it rides the same pipeline)
   int src = 0;
   if (src_active) {
     if (L.src_i1 > L.src_i0) {
@@ -905,22 +931,29 @@ static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* 
     mark("k_source_scatter", 0);
     src = s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2;
   }
-  // (3) velocity divergence (+ k-space filtered source): 3 (4) fields out and back
-  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_r2c(P.u + c * P.RS, H + c * Hl));
-  if (src == 1) LIFU_CUFFT(fft2_r2c(P.S, H + 3 * Hl));
-  mark("cufft2d_r2c_u", 24 + (src == 1 ? 8 : 0));
+  // (3) velocity divergence (+ k-space filtered source): 3 (4) fields out and back, pipelined field by field
   const int nfld = src == 1 ? 4 : 3;
-  LIFU_CHECK(slab_exchange_fwd(s, 0, nfld, 1)); nk += xk;
-  mark("xchg_fwd_u", 8 * nfld);
-  for (int c = 0; c < nfld; ++c) LIFU_CUFFT(fftz(T + c * Hl, CUFFT_FORWARD));
-  k_slab_div_z<<<gbh, 256, 0, st>>>(P, S, src == 1 ? 1 : 0); ++nk;
-  for (int c = 0; c < nfld; ++c) LIFU_CUFFT(fftz(T + c * Hl, CUFFT_INVERSE));
-  mark("z_div", 16 * nfld);
-  LIFU_CHECK(slab_exchange_back(s, 0, nfld, 0, 1)); nk += xk;
-  mark("xchg_back_div", 8 * nfld);
-  for (int c = 0; c < 3; ++c) LIFU_CUFFT(fft2_c2r(H + c * Hl, P.r3 + c * P.RS));
-  if (src == 1) LIFU_CUFFT(fft2_c2r(H + 3 * Hl, P.Sf));
-  mark("cufft2d_c2r_div", 24 + (src == 1 ? 8 : 0));
+  for (int c = 0; c < nfld; ++c) {
+    LIFU_CUFFT(fft2_r2c(c < 3 ? P.u + c * P.RS : P.S, H + c * Hl));
+    xfwd(c, c == 0 ? 1 : (c == 1 ? 2 : 0), c == nfld - 1);
+  }
+  mark("r2c_u", 8 * nfld);
+  for (int c = 0; c < nfld; ++c) {
+    need(c);
+    LIFU_CUFFT(fftz(T + c * Hl, CUFFT_FORWARD));
+    if (c < 2) k_slab_div_z<0><<<gbh, 256, 0, st>>>(P, S, c);
+    else if (c == 2) k_slab_div_z<1><<<gbh, 256, 0, st>>>(P, S, c);
+    else k_slab_div_z<2><<<gbh, 256, 0, st>>>(P, S, c);
+    ++nk;
+    LIFU_CUFFT(fftz(T + c * Hl, CUFFT_INVERSE));
+    xback(c, c, c == nfld - 1);
+  }
+  mark("xchg_fwd_u+z_div", 8 * nfld + 16 * nfld);
+  for (int c = 0; c < nfld; ++c) {
+    need(c);
+    LIFU_CUFFT(fft2_c2r(H + c * Hl, c < 3 ? P.r3 + c * P.RS : P.Sf));
+  }
+  mark("xchg_back_div+c2r", 16 * nfld);
   // (4) density update, source, equation of state, sensor
   if (s->homogeneous) {
     if (src == 0) launch_rho_p<true, 0>(s, gbr); else if (src == 1) launch_rho_p<true, 1>(s, gbr); else launch_rho_p<true, 2>(s, gbr);
@@ -930,26 +963,30 @@ static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* 
   ++nk;
   mark("k_update_rho_p", (s->homogeneous ? 56 : 64) + (src ? 4 : 0));
   if (s->absorbing) {
-    LIFU_CUFFT(fft2_r2c(P.r3, H));
-    LIFU_CUFFT(fft2_r2c(P.r3 + P.RS, H + Hl));
-    mark("cufft2d_r2c_absorb", 16);
-    LIFU_CHECK(slab_exchange_fwd(s, 0, 2, 0)); nk += xk;
-    mark("xchg_fwd_absorb", 16);
-    LIFU_CUFFT(fftz(T, CUFFT_FORWARD)); LIFU_CUFFT(fftz(T + Hl, CUFFT_FORWARD));
-    k_slab_absorb_z<<<gbh, 256, 0, st>>>(P, S); ++nk;
-    LIFU_CUFFT(fftz(T, CUFFT_INVERSE)); LIFU_CUFFT(fftz(T + Hl, CUFFT_INVERSE));
-    mark("z_absorb", 32);
-    LIFU_CHECK(slab_exchange_back(s, 0, 2, 0, 1)); nk += xk;
-    mark("xchg_back_absorb", 16);
-    LIFU_CUFFT(fft2_c2r(H, P.r3));
-    LIFU_CUFFT(fft2_c2r(H + Hl, P.r3 + P.RS));
-    mark("cufft2d_c2r_absorb", 16);
+    for (int c = 0; c < 2; ++c) {
+      LIFU_CUFFT(fft2_r2c(P.r3 + c * P.RS, H + c * Hl));
+      xfwd(c, 0, c == 1);
+    }
+    for (int c = 0; c < 2; ++c) {
+      need(c);
+      LIFU_CUFFT(fftz(T + c * Hl, CUFFT_FORWARD));
+      k_slab_absorb_z<<<gbh, 256, 0, st>>>(P, S, c, c == 0 ? P.y_minus2_half : P.y_minus1_half); ++nk;
+      LIFU_CUFFT(fftz(T + c * Hl, CUFFT_INVERSE));
+      xback(c, c, c == 1);
+    }
+    mark("absorb_fwd+z", 16 + 16 + 32);
+    for (int c = 0; c < 2; ++c) {
+      need(c);
+      LIFU_CUFFT(fft2_c2r(H + c * Hl, P.r3 + c * P.RS));
+    }
+    mark("xchg_back_absorb+c2r", 16 + 16);
     const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
     if (s->homogeneous) k_pressure_absorb<true><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
     else k_pressure_absorb<false><<<gbr, 256, 0, st>>>(P, use_tau, use_eta);
     ++nk;
     mark("k_pressure_absorb", s->homogeneous ? 32 : 44);
   }
+  if (rc != LIFU_OK) { if (g_err.empty()) set_error("slab step: stream/event hand-off failed: %s", cudaGetErrorString(cudaGetLastError())); return rc; }
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
   if (n_ffts) *n_ffts = nf;

@@ -21,6 +21,10 @@ struct SlabCtx {
   float2** d_peer = nullptr;        // device table [G] of every rank's xbuf (own entry = local pointer)
   std::vector<void*> opened;        // IPC mappings to close
   float* d_bar = nullptr;           // barrier / small reductions
+  cudaStream_t xs = nullptr;        // exchange stream (push kernels, barriers, NCCL calls)
+  cudaEvent_t ev[32] = {};          // producer -> exchange and exchange -> consumer hand-offs of one time step
+  int push_ctas_per_sm = 4;         // SM share of the NVLink-bound push kernels (transforms run beside them)
+  bool overlap = false;             // per-field exchanges on `xs` beside the transforms (LIFU_SLAB_OVERLAP overrides)
   cufftHandle r2c2d = 0, c2r2d = 0, c2c1d = 0;
   bool plans = false;
   void* d_fftwork = nullptr;

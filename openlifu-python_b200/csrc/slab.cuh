@@ -104,29 +104,27 @@ struct SlabParams {
 __device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 
 // Forward exchange, sender side: H[f] (local planes, all ky) -> block (z, kyl, kx) of rank q = ky / Nyl.
-// MODE 0: plain; MODE 1: velocity components, f = 0 gets i kx e^{-i kx dx/2}, f = 1 gets i ky e^{-i ky dy/2}.
-// Peer mode writes into rank q's T at plane z0 + zl; staging mode writes block q of the pack buffer
-// (dst_stride_z = Nyl*Nxh in both: a block is [planes][Nyl][Nxh]).
-template <int MODE>
-__global__ void __launch_bounds__(256) k_slab_push_fwd(StepParams P, SlabParams S, int f0, int nf) {
+// KIND 0: plain; 1: x i kx e^{-i kx dx/2} (velocity x); 2: x i ky e^{-i ky dy/2} (velocity y) -- the in-plane
+// divergence multipliers ride on the exchange.  Peer mode writes into rank q's T at plane z0 + zl; staging
+// mode writes block q of the pack buffer (a block is [planes][Nyl][Nxh] in both).
+template <int KIND>
+__global__ void __launch_bounds__(256) k_slab_push_fwd(StepParams P, SlabParams S, int f) {
   const int rows = S.Nzl * S.Ny;                       // (zl, ky) rows of Nxh elements
   const int kx = threadIdx.x & 31;
   const int row_in_blk = threadIdx.x >> 5;             // 8 rows per CTA pass
-  for (int f = f0; f < f0 + nf; ++f) {
-    const float2* src = S.H + f * S.Hl;
-    for (int row = blockIdx.x * 8 + row_in_blk; row < rows; row += gridDim.x * 8) {
-      const int zl = row / S.Ny, ky = row - zl * S.Ny;
-      const int q = ky / S.Nyl, kyl = ky - q * S.Nyl;
-      float2* dst = S.peer[q] + S.peer_T_off + f * S.Hl + ((long long)(S.zoff_T + zl) * S.Nyl + kyl) * S.Nxh;
-      const float2* sp = src + (long long)row * S.Nxh;
-      float2 my = make_float2(1.f, 0.f);
-      if (MODE == 1 && f - f0 == 1) my = P.dny[ky];
-      for (int x = kx; x < S.Nxh; x += 32) {
-        float2 v = sp[x];
-        if (MODE == 1 && f - f0 == 0) v = cmulf(P.dnx[x], v);
-        if (MODE == 1 && f - f0 == 1) v = cmulf(my, v);
-        dst[x] = v;
-      }
+  const float2* src = S.H + f * S.Hl;
+  for (int row = blockIdx.x * 8 + row_in_blk; row < rows; row += gridDim.x * 8) {
+    const int zl = row / S.Ny, ky = row - zl * S.Ny;
+    const int q = ky / S.Nyl, kyl = ky - q * S.Nyl;
+    float2* dst = S.peer[q] + S.peer_T_off + f * S.Hl + ((long long)(S.zoff_T + zl) * S.Nyl + kyl) * S.Nxh;
+    const float2* sp = src + (long long)row * S.Nxh;
+    float2 my = make_float2(1.f, 0.f);
+    if (KIND == 2) my = P.dny[ky];
+    for (int x = kx; x < S.Nxh; x += 32) {
+      float2 v = sp[x];
+      if (KIND == 1) v = cmulf(P.dnx[x], v);
+      if (KIND == 2) v = cmulf(my, v);
+      dst[x] = v;
     }
   }
 }
@@ -189,42 +187,40 @@ __global__ void __launch_bounds__(256) k_slab_grad_z(StepParams P, SlabParams S)
   }
 }
 
-// velocity divergence (+ source): T0, T1 *= kappa/N ; T2 *= i kz e^{-i kz dz/2} kappa/N ; T3 *= cos(c_ref k dt/2)/N
-__global__ void __launch_bounds__(256) k_slab_div_z(StepParams P, SlabParams S, int with_src) {
+// one field of the velocity divergence / source, in place on T[f]:
+// KIND 0: x kappa/N (x and y components: their i k multipliers rode on the exchange);
+// KIND 1: x i kz e^{-i kz dz/2} kappa/N (z component);  KIND 2: x cos(c_ref k dt/2)/N (source field)
+template <int KIND>
+__global__ void __launch_bounds__(256) k_slab_div_z(StepParams P, SlabParams S, int f) {
+  float2* T = S.T + f * S.Hl;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
     int kx, ky, kz;
     t_index(S, i, kx, ky, kz);
     const float a2 = P.ax2[kx] + P.ay2[ky] + P.az2[kz];
-    const float kap = kappa_of(a2) * P.invN;
-    float2 a = S.T[i], b = S.T[S.Hl + i], c = S.T[2 * S.Hl + i];
-    a.x *= kap; a.y *= kap; b.x *= kap; b.y *= kap; c.x *= kap; c.y *= kap;
-    S.T[i] = a;
-    S.T[S.Hl + i] = b;
-    S.T[2 * S.Hl + i] = cmulf(P.dnz[kz], c);
-    if (with_src) {
+    float2 a = T[i];
+    if (KIND == 2) {
       const float cs = cosf(sqrtf(a2)) * P.invN;
-      float2 d = S.T[3 * S.Hl + i];
-      d.x *= cs; d.y *= cs;
-      S.T[3 * S.Hl + i] = d;
+      a.x *= cs; a.y *= cs;
+    } else {
+      const float kap = kappa_of(a2) * P.invN;
+      a.x *= kap; a.y *= kap;
+      if (KIND == 1) a = cmulf(P.dnz[kz], a);
     }
+    T[i] = a;
   }
 }
 
-// absorption operators: T0 *= k^(y-2)/N, T1 *= k^(y-1)/N
-__global__ void __launch_bounds__(256) k_slab_absorb_z(StepParams P, SlabParams S) {
+// absorption operators, one field in place: T[f] *= k^(2e)/N with e = (y-2)/2 (tau operand) or (y-1)/2 (eta operand)
+__global__ void __launch_bounds__(256) k_slab_absorb_z(StepParams P, SlabParams S, int f, float e) {
+  float2* T = S.T + f * S.Hl;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
     int kx, ky, kz;
     t_index(S, i, kx, ky, kz);
     const float k2 = P.kx2[kx] + P.ky2[ky] + P.kz2[kz];
-    float n1 = 0.f, n2 = 0.f;
-    if (k2 > 0.f) {
-      n1 = powf(k2, P.y_minus2_half) * P.invN;
-      n2 = powf(k2, P.y_minus1_half) * P.invN;
-    }
-    float2 a = S.T[i], b = S.T[S.Hl + i];
-    a.x *= n1; a.y *= n1; b.x *= n2; b.y *= n2;
-    S.T[i] = a;
-    S.T[S.Hl + i] = b;
+    const float n1 = k2 > 0.f ? powf(k2, e) * P.invN : 0.f;
+    float2 a = T[i];
+    a.x *= n1; a.y *= n1;
+    T[i] = a;
   }
 }
 
@@ -256,9 +252,9 @@ struct SlabHost {
   }
 };
 
-inline int slab_barrier(lifu_sim* s) {
+inline int slab_barrier(lifu_sim* s, cudaStream_t st) {
   NcclApi* N = nccl_api();
-  LIFU_NCCL(N->AllReduce(s->sl.d_bar, s->sl.d_bar + 1, 1, ncclFloat, ncclSum, (ncclComm_t)s->sl.comm, s->stream));
+  LIFU_NCCL(N->AllReduce(s->sl.d_bar, s->sl.d_bar + 1, 1, ncclFloat, ncclSum, (ncclComm_t)s->sl.comm, st));
   return LIFU_OK;
 }
 
@@ -340,6 +336,15 @@ inline int slab_init(lifu_sim* s, const lifu_slab_desc* d) {
   }
   LIFU_CUDA(cudaMemcpyAsync(L.d_peer, peers.data(), sizeof(float2*) * L.G, cudaMemcpyHostToDevice, s->stream));
   LIFU_CUDA(cudaStreamSynchronize(s->stream));
+  // exchange stream: every push kernel, barrier and NCCL call of the time loop runs on it, in the same order on
+  // every rank; the handle's stream does the transforms and the real-space kernels and meets it through events
+  LIFU_CUDA(cudaStreamCreateWithFlags(&L.xs, cudaStreamNonBlocking));
+  for (auto& e : L.ev) LIFU_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (const char* e = getenv("LIFU_SLAB_PUSH_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 8) L.push_ctas_per_sm = v; }
+  // overlap: per-field exchanges on the exchange stream beside the transforms of the next field (measured +3 % at
+  // G = 2, where half of every exchange is a local copy); otherwise one barrier per batch of fields on one stream
+  L.overlap = L.G >= 2;
+  if (const char* e = getenv("LIFU_SLAB_OVERLAP")) L.overlap = e[0] == '1';
   return LIFU_OK;
 }
 
@@ -347,6 +352,7 @@ inline void slab_destroy(lifu_sim* s) {
   SlabCtx& L = s->sl;
   if (!L.on) return;
   if (L.plans) { cufftDestroy(L.r2c2d); cufftDestroy(L.c2r2d); cufftDestroy(L.c2c1d); }
+  if (L.xs) { cudaStreamSynchronize(L.xs); }
   cudaFree(L.d_fftwork);
   for (void* p : L.opened) cudaIpcCloseMemHandle(p);
   L.opened.clear();
@@ -361,6 +367,8 @@ inline void slab_destroy(lifu_sim* s) {
     cudaFree(L.xbuf);
   }
   L.xbuf = nullptr;
+  if (L.xs) { cudaStreamDestroy(L.xs); L.xs = nullptr; }
+  for (auto& e : L.ev) if (e) { cudaEventDestroy(e); e = nullptr; }
 }
 
 inline int slab_plans(lifu_sim* s) {
@@ -387,51 +395,51 @@ inline int slab_plans(lifu_sim* s) {
   return LIFU_OK;
 }
 
-// Forward exchange of H[f0 .. f0+nf) -> T[f0 .. f0+nf) on every rank.  mode 1 applies the x / y divergence
-// multipliers to the first two fields on the way out.
-inline int slab_exchange_fwd(lifu_sim* s, int f0, int nf, int mode) {
+// Forward exchange of one field, H[f] -> T[f] on every rank, enqueued on `st` (the exchange stream): the sender-side
+// kernel (with the in-plane multiplier `kind`), then the barrier (peer mode) or the grouped send/recv (NCCL mode).
+// The push kernel is NVLink-bound, so it is given a fraction of the SMs: transforms of the next field run beside it.
+inline int slab_exchange_fwd(lifu_sim* s, cudaStream_t st, int f, int kind, bool barrier = true) {
   SlabCtx& L = s->sl;
   const bool staging = L.exchange == 1;
   SlabParams S = SlabHost::params(s, staging);
   const int rows = L.Nzl * s->N[1];
-  const int gb = std::min((rows + 7) / 8, s->n_sm * 8);
-  if (mode == 1) k_slab_push_fwd<1><<<gb, 256, 0, s->stream>>>(s->P, S, f0, nf);
-  else k_slab_push_fwd<0><<<gb, 256, 0, s->stream>>>(s->P, S, f0, nf);
+  const int gb = std::min((rows + 7) / 8, s->n_sm * (L.overlap ? L.push_ctas_per_sm : 8));
+  if (kind == 1) k_slab_push_fwd<1><<<gb, 256, 0, st>>>(s->P, S, f);
+  else if (kind == 2) k_slab_push_fwd<2><<<gb, 256, 0, st>>>(s->P, S, f);
+  else k_slab_push_fwd<0><<<gb, 256, 0, st>>>(s->P, S, f);
   LIFU_CUDA(cudaGetLastError());
-  if (!staging) return slab_barrier(s);
+  if (!staging) return barrier ? slab_barrier(s, st) : LIFU_OK;
   NcclApi* N = nccl_api();
   const long long blk = L.Hl / L.G;                          // complex elements per (field, destination)
   LIFU_NCCL(N->GroupStart());
-  for (int f = f0; f < f0 + nf; ++f)
-    for (int q = 0; q < L.G; ++q) {
-      LIFU_NCCL(N->Send(L.pack + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, s->stream));
-      LIFU_NCCL(N->Recv(S.T + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, s->stream));
-    }
+  for (int q = 0; q < L.G; ++q) {
+    LIFU_NCCL(N->Send(L.pack + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));
+    LIFU_NCCL(N->Recv(S.T + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));
+  }
   LIFU_NCCL(N->GroupEnd());
   return LIFU_OK;
 }
 
-// Backward exchange of T[f0 + f] -> H[fd0 + f*fdstep], f = 0..nf-1.
-inline int slab_exchange_back(lifu_sim* s, int f0, int nf, int fd0, int fdstep) {
+// Backward exchange of one field, T[f] -> H[fd] on every rank, enqueued on `st`.
+inline int slab_exchange_back(lifu_sim* s, cudaStream_t st, int f, int fd, bool barrier = true) {
   SlabCtx& L = s->sl;
   SlabParams S = SlabHost::params(s, false);
   const int rows = s->N[2] * L.Nyl;
-  const int gb = std::min((rows + 7) / 8, s->n_sm * 8);
+  const int gb = std::min((rows + 7) / 8, s->n_sm * (L.overlap ? L.push_ctas_per_sm : 8));
   if (L.exchange == 2) {
-    k_slab_push_back<<<gb, 256, 0, s->stream>>>(S, f0, nf, fd0, fdstep);
+    k_slab_push_back<<<gb, 256, 0, st>>>(S, f, 1, fd, 1);
     LIFU_CUDA(cudaGetLastError());
-    return slab_barrier(s);
+    return barrier ? slab_barrier(s, st) : LIFU_OK;
   }
   NcclApi* N = nccl_api();
   const long long blk = L.Hl / L.G;
   LIFU_NCCL(N->GroupStart());
-  for (int f = 0; f < nf; ++f)
-    for (int q = 0; q < L.G; ++q) {
-      LIFU_NCCL(N->Send(S.T + (f0 + f) * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, s->stream));
-      LIFU_NCCL(N->Recv(L.pack + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, s->stream));
-    }
+  for (int q = 0; q < L.G; ++q) {
+    LIFU_NCCL(N->Send(S.T + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));
+    LIFU_NCCL(N->Recv(L.pack + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));
+  }
   LIFU_NCCL(N->GroupEnd());
-  k_slab_unpack_back<<<gb, 256, 0, s->stream>>>(S, L.pack, nf, fd0, fdstep);
+  k_slab_unpack_back<<<std::min((rows + 7) / 8, s->n_sm * 8), 256, 0, st>>>(S, L.pack + f * L.Hl, 1, fd, 1);
   LIFU_CUDA(cudaGetLastError());
   return LIFU_OK;
 }
