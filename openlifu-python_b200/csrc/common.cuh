@@ -122,6 +122,7 @@ struct V2Params {
   float2* ZSslab;                   // [nzs][Ny/2][Nx]
   float2* HSslab;                   // [nzs][Ny][PH]
   int store_p;                      // write the real-space pressure (last step / debugging)
+  int bx0;                          // added to blockIdx.x by the strided passes (nxt: a 1-wide grid does the Nyquist column only)
 };
 
 

@@ -161,7 +161,8 @@ struct Strided {
 // lane -> (kx, other index) of a strided-pass CTA; false when the CTA has no work.
 // grid.x = nxt regular tiles + 1 Nyquist slot; grid.y runs over the other index (regular) or its 16-blocks.
 __device__ __forceinline__ bool lane_map(const V2Params& Q, int n_other, int l, int& kx, int& o) {
-  if ((int)blockIdx.x < Q.nxt) { kx = blockIdx.x * 16 + l; o = blockIdx.y; return true; }
+  const int bx = (int)blockIdx.x + Q.bx0;
+  if (bx < Q.nxt) { kx = bx * 16 + l; o = blockIdx.y; return true; }
   if ((int)blockIdx.y * 16 >= n_other) return false;
   kx = Q.Nx >> 1;
   o = blockIdx.y * 16 + l;

@@ -10,6 +10,7 @@
 #include "sim.cuh"
 #include "step_kernels.cuh"
 #include "fft_v2.cuh"
+#include "fft_z_tma.cuh"
 #include "slab.cuh"
 
 namespace lifu {
@@ -680,6 +681,40 @@ static bool v2_eligible(const lifu_sim* s) {
   return true;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (liblifusim does not link libcuda)
+typedef CUresult (*tmap_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tmap_encode_fn tmap_encoder() {
+  static tmap_encode_fn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (tmap_encode_fn)p;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+// Tile = 16 kx of one ky row over all z planes of a complex (8-byte) field [comp][z][ky][kx(PH)]
+static bool encode_z_tile_map(void* out, void* base, int PH, int Ny, int nz, int ncomp) {
+  tmap_encode_fn enc = tmap_encoder();
+  if (!enc || nz > 256) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)PH, (cuuint64_t)Ny, (cuuint64_t)nz, (cuuint64_t)ncomp};
+  cuuint64_t strides[3] = {(cuuint64_t)PH * 8, (cuuint64_t)PH * 8 * Ny, (cuuint64_t)PH * 8 * Ny * nz};
+  cuuint32_t box[4] = {16, 1, (cuuint32_t)nz, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const int rank = ncomp > 0 ? 4 : 3;
+  CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, rank, base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static int v2_setup(lifu_sim* s) {
   V2Params& Q = s->Q;
   if (!s->v2_ready) {
@@ -753,6 +788,13 @@ static int v2_setup(lifu_sim* s) {
   }
   Q.z0s = z0; Q.nzs = nz;
   Q.store_p = 0;
+  Q.bx0 = 0;
+  // TMA descriptors of the z passes.  Opt-in (LIFU_Z_TMA=1): on C2 the persistent TMA-fed kernels measure 3 % slower
+  // than the per-thread-load kernels (profiles/r1_z_tma.md) -- the z passes are bound by their two 256-point
+  // transforms per element, not by load latency.
+  const char* zt = getenv("LIFU_Z_TMA");
+  s->z_tma = (zt && zt[0] == '1') && encode_z_tile_map(s->tmH, Q.H4, Q.PH, Q.Ny, Q.Nz, 4) &&
+             encode_z_tile_map(s->tmS, Q.HSslab, Q.PH, Q.Ny, Q.nzs, 0);
   return LIFU_OK;
 }
 
@@ -799,9 +841,26 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   // (1) pressure gradient
   V2_R(Ry, (v2_launch(k2_y_fwd<RR, 0>, dim3(tx, Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_p", 8);
-  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_grad<RR, 2>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
-  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_grad<RR, 1>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
-  else V2_R(Rz, (v2_launch(k2_z_grad<RR, 0>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  // z passes: regular kx tiles through the persistent TMA-fed kernel, the Nyquist column through the per-thread-load
+  // kernel on a 1-wide grid (zx = grid.x of that launch, Qn.bx0 selects the column)
+  const bool ztma = s->z_tma;
+  V2Params Qn = Q;
+  if (ztma) Qn.bx0 = Q.nxt;
+  const unsigned zx = ztma ? 1u : tx;
+  const CUtensorMap& tmH = *reinterpret_cast<const CUtensorMap*>(s->tmH);
+  const CUtensorMap& tmS = *reinterpret_cast<const CUtensorMap*>(s->tmS);
+  const dim3 zgrid((unsigned)std::min(Q.nxt * Q.Ny, 2 * s->n_sm));
+#define V2_ZTMA(OP, NCOMP)                                                                                                   \
+  do {                                                                                                                        \
+    if (poly == 2) V2_R(Rz, (v2_launch(k2_z_tma<RR, OP, 2>, zgrid, 16 * RR, ZTma<RR>::SMEM, st, s->P, Q, tmH, tmS, NCOMP)));   \
+    else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_tma<RR, OP, 1>, zgrid, 16 * RR, ZTma<RR>::SMEM, st, s->P, Q, tmH, tmS, NCOMP))); \
+    else V2_R(Rz, (v2_launch(k2_z_tma<RR, OP, 0>, zgrid, 16 * RR, ZTma<RR>::SMEM, st, s->P, Q, tmH, tmS, NCOMP)));             \
+    ++nk;                                                                                                                     \
+  } while (0)
+  if (ztma) V2_ZTMA(ZOP_GRAD, 1);
+  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_grad<RR, 2>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
+  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_grad<RR, 1>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
+  else V2_R(Rz, (v2_launch(k2_z_grad<RR, 0>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
   ++nk; mark("k2_z_grad", 12);
   V2_R(Ry, (v2_launch(k2_y_inv_grad<RR>, dim3(tx, Q.Nz), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_y_inv_grad", 20);
@@ -824,9 +883,10 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   }
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src == 1 ? 4 : 3;
-  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_div<RR, 2>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
-  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_div<RR, 1>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
-  else V2_R(Rz, (v2_launch(k2_z_div<RR, 0>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q, ncomp)));
+  if (ztma) V2_ZTMA(ZOP_DIV, ncomp);
+  if (poly == 2) V2_R(Rz, (v2_launch(k2_z_div<RR, 2>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn, ncomp)));
+  else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_div<RR, 1>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn, ncomp)));
+  else V2_R(Rz, (v2_launch(k2_z_div<RR, 0>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn, ncomp)));
   ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
   V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, ncomp), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_inv", 8 * ncomp);
@@ -843,7 +903,8 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
     mark("k2_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
     V2_R(Ry, (v2_launch(k2_y_fwd<RR, 3>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
     ++nk; mark("k2_y_fwd_abs", 16);
-    V2_R(Rz, (v2_launch(k2_z_absorb<RR>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+    if (ztma) V2_ZTMA(ZOP_ABS, 2);
+    V2_R(Rz, (v2_launch(k2_z_absorb<RR>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
     ++nk; mark("k2_z_absorb", 16);
     V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
     ++nk; mark("k2_y_inv_abs", 16);

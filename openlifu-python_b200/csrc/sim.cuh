@@ -100,6 +100,9 @@ struct lifu_sim {
   float4* d_tw[3] = {nullptr, nullptr, nullptr};
   float4* d_mul4 = nullptr;    // dpy4, dny4, dpz4, dnz4 packed
   long long slab_planes_alloc = 0;
+  bool z_tma = false;          // z passes through the persistent TMA-fed kernels (fft_z_tma.cuh)
+  unsigned char tmH[128] __attribute__((aligned(64))) = {};   // CUtensorMap of H4[comp][z][ky][kx]
+  unsigned char tmS[128] __attribute__((aligned(64))) = {};   // CUtensorMap of the source slab spectrum
   bool last_used_v2 = false;
 
   // per-stage profiling (lifu_profile_stages)
