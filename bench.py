@@ -209,13 +209,13 @@ def workload_name(args):
 
 
 def c5_scene(n_inner):
-    """SURVEY.md config C5 at a given inner size: 0.5 mm * 216 / n spacing (0.25 mm-class at 728 -> 768^3 with
-    PML), C3 phantom scaled to the grid, the 2x64-element array at its physical size, focus (0,0,50) mm."""
+    """SURVEY.md config C5 at a given inner size: 0.25 mm spacing (728^3 inner -> 768^3 with PML, dt = 83.3 ns),
+    C3 phantom scaled to the grid, the 2x64-element array at its physical size, focus (0,0,50) mm."""
     from openlifu_b200 import configs
     from openlifu_b200.bf import delay_methods
     from openlifu_b200.geo import Point
     arr = configs.openlifu_2x_array()
-    sp = 0.5 * 216.0 / n_inner if n_inner > 216 else 0.5          # mm
+    sp = 0.25 if n_inner > 216 else 0.5                           # mm
     half = (n_inner - 1) * sp / 2.0
     x = np.linspace(-half, half, n_inner)
     z = np.linspace(-4.0, -4.0 + 2 * half, n_inner)

@@ -150,6 +150,8 @@ struct Strided {
   static constexpr int XCH = N * 16 * 8;                       // bytes of one exchange buffer
   static constexpr int TW = (N + 1) * 16;                      // bytes of the twiddle table
   static constexpr int smem(int nbuf) { return nbuf * XCH + TW; }
+  // Stage the twiddle table.  Call it AFTER the first data loads have been issued: the barrier would otherwise
+  // serialise the table's global-load latency with theirs (a fifth of a short-lived CTA, profiles/r1_zdiv_source_stalls.txt).
   static __device__ __forceinline__ const float4* load_tw(unsigned char* smraw, int nbuf, const float4* __restrict__ g) {
     float4* s = reinterpret_cast<float4*>(smraw + nbuf * XCH);
     for (int i = threadIdx.x; i <= N; i += THREADS) s[i] = g[i];
@@ -201,7 +203,6 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
   if (!lane_map(Q, nz, l, kx, z)) return;
   const bool live = z < nz;                       // only a slab's Nyquist tile can run past the end
   const int zc = live ? z : nz - 1;
-  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
   float2* xa = reinterpret_cast<float2*>(smraw);
   const float2* Zin = MODE == 0 ? Q.ZP : ((MODE == 1 || MODE == 3) ? Q.Z4 + comp * Q.ZS : Q.ZSslab);
   float2* Hout = MODE == 2 ? Q.HSslab : Q.H4 + comp * Q.HS;
@@ -210,8 +211,11 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
   const int qstep = R * Q.Nx;
   float2 v[R];
 #pragma unroll
+  for (int q = 0; q < R / 2; ++q) { v[2 * q] = zp[q * qstep + kx]; v[2 * q + 1] = zp[q * qstep + km]; }
+  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
+#pragma unroll
   for (int q = 0; q < R / 2; ++q) {
-    const float2 d = zp[q * qstep + kx], m = zp[q * qstep + km];
+    const float2 d = v[2 * q], m = v[2 * q + 1];
     v[2 * q] = cadd_conj(d, m);                  // 2A = Z[k] + conj Z[-k]          (row t + R*2q)
     v[2 * q + 1] = cmul_mi(csub_conj(d, m));     // 2B = -i (Z[k] - conj Z[-k])     (row t + R*(2q+1))
   }
@@ -242,7 +246,6 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_grad(StepParams 
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
   int kx, ky;
   if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
-  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
   float2* xa = reinterpret_cast<float2*>(smraw);
   float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
   const int zs = Q.Ny * Q.PH, jstep = R * zs;
@@ -250,8 +253,9 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_grad(StepParams 
   float2 v[R], w[R];
 #pragma unroll
   for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
-  strided_fft<R, false>(v, tw, xa, l, t);
   const float axy = P.ax2[kx] + P.ay2[ky];
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
+  strided_fft<R, false>(v, tw, xa, l, t);
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) {
     const int kz = t + R * k1;
@@ -280,7 +284,6 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_y_inv_grad(StepPar
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
   int kx, z;
   if (!lane_map(Q, Q.Nz, l, kx, z)) return;
-  const float4* tw = S::load_tw(smraw, 2, Q.tw4y);
   float2* xa = reinterpret_cast<float2*>(smraw);
   float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
   const float2* hp = Q.H4 + ((long long)z * Q.Ny + t) * Q.PH + kx;      // ky = t + R*k1
@@ -288,10 +291,10 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_y_inv_grad(StepPar
   float2* zp = Q.Z4 + ((long long)z * (Q.Ny / 2) + t) * Q.Nx;
   float2 a[R], c[R];
 #pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) {
-    a[k1] = hp[k1 * kstep];
-    c[k1] = cmul4(a[k1], Q.dpy4[t + R * k1]);
-  }
+  for (int k1 = 0; k1 < R; ++k1) a[k1] = hp[k1 * kstep];
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4y);
+#pragma unroll
+  for (int k1 = 0; k1 < R; ++k1) c[k1] = cmul4(a[k1], Q.dpy4[t + R * k1]);
   strided_fft<R, true>(a, tw, xa, l, t);
   const float4 mx = with_i(P.dpx[kx]);
 #pragma unroll
@@ -318,7 +321,6 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
   int kx, ky;
   if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
-  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
   float2* xa = reinterpret_cast<float2*>(smraw);
   float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
   const int zs = Q.Ny * Q.PH, jstep = R * zs;
@@ -330,7 +332,10 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P
   const float axy = P.ax2[kx] + P.ay2[ky];
   float kap[R];
 #pragma unroll
-  for (int k1 = 0; k1 < R; ++k1) kap[k1] = kappa_sel<POLY>(axy + P.az2[t + R * k1]) * Q.norm;
+  for (int k1 = 0; k1 < R; ++k1) kap[k1] = P.az2[t + R * k1];
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
+#pragma unroll
+  for (int k1 = 0; k1 < R; ++k1) kap[k1] = kappa_sel<POLY>(axy + kap[k1]) * Q.norm;
 #pragma unroll 1
   for (int comp = 0; comp < ncomp; ++comp) {
     // prefetch the next component
@@ -375,7 +380,6 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_absorb(StepParam
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
   int kx, ky;
   if (!lane_map(Q, Q.Ny, l, kx, ky)) return;
-  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
   float2* xa = reinterpret_cast<float2*>(smraw);
   float2* xb = reinterpret_cast<float2*>(smraw + S::XCH);
   const int zs = Q.Ny * Q.PH, jstep = R * zs;
@@ -386,6 +390,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_absorb(StepParam
 #pragma unroll
   for (int j = 0; j < R; ++j) nx[j] = hp[Q.HS + j * jstep];
   const float kxy = P.kx2[kx] + P.ky2[ky];
+  const float4* tw = S::load_tw(smraw, 2, Q.tw4z);
 #pragma unroll 1
   for (int comp = 0; comp < 2; ++comp) {
     strided_fft<R, false>(v, tw, xa, l, t);
@@ -414,13 +419,13 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_inv(StepParams P
   const int comp = blockIdx.z;
   int kx, z;
   if (!lane_map(Q, Q.Nz, l, kx, z)) return;
-  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
   float2* xa = reinterpret_cast<float2*>(smraw);
   const float2* hp = Q.H4 + comp * Q.HS + ((long long)z * Q.Ny + t) * Q.PH + kx;
   const int kstep = R * Q.PH;
   float2 a[R];
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) a[k1] = hp[k1 * kstep];
+  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
   strided_fft<R, true>(a, tw, xa, l, t);
   merge_store<R>(Q.Z4 + comp * Q.ZS + ((long long)z * (Q.Ny / 2) + t) * Q.Nx, a, kx, Q.Nx, true);
 }
