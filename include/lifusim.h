@@ -193,6 +193,59 @@ int lifu_get_info(lifu_sim* sim, lifu_stats* stats);
 int lifu_profile_stages(lifu_sim* sim, int reps, int with_source, int max_stages, char* names,
                         int name_stride, double* ms, double* bytes_per_voxel, int* n_stages);
 
+/* ---- beam analysis of the simulated fields ------------------------------------
+ * The O(V) passes of Solution.analyze (/root/reference/src/openlifu/plan/solution.py:135-281), which the
+ * reference runs twice per calc_solution (inside Solution.scale, plan/protocol.py:372, and at :396): the
+ * focus-frame distance map and the ellipsoid masks (solution_analysis.py:319-442 get_focus_matrix,
+ * get_offset_grid, calc_dist_from_focus, get_mask), the masked maxima (solution.py:196-199,243-258), the
+ * -3 dB value-weighted centroid of the main lobe (solution.py:200-208, find_centroid :306-317) and the
+ * trilinear samples along the three focus-frame axes that the beam widths are read from
+ * (interp_transformed_axis :444-487, get_beam_bounds :489-535).  Scalar post-processing (unit factors,
+ * duty cycles, beam-width edges of the sampled lines, MI/TIC/power) stays on the host.
+ *
+ * One handle holds the fields of every focus of a solution on the device.  All geometry is float64 with
+ * round-to-nearest operations in the reference's evaluation order, so masks, maxima and line samples are
+ * bit-identical to the numpy evaluation; the centroid sums are accumulated in float64.
+ *   lifu_analysis_create      n = (Nx,Ny,Nz) of the fields; x,y,z = float64 coordinate vectors (analysis units);
+ *                             z_ok[Nz] = 1 where z > sidelobe_zmin (solution.py:194), NULL = all ones
+ *   lifu_analysis_set_focus   pnp = float32 peak-negative-pressure field of this focus in its stored unit,
+ *                             ipa = float64 intensity field; HOST or DEVICE pointers; stride = element strides
+ *                             of (x,y,z) and must describe a dense array (C or Fortran order or any permutation)
+ *   lifu_analysis_run_focus   line_pts: host float64 [(n_line[0]+n_line[1]+n_line[2])][3] sample points in grid
+ *                             coordinates; line_vals: host float64, same count (NaN outside the grid) */
+typedef struct lifu_analysis lifu_analysis; /* opaque */
+
+typedef struct lifu_focus_query {
+  double w[3][4];            /* rows 0..2 of inverse(get_focus_matrix(focus, origin)):
+                                frame coordinate i = ((w[i][0]*x + w[i][1]*y) + w[i][2]*z) + w[i][3] */
+  double aspect[3];          /* mainlobe_aspect_ratio: coordinate i is divided by aspect[i] */
+  double mainlobe_radius;    /* main lobe: dist <  mainlobe_radius */
+  double sidelobe_radius;    /* side lobe: dist >  sidelobe_radius and z_ok */
+  double centroid_factor;    /* centroid keeps main-lobe voxels with pnp > float32(main_pnp * centroid_factor) */
+  float pnp_scale;           /* float32 factor from the stored pressure unit to the analysis unit (Pa -> MPa: 1e-6f) */
+  int32_t n_line[3];         /* samples on the lateral / elevation / axial line (0 = none) */
+} lifu_focus_query;
+
+typedef struct lifu_focus_metrics {
+  double main_pnp, side_pnp, global_pnp;   /* maxima of float32(pnp*pnp_scale) over main lobe / side lobe / z_ok;
+                                              NaN when the selection holds no non-NaN value */
+  double main_ipa, side_ipa, global_ipa;   /* the same selections of this focus' intensity */
+  double main_ipa_all, global_ipa_all;     /* main-lobe / z_ok maximum over EVERY focus' intensity field
+                                              (the reference masks the whole stack, solution.py:245,266) */
+  int64_t n_main, n_side, n_global;        /* voxels in each selection */
+  double cen_w, cen_wx, cen_wy, cen_wz;    /* sum of w, w*x, w*y, w*z over the -3 dB part of the main lobe */
+  int64_t n_centroid;
+  double kernel_ms;                        /* CUDA-event time of this call's kernels */
+} lifu_focus_metrics;
+
+int lifu_analysis_create(int device, void* cuda_stream, const int32_t n[3], int32_t n_foci, const double* x,
+                         const double* y, const double* z, const uint8_t* z_ok, lifu_analysis** out);
+int lifu_analysis_set_focus(lifu_analysis* a, int32_t focus, const float* pnp, const double* ipa,
+                            const int64_t stride[3]);
+int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_query* q, const double* line_pts,
+                            lifu_focus_metrics* out, double* line_vals);
+int lifu_analysis_destroy(lifu_analysis* a);
+
 #ifdef __cplusplus
 }
 #endif

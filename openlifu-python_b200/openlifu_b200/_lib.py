@@ -48,6 +48,24 @@ class lifu_slab_layout(C.Structure):
                 ("sensor_z0", C.c_int32), ("sensor_nz", C.c_int32), ("medium_z0", C.c_int32), ("medium_nz", C.c_int32)]
 
 
+class lifu_focus_query(C.Structure):
+    _fields_ = [("w", (C.c_double * 4) * 3), ("aspect", C.c_double * 3), ("mainlobe_radius", C.c_double),
+                ("sidelobe_radius", C.c_double), ("centroid_factor", C.c_double), ("pnp_scale", C.c_float),
+                ("n_line", C.c_int32 * 3)]
+
+
+class lifu_focus_metrics(C.Structure):
+    _fields_ = [("main_pnp", C.c_double), ("side_pnp", C.c_double), ("global_pnp", C.c_double),
+                ("main_ipa", C.c_double), ("side_ipa", C.c_double), ("global_ipa", C.c_double),
+                ("main_ipa_all", C.c_double), ("global_ipa_all", C.c_double),
+                ("n_main", C.c_int64), ("n_side", C.c_int64), ("n_global", C.c_int64),
+                ("cen_w", C.c_double), ("cen_wx", C.c_double), ("cen_wy", C.c_double), ("cen_wz", C.c_double),
+                ("n_centroid", C.c_int64), ("kernel_ms", C.c_double)]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
 EXCHANGE_MODES = {"auto": 0, "nccl": 1, "peer": 2}
 ALPHA_MODES = {"binary": 0, "no_dispersion": 1, "no_absorption": 2}
 SOURCE_MODES = {"additive": 0, "additive-no-correction": 1}
@@ -100,6 +118,10 @@ def load():
         "lifu_create_slab": (C.c_int, [C.POINTER(lifu_grid), C.c_int, vp, C.POINTER(lifu_slab_desc), C.POINTER(vp)]),
         "lifu_slab_layout_of": (C.c_int, [vp, C.POINTER(lifu_slab_layout)]),
         "lifu_set_medium_planes": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int, i32, i32]),
+        "lifu_analysis_create": (C.c_int, [C.c_int, vp, C.POINTER(i32), i32, vp, vp, vp, vp, C.POINTER(vp)]),
+        "lifu_analysis_set_focus": (C.c_int, [vp, i32, vp, vp, C.POINTER(i64)]),
+        "lifu_analysis_run_focus": (C.c_int, [vp, i32, C.POINTER(lifu_focus_query), vp, C.POINTER(lifu_focus_metrics), vp]),
+        "lifu_analysis_destroy": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -115,7 +137,8 @@ EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_a
             "lifu_set_medium", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
-            "lifu_set_medium_planes"]
+            "lifu_set_medium_planes", "lifu_analysis_create", "lifu_analysis_set_focus", "lifu_analysis_run_focus",
+            "lifu_analysis_destroy"]
 
 
 def _check(rc):
@@ -305,3 +328,88 @@ class LifuSim:
         st = lifu_stats()
         _check(self._lib.lifu_get_info(self._h, C.byref(st)))
         return st.as_dict()
+
+
+class BeamAnalysis:
+    """Device-side beam analysis handle (``lifu_analysis_*``): holds the fields of every focus of a solution
+    and evaluates the O(V) passes of ``Solution.analyze`` on the GPU.  No CPU fallback."""
+
+    def __init__(self, axes, n_foci, z_ok=None, device=0, stream=0):
+        self._h = C.c_void_p()
+        self._lib = load()
+        self.axes = [np.ascontiguousarray(a, dtype=np.float64) for a in axes]
+        self.n = tuple(int(a.size) for a in self.axes)
+        self.n_foci = int(n_foci)
+        zk = None if z_ok is None else np.ascontiguousarray(z_ok, dtype=np.uint8)
+        _check(self._lib.lifu_analysis_create(int(device), C.c_void_p(int(stream) or None), (C.c_int32 * 3)(*self.n),
+                                              self.n_foci, _ptr(self.axes[0]), _ptr(self.axes[1]), _ptr(self.axes[2]),
+                                              _ptr(zk), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.lifu_analysis_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_focus(self, focus, pnp, ipa, strides=None):
+        """Stage one focus' fields.  numpy arrays of shape (Nx,Ny,Nz) in any dense layout (float32 pressure,
+        float64 intensity; both the same layout), or raw device pointers with explicit element ``strides``."""
+        if strides is None:
+            pnp = np.asarray(pnp)
+            if pnp.dtype != np.float32 or pnp.shape != self.n:
+                raise ValueError(f"pnp must be a float32 array of shape {self.n}")
+            ipa = np.asarray(ipa)
+            if ipa.dtype != np.float64 or ipa.shape != self.n:
+                raise ValueError(f"ipa must be a float64 array of shape {self.n}")
+            if not (pnp.flags.c_contiguous or pnp.flags.f_contiguous):
+                pnp = np.ascontiguousarray(pnp)
+            strides = tuple(s // pnp.itemsize for s in pnp.strides)
+            if tuple(s // ipa.itemsize for s in ipa.strides) != strides:
+                ipa = np.asarray(ipa, order="C" if pnp.flags.c_contiguous else "F")
+                if tuple(s // ipa.itemsize for s in ipa.strides) != strides:
+                    ipa = np.ascontiguousarray(ipa)
+                    pnp = np.ascontiguousarray(pnp)
+                    strides = tuple(s // pnp.itemsize for s in pnp.strides)
+        _check(self._lib.lifu_analysis_set_focus(self._h, int(focus), _ptr(pnp), _ptr(ipa),
+                                                 (C.c_int64 * 3)(*[int(s) for s in strides])))
+
+    def run_focus(self, focus, w, aspect, mainlobe_radius, sidelobe_radius, pnp_scale, line_pts=None,
+                  centroid_factor=10 ** (-3 / 20)):
+        """Metrics of one focus.  ``w``: inverse focus matrix (4x4 or 3x4); ``line_pts``: list of three (n,3)
+        arrays of grid coordinates (or None).  Returns (metrics dict, [line value arrays])."""
+        q = lifu_focus_query()
+        w = np.asarray(w, dtype=np.float64)
+        for i in range(3):
+            for j in range(4):
+                q.w[i][j] = float(w[i, j])
+            q.aspect[i] = float(aspect[i])
+        q.mainlobe_radius, q.sidelobe_radius = float(mainlobe_radius), float(sidelobe_radius)
+        q.centroid_factor = float(centroid_factor)
+        q.pnp_scale = float(pnp_scale)
+        pts = vals = None
+        sizes = [0, 0, 0]
+        if line_pts is not None:
+            sizes = [int(np.shape(p)[0]) for p in line_pts]
+            pts = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 3) for p in line_pts]))
+            vals = np.empty(pts.shape[0], dtype=np.float64)
+        q.n_line[:] = sizes
+        m = lifu_focus_metrics()
+        _check(self._lib.lifu_analysis_run_focus(self._h, int(focus), C.byref(q), _ptr(pts), C.byref(m), _ptr(vals)))
+        lines = []
+        if vals is not None:
+            o = 0
+            for k in sizes:
+                lines.append(vals[o:o + k])
+                o += k
+        return m.as_dict(), lines

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import base64
 import json
+import os
 import tempfile
 from dataclasses import asdict, dataclass, field
 from datetime import datetime
@@ -73,6 +74,22 @@ def _masked_max(values: np.ndarray, mask: np.ndarray) -> float:
     return float(sel.max()) if sel.size else float("nan")
 
 
+def _pick_engine(engine, simulation_result) -> str:
+    engine = engine or os.environ.get("LIFU_ANALYZE") or None
+    if engine is None:
+        from ..util.checkgpu import gpu_available
+        ok = False
+        try:
+            ok = (np.asarray(simulation_result["p_min"].data).dtype == np.float32
+                  and simulation_result["p_min"].ndim == 4 and gpu_available())
+        except Exception:  # noqa: BLE001
+            ok = False
+        engine = "cuda" if ok else "host"
+    if engine not in ("cuda", "host"):
+        raise ValueError(f"Unknown analysis engine '{engine}' (expected 'cuda' or 'host')")
+    return engine
+
+
 @dataclass
 class Solution:
     id: str = "solution"
@@ -129,11 +146,20 @@ class Solution:
 
     # ------------------------------------------------------------------------------ analysis
     def analyze(self, options: SolutionAnalysisOptions = SolutionAnalysisOptions(),
-                param_constraints: Dict[str, ParameterConstraint] | None = None) -> SolutionAnalysis:
+                param_constraints: Dict[str, ParameterConstraint] | None = None,
+                engine: str | None = None) -> SolutionAnalysis:
         """Beam metrics per focus (reference ``analyze``, solution.py:135-281).
 
         One pass per focus over the grid: the focus-frame distance map gives the main-lobe /
-        side-lobe selections, six trilinear line scans give the beam widths."""
+        side-lobe selections, six trilinear line scans give the beam widths.
+
+        ``engine`` (not in the reference): ``"cuda"`` evaluates the O(V) passes with the ``lifu_analysis_*``
+        kernels of liblifusim and raises if the library or a GPU is missing; ``"host"`` is the
+        numpy evaluation the reference's own analysis corresponds to.  ``None``: ``$LIFU_ANALYZE`` if set, else
+        "cuda" when a GPU is visible and the fields have the solver's dtypes, else "host"."""
+        engine = _pick_engine(engine, self.simulation_result)
+        if engine == "cuda":
+            return self._analyze_cuda(options, param_constraints)
         out = SolutionAnalysis()
         units = options.distance_units
         dt = 1 / (self.pulse.frequency * 20)
@@ -228,6 +254,135 @@ class Solution:
             out.p0_MPa += [1e-6 * float(np.max(p0_Pa))]
 
         out.global_ispta_mWcm2 = float(np.nanmax(ita_v * z_ok[None, None, None, :]))
+        out.MI = float(np.max(out.mainlobe_pnp_MPa) / np.sqrt(self.pulse.frequency * 1e-6))
+        out.TIC = float(np.mean(TIC))
+        out.voltage_V = self.voltage
+        out.power_W = float(np.mean(power_W))
+        out.param_constraints = {} if param_constraints is None else param_constraints
+        return out
+
+    def _analyze_cuda(self, options: SolutionAnalysisOptions,
+                      param_constraints: Dict[str, ParameterConstraint] | None = None) -> SolutionAnalysis:
+        """``analyze`` with every pass over the fields on the GPU (``lifu_analysis_*``, csrc/analysis.cu).
+
+        The fields are staged once in their stored units (float32 Pa, float64 W/cm^2): the unit factors are
+        monotone, so they are applied to the reduced values in the order ``rescale_data_arr`` / ``get_ita``
+        apply them to the arrays -- the results are the same floating-point numbers."""
+        from .. import _lib
+        from ..sim.kwave_if import _device
+        out = SolutionAnalysis()
+        units = options.distance_units
+        dt = 1 / (self.pulse.frequency * 20)
+        input_signal_V = self.pulse.calc_pulse(self.pulse.calc_time(dt)) * self.voltage
+        res = self.simulation_result
+        p_da, i_da = res["p_min"], res["intensity"]
+        if list(p_da.dims)[0] != "focal_point_index" or p_da.ndim != 4:
+            raise ValueError("the device analysis expects fields of dims (focal_point_index, x, y, z)")
+        pnp_raw = np.asarray(p_da.data)
+        ipa_raw = np.asarray(i_da.data)
+        if pnp_raw.dtype != np.float32:
+            raise ValueError(f"the device analysis expects the solver's float32 p_min, got {pnp_raw.dtype}")
+        if ipa_raw.dtype != np.float64:
+            ipa_raw = ipa_raw.astype(np.float64)
+        pnp_scale = np.float32(getunitconversion(p_da.attrs["units"], "MPa"))
+        ipa_scale = getunitconversion(i_da.attrs["units"], "W/cm^2")
+        ita_scale = getunitconversion(i_da.attrs["units"], "mW/cm^2")
+        dc_pt, dc_seq = self.get_pulsetrain_dutycycle(), self.get_sequence_dutycycle()
+        if min(ipa_scale, ita_scale, dc_pt, dc_seq, float(pnp_scale)) < 0:
+            raise ValueError("negative unit factor")
+
+        def to_ipa(v):      # rescale_data_arr(intensity, "W/cm^2")
+            return v * ipa_scale
+
+        def to_ita(v):      # get_ita: rescale to mW/cm^2, then the two duty cycles, left to right
+            return v * ita_scale * dc_pt * dc_seq
+
+        if options.sidelobe_radius is np.nan:
+            options.sidelobe_radius = options.mainlobe_radius
+        dims = list(p_da.dims)[1:]
+        axes, to_mm_axes = [], []
+        for d in dims:
+            c = p_da.coords[d]
+            cu = c.attrs.get("units", None)
+            a = np.asarray(c.data, dtype=np.float64)
+            axes.append(getunitconversion(cu, units) * a if cu is not None else a)     # rescale_coords
+            to_mm_axes.append(getunitconversion(units, "mm"))
+        z_ok = axes[2] > options.sidelobe_zmin
+        ar = options.mainlobe_aspect_ratio
+
+        standoff_Z = options.standoff_density * 1500
+        c_tic = 40e-3
+        d_eq_cm = np.sqrt(4 * self.transducer.get_area("cm") / np.pi)
+        ele_sizes_cm2 = np.array([el.get_area("cm") for el in self.transducer.elements])
+        out.duty_cycle_pulse_train_pct = dc_pt * 100
+        out.duty_cycle_sequence_pct = dc_seq * 100
+        seq = self.sequence
+        if seq.pulse_train_interval == 0:
+            out.sequence_duration_s = float(seq.pulse_interval * seq.pulse_count * seq.pulse_train_count)
+        else:
+            out.sequence_duration_s = float(seq.pulse_train_interval * seq.pulse_train_count)
+
+        nf = self.num_foci()
+        power_W = np.zeros(nf)
+        TIC = np.zeros(nf)
+        to_mm = getunitconversion(units, "mm")
+        global_all = np.nan
+        with _lib.BeamAnalysis(axes, nf, z_ok=z_ok, device=_device()) as ana:
+            for i in range(nf):
+                ana.set_focus(i, pnp_raw[i], ipa_raw[i])
+            for i in range(nf):
+                focus = self.foci[i].get_position(units=units)
+                focus_mm = self.foci[i].get_position(units="mm")
+                out.target_position_lat_mm += [focus_mm[0]]
+                out.target_position_ele_mm += [focus_mm[1]]
+                out.target_position_ax_mm += [focus_mm[2]]
+                apod = self.apodizations[i]
+                origin = self.transducer.get_effective_origin(apodizations=apod, units=units)
+                p0_Pa = np.max(self.transducer.calc_output(input_signal_V.copy(), dt, delays=self.delays[i, :], apod=apod), axis=1)
+
+                frame = FocusFrame(focus, origin)
+                offs, pts = [], []
+                for k, scale in enumerate(ar):
+                    o = np.linspace(-scale * options.beamwidth_radius, scale * options.beamwidth_radius, pnp_raw.shape[1 + k] * 2)
+                    offs.append(o)
+                    pts.append(frame.line(k, o))
+                m, lines = ana.run_focus(i, frame.inverse, ar, options.mainlobe_radius, options.sidelobe_radius,
+                                         pnp_scale, line_pts=pts)
+                pk = m["main_pnp"]
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    tot = np.float32(m["cen_w"])          # the reference's total is a float32 sum
+                    cen = [float(np.float64(m[key]) / tot * s) for key, s in zip(("cen_wx", "cen_wy", "cen_wz"), to_mm_axes)]
+                out.focal_centroid_lat_mm += [cen[0]]
+                out.focal_centroid_ele_mm += [cen[1]]
+                out.focal_centroid_ax_mm += [cen[2]]
+                out.mainlobe_pnp_MPa += [pk]
+                for k, named in enumerate(("lat", "ele", "ax")):
+                    for db in (3, 6):
+                        neg, pos = _bounds_from_line(offs[k], lines[k], pk * 10 ** (-db / 20))
+                        name = f"beamwidth_{named}_{db}dB_mm"
+                        setattr(out, name, [*getattr(out, name), to_mm * (pos - neg)])
+                out.mainlobe_isppa_Wcm2 += [float(to_ipa(m["main_ipa"]))]
+                out.mainlobe_ispta_mWcm2 += [float(to_ita(m["main_ipa_all"]))]
+                side_pnp, side_ipa = m["side_pnp"], float(to_ipa(m["side_ipa"]))
+                out.sidelobe_pnp_MPa += [side_pnp]
+                out.sidelobe_isppa_Wcm2 += [side_ipa]
+                out.sidelobe_to_mainlobe_pressure_ratio += [_ratio(side_pnp, out.mainlobe_pnp_MPa[-1])]
+                out.sidelobe_to_mainlobe_intensity_ratio += [_ratio(side_ipa, out.mainlobe_isppa_Wcm2[-1])]
+                out.global_pnp_MPa += [m["global_pnp"]]
+                out.global_isppa_Wcm2 += [float(to_ipa(m["global_ipa"]))]
+                global_all = m["global_ipa_all"]
+
+                i0ta_Wcm2 = (p0_Pa ** 2 / (2 * standoff_Z)) * 1e-4 * out.duty_cycle_sequence_pct / 100
+                power_W[i] = np.mean(np.sum(i0ta_Wcm2 * ele_sizes_cm2 * self.apodizations[i, :]))
+                TIC[i] = power_W[i] / (d_eq_cm * c_tic)
+                out.p0_MPa += [1e-6 * float(np.max(p0_Pa))]
+
+        # nanmax(ita * z_ok): planes with z_ok False contribute ita * 0 = 0 (NaN where ita is not finite)
+        cands = [to_ita(global_all)]
+        if not bool(np.all(z_ok)):
+            cands.append(0.0)
+        cands = [c for c in cands if not np.isnan(c)]
+        out.global_ispta_mWcm2 = float(max(cands)) if cands else float("nan")
         out.MI = float(np.max(out.mainlobe_pnp_MPa) / np.sqrt(self.pulse.frequency * 1e-6))
         out.TIC = float(np.mean(TIC))
         out.voltage_V = self.voltage

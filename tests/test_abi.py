@@ -69,3 +69,13 @@ def test_bad_arguments_are_value_errors(lifu_lib):
         lifu_lib.pml_auto((0, 4, 4))
     with pytest.raises(ValueError):
         lifu_lib.make_time((4, 4, 4), (1e-3,) * 3, c_ref=-1.0)
+
+
+def test_device_analysis_without_gpu_fails_loudly(lifu_lib):
+    """Solution.analyze(engine="cuda") has no CPU fallback: without a GPU the C ABI refuses."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ax = [np.linspace(0, 1, 4)] * 3
+    with pytest.raises(lifu_lib.LifuError, match="no CPU fallback"):
+        lifu_lib.BeamAnalysis(ax, 1)
