@@ -88,7 +88,7 @@ def c4(n_inner: int = 216, num_spokes: int = 31):
     cfg = c2(n_inner)
     cfg["name"] = "C4"
     cfg["focal_pattern"] = focal_patterns.Wheel(center=True, num_spokes=num_spokes, spoke_radius=5.0, distance_units="mm")
-    cfg["sequence"] = Sequence(pulse_count=num_spokes + 1)
+    cfg["sequence"] = Sequence(pulse_interval=0.1, pulse_count=num_spokes + 1, pulse_train_interval=0.1 * (num_spokes + 1))
     return cfg
 
 
