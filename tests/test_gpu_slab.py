@@ -64,22 +64,39 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("case,exchange", [("water", "peer"), ("water", "nccl"), ("phantom", "auto")])
-def test_two_rank_slab(lifu_lib, tmp_path, case, exchange):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+def _run_ranks(tmp_path, world, case, exchange):
     out = tmp_path / "res.json"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
            "127.0.0.1", "--master-port", str(_free_port()), str(ROOT / "tests" / "slab_rank.py"), "--case", case,
            "--exchange", exchange, "--out", str(out)]
     r = subprocess.run(cmd, cwd=str(ROOT), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
-    assert res["finite"] and res["world"] == 2
+    assert res["finite"] and res["world"] == world
     for k in ("p_max", "p_min"):
         assert res["vs_single"][k] < 1e-5, res
         assert res["vs_oracle"][k] < TOL, res
+    return res
+
+
+@pytest.mark.parametrize("case,exchange", [("water", "peer"), ("water", "nccl"), ("phantom", "auto")])
+def test_two_rank_slab(lifu_lib, tmp_path, case, exchange):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _run_ranks(tmp_path, 2, case, exchange)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+@pytest.mark.parametrize("case,exchange", [("water", "nccl"), ("phantom", "peer")])
+def test_many_rank_slab(lifu_lib, tmp_path, world, case, exchange):
+    """64^3 expanded grid over 4 / 8 ranks (8 planes per rank at 8: the first and last ranks hold only PML planes
+    and write no sensor data)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
+    res = _run_ranks(tmp_path, world, case, exchange)
+    assert sum(nz for _, nz in res["planes"]) == 36
 
 
 @pytest.mark.parametrize("case", ["water", "phantom"])
