@@ -325,7 +325,7 @@ class Protocol:
             return solution, None, None
         # pressures: max over foci; intensity: mean over foci (protocol.py:382-392)
         res = solution.simulation_result
-        aggregated = deepcopy(res).drop_dims("focal_point_index")
+        aggregated = deepcopy(res.drop_dims("focal_point_index"))     # every field carries the dim: copy what is left
         aggregated["p_min"] = res["p_min"].max(dim="focal_point_index", keep_attrs=True)
         aggregated["p_max"] = res["p_max"].max(dim="focal_point_index", keep_attrs=True)
         aggregated["intensity"] = res["intensity"].mean(dim="focal_point_index", keep_attrs=True)

@@ -82,13 +82,19 @@ class SegmentationMethod(ABC):
         # one gather through a per-label lookup table instead of a boolean pass per material;
         # labels outside the table keep the reference's initial value 0
         n_mat = len(materials)
-        valid = (labels >= 0) & (labels < n_mat)
-        safe = np.where(valid, labels, 0).astype(np.intp)
+        lo, hi = (int(labels.min()), int(labels.max())) if labels.size else (0, 0)
+        uniform = lo == hi                                        # e.g. the reference-material volume of UniformWater
+        if not uniform:
+            valid = (labels >= 0) & (labels < n_mat)
+            safe = np.where(valid, labels, 0).astype(np.intp)
         params = xa.Dataset()
         for pid in PARAM_INFO:
             info = Material.param_info(pid)
             lut = np.array([getattr(m, pid) for m in materials.values()], dtype=np.float64)
-            data = np.where(valid, lut[safe], 0.0)
+            if uniform:
+                data = np.full(labels.shape, lut[lo] if 0 <= lo < n_mat else 0.0, dtype=np.float64)
+            else:
+                data = np.where(valid, lut[safe], 0.0)
             params[pid] = xa.DataArray(data, coords=seg.coords, dims=seg.dims,
                                        attrs={"units": info["units"], "long_name": info["name"],
                                               "ref_value": ref.get_param(pid)})

@@ -440,15 +440,15 @@ if not HAVE_XARRAY:
             return self._replace(data, dims=dims, keep_attrs=keep_attrs)
 
         def max(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
-            fn = np.nanmax if (skipna and self._data.dtype.kind == "f") else np.max
+            fn = _skipna(np.max, np.nanmax) if (skipna and self._data.dtype.kind == "f") else np.max
             return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
         def min(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
-            fn = np.nanmin if (skipna and self._data.dtype.kind == "f") else np.min
+            fn = _skipna(np.min, np.nanmin) if (skipna and self._data.dtype.kind == "f") else np.min
             return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
         def mean(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
-            fn = np.nanmean if (skipna and self._data.dtype.kind == "f") else np.mean
+            fn = _skipna(np.mean, np.nanmean) if (skipna and self._data.dtype.kind == "f") else np.mean
             return self._reduce(_quiet(fn), dim, keep_attrs, axis=axis)
 
         def sum(self, dim=None, keep_attrs=False, skipna=True, axis=None, out=None, **_kw):
@@ -580,6 +580,16 @@ if not HAVE_XARRAY:
 
         def to_dataset(self, name=None):
             return Dataset({name or self.name: self})
+
+    def _skipna(plain, nan_aware):
+        """NaN-skipping reduction that only pays for the NaN handling when a NaN is there: the plain reduction
+        propagates NaN, so a NaN-free result is already the NaN-skipping one (same summation order for mean)."""
+        def g(a, axis=None, **kw):
+            r = plain(a, axis=axis, **kw)
+            if np.isnan(r).any():
+                return nan_aware(a, axis=axis, **kw)
+            return r
+        return g
 
     def _quiet(fn):
         def g(a, axis=None, **kw):
@@ -791,7 +801,17 @@ if not HAVE_XARRAY:
                 labels.append(c.data.item() if c is not None else len(labels))
         first = pieces[0]
         ax = first.dims.index(dim)
-        data = np.concatenate([np.asarray(p.data) for p in pieces], axis=ax)
+        arrs = [np.asarray(p.data) for p in pieces]
+        if (ax == 0 and first.ndim > 2 and all(a.shape[0] == 1 and a.dtype == arrs[0].dtype and a.shape == arrs[0].shape
+                                                and a[0].flags.f_contiguous and not a[0].flags.c_contiguous for a in arrs)):
+            # Fortran-ordered pieces (what run_simulation returns, kwave_if.py:132-141 reshape(order='F')): keep every
+            # piece's memory order inside the stack, so stacking is one block copy per piece instead of a strided transpose
+            buf = np.empty((len(arrs),) + arrs[0].shape[1:][::-1], dtype=arrs[0].dtype)
+            data = buf.transpose((0,) + tuple(range(first.ndim - 1, 0, -1)))
+            for i, a in enumerate(arrs):
+                data[i] = a[0]
+        else:
+            data = np.concatenate(arrs, axis=ax)
         out = first._replace(data)
         out._coords = Coordinates()
         for k, v in first._coords._vars.items():
