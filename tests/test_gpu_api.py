@@ -1,0 +1,124 @@
+"""The public API on one B200: openlifu_b200.sim.run_simulation and Protocol.calc_solution (the calls OpenLIFU
+makes, /root/reference/src/openlifu/sim/kwave_if.py:80-146 and plan/protocol.py:242-398) against the CPU oracle
+run on the same plain-data scene.  Tolerance: 1e-4 relative L2 on p_max / p_min / intensity (north star); the
+Dataset layout (dims, dtypes, attrs, DataArray names) is compared exactly."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from oracle import scene as osc
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _scene(arr, params, sensitivity):
+    coords = [np.asarray(params.coords[d].data, dtype=np.float64) for d in ("x", "y", "z")]
+    pos = np.array([el.get_position(units="m") for el in arr.elements])
+    size = np.array([el.get_size(units="m") for el in arr.elements])
+    ang = np.array([el.get_angle(units="deg") for el in arr.elements])
+    return osc.Scene(coords=coords, coord_scale=1e-3, elem_pos_m=pos, elem_size_m=size, elem_angles_deg=ang,
+                     sound_speed=np.asarray(params["sound_speed"].data), density=np.asarray(params["density"].data),
+                     attenuation=np.asarray(params["attenuation"].data), sensitivity=sensitivity)
+
+
+def _setup(spacing=1.0, steps=70):
+    from openlifu_b200.seg import seg_methods
+    from openlifu_b200.sim import SimSetup
+    from openlifu_b200.xdc import Transducer
+    arr = Transducer.gen_matrix_array(nx=3, ny=2, pitch=3, kerf=0.5, units="mm", sensitivity=1e5)
+    setup = SimSetup(spacing=spacing, x_extent=(-14, 14), y_extent=(-12, 12), z_extent=(-3, 30), dt=2.5e-7, t_end=steps * 2.5e-7)
+    params = setup.setup_sim_scene(seg_methods.UniformWater())
+    return arr, setup, params
+
+
+def test_run_simulation_matches_oracle_and_reference_layout(lifu_lib):
+    from openlifu_b200.bf import delay_methods
+    from openlifu_b200.geo import Point
+    from openlifu_b200.sim import run_simulation
+    arr, setup, params = _setup()
+    delays = delay_methods.Direct().calc_delays(arr, Point(position=(1.0, -2.0, 20.0), units="mm"), params)
+    apod = np.array([1.0, 0.0, 0.5, 1.0, 1.0, 0.25])            # one element switched off, ragged weights
+    ds, out = run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=400e3, cycles=3, amplitude=2.0,
+                             dt=setup.dt, t_end=setup.t_end, gpu=True)
+    want = osc.run_simulation(_scene(arr, params, 1e5), delays=delays, apod=apod, freq=400e3, cycles=3, amplitude=2.0,
+                              dt=setup.dt, t_end=setup.t_end)
+    assert list(ds.data_vars) == ["p_max", "p_min", "intensity"]                 # kwave_if.py:142-145
+    n = tuple(len(params.coords[d]) for d in ("x", "y", "z"))
+    for k, dtype, units, long_name in (("p_max", np.float32, "Pa", "PPP"), ("p_min", np.float32, "Pa", "PNP"),
+                                       ("intensity", np.float64, "W/cm^2", "Intensity")):
+        da = ds[k]
+        assert tuple(da.dims) == ("x", "y", "z") and np.asarray(da.data).shape == n
+        assert np.asarray(da.data).dtype == dtype and np.asarray(da.data).flags.writeable
+        assert da.attrs["units"] == units and da.attrs["long_name"] == long_name
+        assert cases.rel_l2(da.data, want[k]) < TOL, k
+    assert float(np.asarray(ds["p_min"].data).max()) > 0                          # PNP is stored sign-flipped (:136)
+    # defaults: delays -> zeros, apod -> ones (kwave_if.py:98-99)
+    ds0, _ = run_simulation(arr=arr, params=params, freq=400e3, cycles=3, dt=setup.dt, t_end=setup.t_end)
+    want0 = osc.run_simulation(_scene(arr, params, 1e5), freq=400e3, cycles=3, dt=setup.dt, t_end=setup.t_end)
+    assert cases.rel_l2(ds0["p_max"].data, want0["p_max"]) < TOL
+
+
+def test_run_simulation_heterogeneous_and_ref_values_only(lifu_lib):
+    from openlifu_b200.sim import run_simulation
+    arr, setup, params = _setup(steps=80)
+    shape = np.asarray(params["sound_speed"].data).shape
+    c0, rho0, al = cases.layered_phantom(shape)
+    params["sound_speed"].data[...] = c0
+    params["density"].data[...] = rho0
+    params["attenuation"].data[...] = al
+    kw = dict(freq=400e3, cycles=2, dt=1.5e-7, t_end=80 * 1.5e-7)
+    ds, _ = run_simulation(arr=arr, params=params, **kw)
+    want = osc.run_simulation(_scene(arr, params, 1e5), **kw)
+    for k in ("p_max", "p_min", "intensity"):
+        assert cases.rel_l2(ds[k].data, want[k]) < TOL, k
+    # ref_values_only: the medium is the maps' ref_value scalars (kwave_if.py:52-56), the intensity still uses the maps
+    ds_r, _ = run_simulation(arr=arr, params=params, ref_values_only=True, **kw)
+    sc = _scene(arr, params, 1e5)
+    sc.extras["ref_values"] = {k: params[k].attrs["ref_value"] for k in ("sound_speed", "density", "attenuation")}
+    want_r = osc.run_simulation(sc, ref_values_only=True, **kw)
+    for k in ("p_max", "p_min", "intensity"):
+        assert cases.rel_l2(ds_r[k].data, want_r[k]) < TOL, k
+    assert cases.rel_l2(ds_r["p_max"].data, ds["p_max"].data) > 1e-2                # really a different medium
+
+
+def test_calc_solution_wheel_on_gpu(lifu_lib):
+    """Per-focus loop, stacking, scaling, aggregation and both analysis engines on real solver output."""
+    from openlifu_b200.bf import Pulse, Sequence, focal_patterns
+    from openlifu_b200.geo import Point
+    from openlifu_b200.plan import Protocol, SolutionAnalysisOptions
+    from openlifu_b200.sim import SimSetup
+    from openlifu_b200.xdc import Transducer
+    arr = Transducer.gen_matrix_array(nx=4, ny=4, pitch=3, kerf=0.5, units="mm", sensitivity=1e5)
+    setup = SimSetup(spacing=1.0, x_extent=(-15, 15), y_extent=(-15, 15), z_extent=(-3, 36), dt=2.5e-7, t_end=110 * 2.5e-7)
+    pattern = focal_patterns.Wheel(center=True, num_spokes=2, spoke_radius=3, distance_units="mm", target_pressure=0.3, units="MPa")
+    pr = Protocol(pulse=Pulse(frequency=400e3, duration=3 / 400e3), sequence=Sequence(pulse_interval=0.01, pulse_count=3, pulse_train_interval=0),
+                  focal_pattern=pattern, sim_setup=setup)
+    target = Point(position=np.array([0.0, 0.0, 22.0]), units="mm", id="tgt")
+    opts = SolutionAnalysisOptions(mainlobe_radius=2.5, beamwidth_radius=5.0, sidelobe_radius=3.0, sidelobe_zmin=1.0, distance_units="mm")
+    sol_raw, _, _ = pr.calc_solution(target, arr, simulate=True, scale=False, analysis_options=opts)
+    res = sol_raw.simulation_result
+    assert tuple(res["p_min"].dims) == ("focal_point_index", "x", "y", "z") and res["p_min"].data.shape[0] == 3
+    params = setup.setup_sim_scene(pr.seg_method)
+    sc = _scene(arr, params, 1e5)
+    geometry = osc.source_geometry(sc)
+    for i, focus in enumerate(sol_raw.foci):
+        want = osc.run_simulation(sc, delays=sol_raw.delays[i], apod=sol_raw.apodizations[i], freq=400e3, cycles=3,
+                                  dt=setup.dt, t_end=setup.t_end, geometry=geometry)
+        for k in ("p_max", "p_min", "intensity"):
+            assert cases.rel_l2(res[k].data[i], want[k]) < TOL, (i, k)
+    # scaled solution: analysis engines agree, every focus reaches the target pressure, aggregation = max / mean
+    sol, agg, ana = pr.calc_solution(target, arr, simulate=True, scale=True, analysis_options=opts)
+    host = sol.analyze(options=opts, engine="host")
+    dev = sol.analyze(options=opts, engine="cuda")
+    for k, v in host.__dict__.items():
+        if k == "param_constraints" or v is None:
+            continue
+        np.testing.assert_allclose(np.asarray(getattr(dev, k), dtype=float), np.asarray(v, dtype=float), rtol=1e-6,
+                                   equal_nan=True, err_msg=k)
+    np.testing.assert_allclose(ana.mainlobe_pnp_MPa, [0.3] * 3, rtol=1e-5)
+    r = sol.simulation_result
+    assert np.array_equal(agg["p_min"].data, np.max(r["p_min"].data, axis=0))
+    np.testing.assert_allclose(agg["intensity"].data, np.mean(r["intensity"].data, axis=0), rtol=1e-12)
