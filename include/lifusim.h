@@ -235,7 +235,9 @@ typedef struct lifu_focus_metrics {
   int64_t n_main, n_side, n_global;        /* voxels in each selection */
   double cen_w, cen_wx, cen_wy, cen_wz;    /* sum of w, w*x, w*y, w*z over the -3 dB part of the main lobe */
   int64_t n_centroid;
-  double kernel_ms;                        /* CUDA-event time of this call's kernels */
+  double kernel_ms;                        /* CUDA-event time from the first to the last kernel of this call
+                                              (includes the host round trip between the two passes) */
+  double reduce_ms;                        /* CUDA-event time of k_focus_reduce alone (the pass that streams the fields) */
 } lifu_focus_metrics;
 
 int lifu_analysis_create(int device, void* cuda_stream, const int32_t n[3], int32_t n_foci, const double* x,

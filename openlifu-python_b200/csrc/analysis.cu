@@ -29,34 +29,15 @@ struct AnaGeom {
   const unsigned char* z_ok;
 };
 
-__device__ __forceinline__ void ana_index(const AnaGeom& g, unsigned m, int& ix, int& iy, int& iz) {
-  unsigned i2 = m % (unsigned)g.md[2];
-  unsigned t = m / (unsigned)g.md[2];
-  unsigned i1 = t % (unsigned)g.md[1];
-  unsigned i0 = t / (unsigned)g.md[1];
-  int li[3];
-  li[0] = li[1] = li[2] = 0;
-#pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    if (g.ax_of[0] == a) li[a] = (int)i0;
-    else if (g.ax_of[1] == a) li[a] = (int)i1;
-    else li[a] = (int)i2;
-  }
-  ix = li[0]; iy = li[1]; iz = li[2];
-}
-
-// sqrt(sum_i (((t_i0[x] + t_i1[y]) + t_i2[z]) + w_i3) / ar_i)^2), the order of FocusFrame.distance
-// (host mirror of calc_dist_from_focus, solution_analysis.py:384-403)
-__device__ __forceinline__ double ana_dist(const AnaGeom& g, int ix, int iy, int iz) {
-  double acc = 0.0;
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    double c = __dadd_rn(__dadd_rn(__dadd_rn(__ldg(g.t[i][0] + ix), __ldg(g.t[i][1] + iy)), __ldg(g.t[i][2] + iz)), g.w3[i]);
-    c = __ddiv_rn(c, g.ar[i]);
-    acc = __dadd_rn(acc, __dmul_rn(c, c));
-  }
-  return __dsqrt_rn(acc);
-}
+// Selection of one voxel: main lobe (dist < r_main) and "outside the side-lobe radius" (dist > r_side), decided
+// exactly as the reference does, i.e. on sqrt_rn(sum_i ((c_i / ar_i)^2)).  The divisions and the square root are only
+// evaluated for voxels whose squared distance (formed with reciprocals) lies within 1e-12 relative of a threshold:
+// the two evaluations differ by a few ulp (< 2e-15 relative), so outside that band the comparison cannot flip.
+struct AnaBand {
+  double inv_ar[3];
+  double lo_m, hi_m, lo_s, hi_s;   // r^2 (1 -+ 1e-12) for the main-lobe and the side-lobe radius
+  int exact_only;                  // degenerate radii: always take the exact path
+};
 
 constexpr int ANA_THREADS = 256;
 constexpr int N_MAX = 8;   // main/side/global pnp, main/side/global ipa, main/global ipa over all foci
@@ -75,38 +56,110 @@ __device__ __forceinline__ long long warp_sum_ll(long long v) {
   return v;
 }
 
-// fmax() returns the non-NaN operand, so starting from NaN gives "maximum ignoring NaN, NaN when nothing
-// was selected" -- the semantics of DataArray.where(mask).max().
-__global__ void __launch_bounds__(ANA_THREADS)
-k_focus_reduce(AnaGeom g, const float* __restrict__ pnp, const double* __restrict__ ipa,
+// The reference's distance, operation by operation (rare path).
+__device__ __forceinline__ double ana_exact_dist(double c0, double c1, double c2, double a0, double a1, double a2) {
+  const double q0 = __ddiv_rn(c0, a0), q1 = __ddiv_rn(c1, a1), q2 = __ddiv_rn(c2, a2);
+  double e = __dmul_rn(q0, q0);                       // 0 + q0^2
+  e = __dadd_rn(e, __dmul_rn(q1, q1));
+  e = __dadd_rn(e, __dmul_rn(q2, q2));
+  return __dsqrt_rn(e);
+}
+
+// Row-wise traversal shared by the two field passes: a warp owns rows of the fastest memory axis (lanes stride over
+// it, so loads are coalesced and no per-voxel division is needed); the focus-frame terms of the two slower axes are
+// row constants.  FAST = logical axis (0 x, 1 y, 2 z) that is fastest in memory.
+template <int FAST>
+struct AnaRow {
+  double ra[3], rb[3];      // row-constant terms of the two non-fast axes, in logical axis order
+  const double* tf[3];      // per-voxel term tables of the fast axis
+  static constexpr int A = FAST == 0 ? 1 : 0, B = FAST == 2 ? 1 : 2;   // the two slow logical axes, ascending
+  int ia, ib;               // the row's indices along A and B
+  __device__ __forceinline__ void begin(const AnaGeom& g, unsigned row) {
+    const unsigned i1 = row % (unsigned)g.md[1], i0 = row / (unsigned)g.md[1];
+    const bool swapped = g.ax_of[0] != A;                               // memory dim 0 holds logical axis B
+    ia = (int)(swapped ? i1 : i0);
+    ib = (int)(swapped ? i0 : i1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      ra[i] = __ldg(g.t[i][A] + ia);
+      rb[i] = __ldg(g.t[i][B] + ib);
+      tf[i] = g.t[i][FAST];
+    }
+  }
+  __device__ __forceinline__ int index_of(int axis, int k) const { return axis == FAST ? k : (axis == A ? ia : ib); }
+  // ((t_x + t_y) + t_z) + w3 in the reference's order, whichever axis is the per-voxel one
+  __device__ __forceinline__ double coord(const AnaGeom& g, int i, int k) const {
+    const double v = __ldg(tf[i] + k);
+    double c;
+    if (FAST == 0) c = __dadd_rn(__dadd_rn(v, ra[i]), rb[i]);
+    else if (FAST == 1) c = __dadd_rn(__dadd_rn(ra[i], v), rb[i]);
+    else c = __dadd_rn(__dadd_rn(ra[i], rb[i]), v);
+    return __dadd_rn(c, g.w3[i]);
+  }
+  __device__ __forceinline__ void select(const AnaGeom& g, const AnaBand& b, double r_main, double r_side, int k,
+                                         bool& in_main, bool& out_side) const {
+    double c[3], acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      c[i] = coord(g, i, k);
+      const double s = c[i] * b.inv_ar[i];
+      acc = fma(s, s, acc);
+    }
+    const bool near_m = acc > b.lo_m && acc < b.hi_m, near_s = acc > b.lo_s && acc < b.hi_s;
+    if (b.exact_only || near_m || near_s) {
+      const double d = ana_exact_dist(c[0], c[1], c[2], g.ar[0], g.ar[1], g.ar[2]);
+      in_main = d < r_main;
+      out_side = d > r_side;
+    } else {
+      in_main = acc <= b.lo_m;
+      out_side = acc >= b.hi_s;
+    }
+  }
+};
+
+// fmax() / fmaxf() return the non-NaN operand, so starting from NaN gives "maximum ignoring NaN, NaN when nothing
+// was selected" -- the semantics of DataArray.where(mask).max().  The pressure maxima are taken in float32 (the
+// field's own type; the conversion to float64 is monotone and exact).
+template <int FAST>
+__global__ void __launch_bounds__(ANA_THREADS, 3)
+k_focus_reduce(AnaGeom g, AnaBand band, const float* __restrict__ pnp, const double* __restrict__ ipa,
                const double* __restrict__ ipa_all, float scale, double r_main, double r_side,
                double* __restrict__ part_max, long long* __restrict__ part_cnt) {
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-  double mx[N_MAX];
-#pragma unroll
-  for (int k = 0; k < N_MAX; ++k) mx[k] = qnan;
-  long long cnt[N_CNT] = {0, 0, 0};
-  for (unsigned m = blockIdx.x * ANA_THREADS + threadIdx.x; m < g.V; m += gridDim.x * ANA_THREADS) {
-    int ix, iy, iz;
-    ana_index(g, m, ix, iy, iz);
-    double d = ana_dist(g, ix, iy, iz);
-    bool zok = g.z_ok[iz] != 0;
-    bool in_main = d < r_main;
-    bool in_side = (d > r_side) && zok;
-    double p = (double)__fmul_rn(pnp[m], scale);
-    double I = ipa[m];
-    double Ia = ipa_all[m];
-    if (in_main) { mx[0] = fmax(mx[0], p); mx[3] = fmax(mx[3], I); mx[6] = fmax(mx[6], Ia); ++cnt[0]; }
-    if (in_side) { mx[1] = fmax(mx[1], p); mx[4] = fmax(mx[4], I); ++cnt[1]; }
-    if (zok)     { mx[2] = fmax(mx[2], p); mx[5] = fmax(mx[5], I); mx[7] = fmax(mx[7], Ia); ++cnt[2]; }
+  const float qnanf = __int_as_float(0x7fc00000);
+  float mp[3] = {qnanf, qnanf, qnanf};                 // main / side / global pressure
+  double mi[5] = {qnan, qnan, qnan, qnan, qnan};       // main / side / global intensity, main / global over all foci
+  int cnt[N_CNT] = {0, 0, 0};
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned rows = (unsigned)g.md[0] * (unsigned)g.md[1], nfast = (unsigned)g.md[2];
+  const unsigned warps = gridDim.x * (ANA_THREADS / 32);
+  AnaRow<FAST> R;
+  for (unsigned row = blockIdx.x * (ANA_THREADS / 32) + wid; row < rows; row += warps) {
+    R.begin(g, row);
+    const size_t base = (size_t)row * nfast;
+    const bool row_zok = FAST == 2 ? true : g.z_ok[R.index_of(2, 0)] != 0;
+    for (unsigned k = lane; k < nfast; k += 32) {
+      // the streamed operands first, so that they are in flight while the selection is evaluated
+      const float praw = __ldcs(pnp + base + k);
+      const double I = __ldcs(ipa + base + k);
+      const double Ia = __ldcs(ipa_all + base + k);
+      bool in_main, out_side;
+      R.select(g, band, r_main, r_side, (int)k, in_main, out_side);
+      const bool zok = FAST == 2 ? g.z_ok[k] != 0 : row_zok;
+      const bool in_side = out_side && zok;
+      const float p = __fmul_rn(praw, scale);
+      if (in_main) { mp[0] = fmaxf(mp[0], p); mi[0] = fmax(mi[0], I); mi[3] = fmax(mi[3], Ia); ++cnt[0]; }
+      if (in_side) { mp[1] = fmaxf(mp[1], p); mi[1] = fmax(mi[1], I); ++cnt[1]; }
+      if (zok)     { mp[2] = fmaxf(mp[2], p); mi[2] = fmax(mi[2], I); mi[4] = fmax(mi[4], Ia); ++cnt[2]; }
+    }
   }
+  double mx[N_MAX] = {(double)mp[0], (double)mp[1], (double)mp[2], mi[0], mi[1], mi[2], mi[3], mi[4]};
   __shared__ double s_mx[ANA_THREADS / 32][N_MAX];
   __shared__ long long s_cnt[ANA_THREADS / 32][N_CNT];
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < N_MAX; ++k) { double v = warp_fmax(mx[k]); if (lane == 0) s_mx[wid][k] = v; }
 #pragma unroll
-  for (int k = 0; k < N_CNT; ++k) { long long v = warp_sum_ll(cnt[k]); if (lane == 0) s_cnt[wid][k] = v; }
+  for (int k = 0; k < N_CNT; ++k) { long long v = warp_sum_ll((long long)cnt[k]); if (lane == 0) s_cnt[wid][k] = v; }
   __syncthreads();
   if (threadIdx.x < N_MAX) {
     double v = qnan;
@@ -121,27 +174,35 @@ k_focus_reduce(AnaGeom g, const float* __restrict__ pnp, const double* __restric
 }
 
 // w = pnp where (main lobe and pnp > cutoff) else 0 (float32, as the reference's where()); sums of w and w*axis.
+template <int FAST>
 __global__ void __launch_bounds__(ANA_THREADS)
-k_focus_centroid(AnaGeom g, const float* __restrict__ pnp, float scale, double r_main, float cutoff,
+k_focus_centroid(AnaGeom g, AnaBand band, const float* __restrict__ pnp, float scale, double r_main, float cutoff,
                  double* __restrict__ part_sum, long long* __restrict__ part_cnt) {
   double s[4] = {0, 0, 0, 0};
   long long cnt = 0;
-  for (unsigned m = blockIdx.x * ANA_THREADS + threadIdx.x; m < g.V; m += gridDim.x * ANA_THREADS) {
-    int ix, iy, iz;
-    ana_index(g, m, ix, iy, iz);
-    if (!(ana_dist(g, ix, iy, iz) < r_main)) continue;
-    float p = __fmul_rn(pnp[m], scale);
-    if (!(p > cutoff)) continue;
-    double w = (double)p;
-    s[0] += w;
-    s[1] += w * __ldg(g.axis[0] + ix);
-    s[2] += w * __ldg(g.axis[1] + iy);
-    s[3] += w * __ldg(g.axis[2] + iz);
-    ++cnt;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned rows = (unsigned)g.md[0] * (unsigned)g.md[1], nfast = (unsigned)g.md[2];
+  const unsigned warps = gridDim.x * (ANA_THREADS / 32);
+  AnaRow<FAST> R;
+  for (unsigned row = blockIdx.x * (ANA_THREADS / 32) + wid; row < rows; row += warps) {
+    R.begin(g, row);
+    const size_t base = (size_t)row * nfast;
+    for (unsigned k = lane; k < nfast; k += 32) {
+      bool in_main, out_side;
+      R.select(g, band, r_main, r_main, (int)k, in_main, out_side);
+      if (!in_main) continue;
+      const float p = __fmul_rn(pnp[base + k], scale);
+      if (!(p > cutoff)) continue;
+      const double w = (double)p;
+      s[0] += w;
+      s[1] += w * __ldg(g.axis[0] + R.index_of(0, (int)k));
+      s[2] += w * __ldg(g.axis[1] + R.index_of(1, (int)k));
+      s[3] += w * __ldg(g.axis[2] + R.index_of(2, (int)k));
+      ++cnt;
+    }
   }
   __shared__ double s_s[ANA_THREADS / 32][4];
   __shared__ long long s_c[ANA_THREADS / 32];
-  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < 4; ++k) { double v = warp_sum(s[k]); if (lane == 0) s_s[wid][k] = v; }
   { long long v = warp_sum_ll(cnt); if (lane == 0) s_c[wid] = v; }
@@ -221,7 +282,7 @@ struct lifu_analysis {
   double* d_pts = nullptr;
   double* d_line = nullptr;
   int line_cap = 0;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
 };
 
 static void ana_free(lifu_analysis* a) {
@@ -233,6 +294,7 @@ static void ana_free(lifu_analysis* a) {
     if (p) cudaFree(p);
   if (a->e0) cudaEventDestroy(a->e0);
   if (a->e1) cudaEventDestroy(a->e1);
+  if (a->e2) cudaEventDestroy(a->e2);
   delete a;
 }
 
@@ -292,6 +354,7 @@ int lifu_analysis_create(int device, void* cuda_stream, const int32_t n[3], int3
   if (e == cudaSuccess) e = cudaMemcpyAsync(a->d_zok, zk.data(), (size_t)n[2], cudaMemcpyHostToDevice, a->stream);
   if (e == cudaSuccess) e = cudaEventCreate(&a->e0);
   if (e == cudaSuccess) e = cudaEventCreate(&a->e1);
+  if (e == cudaSuccess) e = cudaEventCreate(&a->e2);
   if (e == cudaSuccess) e = cudaStreamSynchronize(a->stream);
   if (e != cudaSuccess) { set_error("lifu_analysis_create: %s", cudaGetErrorString(e)); ana_free(a); return LIFU_ERR_CUDA; }
   *out = a;
@@ -387,12 +450,29 @@ int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_qu
   g.z_ok = a->d_zok;
   LIFU_CUDA(cudaMemcpyAsync(a->d_terms, terms.data(), terms.size() * sizeof(double), cudaMemcpyHostToDevice, st));
 
+  AnaBand band, band_c;
+  {
+    const double rm = q->mainlobe_radius, rs = q->sidelobe_radius, eps = 1e-12;
+    for (int i = 0; i < 3; ++i) band.inv_ar[i] = 1.0 / q->aspect[i];
+    band.lo_m = rm * rm * (1.0 - eps); band.hi_m = rm * rm * (1.0 + eps);
+    band.lo_s = rs * rs * (1.0 - eps); band.hi_s = rs * rs * (1.0 + eps);
+    band.exact_only = !(rm > 0.0 && rs > 0.0 && std::isfinite(rm) && std::isfinite(rs)) ? 1 : 0;
+    band_c = band;                                   // centroid pass: only the main-lobe radius matters
+    band_c.lo_s = band.lo_m; band_c.hi_s = band.hi_m;
+  }
   const float* dp = a->d_pnp + (size_t)focus * a->V;
   const double* di = a->d_ipa + (size_t)focus * a->V;
   LIFU_CUDA(cudaEventRecord(a->e0, st));
-  k_focus_reduce<<<a->blocks, ANA_THREADS, 0, st>>>(g, dp, di, a->d_all, q->pnp_scale, q->mainlobe_radius, q->sidelobe_radius,
-                                                    a->d_part, a->d_cnt);
+  const int fast = a->ax_of[2];
+#define ANA_FAST(KERNEL, ...)                                                          \
+  do {                                                                                 \
+    if (fast == 0) KERNEL<0><<<a->blocks, ANA_THREADS, 0, st>>>(__VA_ARGS__);          \
+    else if (fast == 1) KERNEL<1><<<a->blocks, ANA_THREADS, 0, st>>>(__VA_ARGS__);     \
+    else KERNEL<2><<<a->blocks, ANA_THREADS, 0, st>>>(__VA_ARGS__);                    \
+  } while (0)
+  ANA_FAST(k_focus_reduce, g, band, dp, di, a->d_all, q->pnp_scale, q->mainlobe_radius, q->sidelobe_radius, a->d_part, a->d_cnt);
   LIFU_CUDA(cudaGetLastError());
+  LIFU_CUDA(cudaEventRecord(a->e2, st));
   std::vector<double> hmax((size_t)a->blocks * N_MAX);
   std::vector<long long> hcnt((size_t)a->blocks * N_CNT);
   LIFU_CUDA(cudaMemcpyAsync(hmax.data(), a->d_part, hmax.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -413,7 +493,7 @@ int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_qu
   // centroid of the -3 dB part of the main lobe; the cutoff is compared in float32 like the float32 field is
   const volatile double cut64 = out->main_pnp * q->centroid_factor;
   float cutoff = (float)cut64;
-  k_focus_centroid<<<a->blocks, ANA_THREADS, 0, st>>>(g, dp, q->pnp_scale, q->mainlobe_radius, cutoff, a->d_part, a->d_cnt);
+  ANA_FAST(k_focus_centroid, g, band_c, dp, q->pnp_scale, q->mainlobe_radius, cutoff, a->d_part, a->d_cnt);
   LIFU_CUDA(cudaGetLastError());
   if (n_pts > 0) {
     if (n_pts > a->line_cap) {
@@ -448,6 +528,8 @@ int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_qu
   float ms = 0.f;
   LIFU_CUDA(cudaEventElapsedTime(&ms, a->e0, a->e1));
   out->kernel_ms = ms;
+  LIFU_CUDA(cudaEventElapsedTime(&ms, a->e0, a->e2));
+  out->reduce_ms = ms;
   return LIFU_OK;
 }
 

@@ -60,7 +60,7 @@ class lifu_focus_metrics(C.Structure):
                 ("main_ipa_all", C.c_double), ("global_ipa_all", C.c_double),
                 ("n_main", C.c_int64), ("n_side", C.c_int64), ("n_global", C.c_int64),
                 ("cen_w", C.c_double), ("cen_wx", C.c_double), ("cen_wy", C.c_double), ("cen_wz", C.c_double),
-                ("n_centroid", C.c_int64), ("kernel_ms", C.c_double)]
+                ("n_centroid", C.c_int64), ("kernel_ms", C.c_double), ("reduce_ms", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}

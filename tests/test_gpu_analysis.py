@@ -172,7 +172,7 @@ def test_selection_sizes_and_lines_bit_exact():
         assert m["n_centroid"] == int(sel.sum())
         np.testing.assert_allclose(m["cen_w"], pm[sel].sum(), rtol=1e-12)
     for key in results[0][0]:
-        if key != "kernel_ms":
+        if key not in ("kernel_ms", "reduce_ms"):
             np.testing.assert_allclose(results[0][0][key], results[1][0][key], rtol=1e-13, err_msg=key)
 
 
@@ -203,7 +203,8 @@ def test_full_size_properties_c2():
             t2 = time.perf_counter()
         out.append(ms)
         print(f"216^3 x 2 foci: staging {1e3 * (t1 - t0):.1f} ms, analysis {1e3 * (t2 - t1):.2f} ms wall, "
-              f"kernels {ms[0]['kernel_ms']:.3f} + {ms[1]['kernel_ms']:.3f} ms")
+              f"kernels {ms[0]['kernel_ms']:.3f} + {ms[1]['kernel_ms']:.3f} ms, k_focus_reduce {ms[0]['reduce_ms']:.4f} + "
+              f"{ms[1]['reduce_ms']:.4f} ms = {20 * n ** 3 / ms[1]['reduce_ms'] / 1e6:.0f} GB/s")
     for f in range(2):
         a, b = out[0][f], out[1][f]
         for k in ("main_pnp", "side_pnp", "global_pnp", "cen_w", "cen_wx", "cen_wy", "cen_wz"):
@@ -214,3 +215,27 @@ def test_full_size_properties_c2():
         vol = 4.0 / 3.0 * np.pi * 2.5 * 2.5 * 12.5
         assert abs(a["n_main"] * voxel / vol - 1.0) < 0.02
         assert a["n_global"] == int(z_ok.sum()) * n * n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("aspect", [(1.0, 1.0, 1.0), (1.0, 1.0, 5.0), (3.0, 0.7, 1.3)])
+def test_voxels_exactly_on_the_radius(aspect):
+    """Axis-aligned focus frame on a 0.5 mm lattice: many voxels sit exactly on the 2.5 mm radius (3-4-5 triples), where
+    `dist < r` / `dist > r` must come out as numpy computes them (the kernel's reciprocal pre-test may not decide these)."""
+    ax = [np.arange(-20, 21) * 0.5, np.arange(-18, 19) * 0.5, 20.0 + np.arange(0, 61) * 0.5]
+    rng = np.random.default_rng(3)
+    p = (1e6 * rng.random((41, 37, 61))).astype(np.float32)
+    I = p.astype(np.float64) ** 2 * 1e-10
+    frame = FocusFrame(np.array([0.0, 0.0, 30.0]), np.zeros(3))
+    dist = frame.distance(ax, aspect)
+    on = int((dist == 2.5).sum())
+    if aspect == (1.0, 1.0, 1.0):
+        assert on >= 30
+    main, side = dist < 2.5, dist > 2.5
+    with _lib.BeamAnalysis(ax, 1) as ana:
+        ana.set_focus(0, p, I)
+        m, _ = ana.run_focus(0, frame.inverse, aspect, 2.5, 2.5, np.float32(1e-6))
+    assert m["n_main"] == int(main.sum()) and m["n_side"] == int(side.sum())
+    assert m["n_main"] + m["n_side"] + on == p.size
+    pm = (p * np.float32(1e-6)).astype(np.float64)
+    assert m["main_pnp"] == pm[main].max() and m["side_pnp"] == pm[side].max() and m["side_ipa"] == I[side].max()
