@@ -138,11 +138,15 @@ k_focus_reduce(AnaGeom g, AnaBand band, const float* __restrict__ pnp, const dou
     R.begin(g, row);
     const size_t base = (size_t)row * nfast;
     const bool row_zok = FAST == 2 ? true : g.z_ok[R.index_of(2, 0)] != 0;
+    // register double buffer over the row: the streamed operands of element k + 32 are in flight while element k
+    // is classified
+    float praw_n = 0.f;
+    double I_n = 0.0, Ia_n = 0.0;
+    if ((unsigned)lane < nfast) { praw_n = __ldcs(pnp + base + lane); I_n = __ldcs(ipa + base + lane); Ia_n = __ldcs(ipa_all + base + lane); }
     for (unsigned k = lane; k < nfast; k += 32) {
-      // the streamed operands first, so that they are in flight while the selection is evaluated
-      const float praw = __ldcs(pnp + base + k);
-      const double I = __ldcs(ipa + base + k);
-      const double Ia = __ldcs(ipa_all + base + k);
+      const float praw = praw_n;
+      const double I = I_n, Ia = Ia_n;
+      if (k + 32 < nfast) { praw_n = __ldcs(pnp + base + k + 32); I_n = __ldcs(ipa + base + k + 32); Ia_n = __ldcs(ipa_all + base + k + 32); }
       bool in_main, out_side;
       R.select(g, band, r_main, r_side, (int)k, in_main, out_side);
       const bool zok = FAST == 2 ? g.z_ok[k] != 0 : row_zok;
