@@ -490,7 +490,7 @@ def main():
             ds, out = kwave_if.run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=freq, cycles=cycles,
                                               dt=cfg["setup"].dt, t_end=cfg["setup"].t_end, cfl=cfg["setup"].cfl,
                                               amplitude=amp, gpu=True)
-            med = 3 * 4 if homog else 3 * 4 * n_inner_vox
+            med = 3 * 4 if homog else 3 * 8 * n_inner_vox      # float64 maps go up as they are (lifu_set_medium_f64)
             h2d = med + 4 * base.size + 8 * arr.numelements()
             d2h = 2 * 4 * n_inner_vox
             api_loop_ms.append(out["stats"]["loop_ms"])

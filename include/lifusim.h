@@ -102,6 +102,14 @@ int lifu_destroy(lifu_sim* sim);
 int lifu_set_medium(lifu_sim* sim, const float* c0, const float* rho0, const float* alpha_db,
                     float alpha_power, int alpha_mode, int homogeneous);
 
+/* Same as lifu_set_medium for heterogeneous media, taking the arrays the reference holds --
+ * params['sound_speed'|'density'|'attenuation'].data: float64, (Nx,Ny,Nz), C order (sim_setup.py:107-116,
+ * seg_method.py:84-97) -- without a host-side conversion: each map is copied as one block and rounded to
+ * float32 (round-to-nearest, = data_cast='single') and re-laid out on the device.  stride = element
+ * strides of (x, y, z); must describe a dense array.  alpha_db may be NULL.  Not for slab handles. */
+int lifu_set_medium_f64(lifu_sim* sim, const double* c0, const double* rho0, const double* alpha_db,
+                        const int64_t stride[3], float alpha_power, int alpha_mode);
+
 /* Replaces get_karray + get_array_binary_mask + the weight half of
  * get_distributed_source_signal (kwave_if.py:29-47,75-77): off-grid rectangular elements
  * spread with the truncated-sinc band-limited interpolant, computed on the GPU.

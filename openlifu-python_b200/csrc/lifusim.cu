@@ -435,8 +435,10 @@ int lifu_destroy(lifu_sim* s) {
   return LIFU_OK;
 }
 
+// stride64 != NULL: the maps are float64 arrays of the whole inner grid with those element strides (x, y, z).
 static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
-                           float alpha_power, int alpha_mode, int homogeneous, int plane0, int n_planes) {
+                           float alpha_power, int alpha_mode, int homogeneous, int plane0, int n_planes,
+                           const int64_t* stride64 = nullptr) {
   if (!s || !c0 || !rho0) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
   if (alpha_mode < 0 || alpha_mode > 2) { set_error("lifu_set_medium: alpha_mode %d unknown", alpha_mode); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(s->device));
@@ -498,9 +500,14 @@ static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, cons
     const float* src[3] = {c0, rho0, alpha_db};
     float* dst[3] = {s->d_c0e, s->d_rho0e, s->d_alphae};
     for (int m = 0; m < 3; ++m) {
-      if (src[m]) {
+      if (src[m] && stride64) {
+        // float64 maps in the caller's layout: one block copy, conversion + re-layout on the device
+        LIFU_CUDA(cudaMemcpyAsync(stage, src[m], sizeof(double) * (size_t)s->Vin, cudaMemcpyDefault, st));
+        k_expand_edge<double><<<gbe, 256, 0, st>>>(reinterpret_cast<const double*>(stage), dst[m], P, 0, n_exp,
+                                                   stride64[0], stride64[1], stride64[2]);
+      } else if (src[m]) {
         LIFU_CUDA(cudaMemcpyAsync(stage, src[m] + (long long)(need_lo - plane0) * plane, inb, cudaMemcpyDefault, st));
-        k_expand_edge<<<gbe, 256, 0, st>>>(stage, dst[m], P, need_lo, n_exp);
+        k_expand_edge<float><<<gbe, 256, 0, st>>>(stage, dst[m], P, need_lo, n_exp, 1, s->n[0], plane);
       } else {
         k_fill<<<gbe, 256, 0, st>>>(dst[m], Ve, 0.f);
       }
@@ -541,6 +548,27 @@ static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, cons
 int lifu_set_medium(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
                     float alpha_power, int alpha_mode, int homogeneous) {
   return set_medium_impl(s, c0, rho0, alpha_db, alpha_power, alpha_mode, homogeneous, 0, s ? s->n[2] : 0);
+}
+
+int lifu_set_medium_f64(lifu_sim* s, const double* c0, const double* rho0, const double* alpha_db,
+                        const int64_t stride[3], float alpha_power, int alpha_mode) {
+  if (!s || !c0 || !rho0 || !stride) { set_error("lifu_set_medium_f64: null argument"); return LIFU_ERR_INVALID; }
+  if (s->sl.on) { set_error("lifu_set_medium_f64: not available on a slab handle (use lifu_set_medium_planes)"); return LIFU_ERR_STATE; }
+  // the strides must be a dense permutation of (Nx, Ny, Nz): the array is copied as one block
+  int order[3] = {0, 1, 2};
+  std::sort(order, order + 3, [&](int a, int b) { return stride[a] < stride[b] || (stride[a] == stride[b] && s->n[a] < s->n[b]); });
+  int64_t expect = 1;
+  for (int k = 0; k < 3; ++k) {
+    if (s->n[order[k]] > 1 && stride[order[k]] != expect) {
+      set_error("lifu_set_medium_f64: strides (%lld, %lld, %lld) do not describe a dense (%d, %d, %d) array",
+                (long long)stride[0], (long long)stride[1], (long long)stride[2], s->n[0], s->n[1], s->n[2]);
+      return LIFU_ERR_INVALID;
+    }
+    expect *= s->n[order[k]];
+  }
+  if (sizeof(double) * (size_t)s->Vin > sizeof(float) * 3 * (size_t)s->RS) { set_error("lifu_set_medium_f64: staging area too small"); return LIFU_ERR_NOMEM; }
+  return set_medium_impl(s, reinterpret_cast<const float*>(c0), reinterpret_cast<const float*>(rho0),
+                         reinterpret_cast<const float*>(alpha_db), alpha_power, alpha_mode, 0, 0, s->n[2], stride);
 }
 
 int lifu_set_medium_planes(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,

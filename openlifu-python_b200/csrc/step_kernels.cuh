@@ -328,8 +328,11 @@ __global__ void k_fill(float* a, long long n, float v) {
 // Expand an inner-grid map to the PML-padded grid by edge replication (ledger A11).
 // `in` holds the inner planes [plane0, ...); `out` receives n_planes expanded planes starting at the
 // global plane P.z0 (a slab rank asks for one halo plane more than it owns: staggered density along z).
-__global__ void k_expand_edge(const float* __restrict__ in, float* __restrict__ out, StepParams P, int plane0,
-                              int n_planes) {
+// T = float: x-fastest planes (sx, sy, sz) = (1, nx, nx*ny).  T = double: the caller's float64 array with its own
+// element strides (e.g. C order: z fastest), rounded to float32 here exactly as numpy's astype(float32) rounds.
+template <typename T>
+__global__ void k_expand_edge(const T* __restrict__ in, float* __restrict__ out, StepParams P, int plane0,
+                              int n_planes, long long sx, long long sy, long long sz) {
   const long long n = (long long)P.Nx * P.Ny * n_planes;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -340,7 +343,7 @@ __global__ void k_expand_edge(const float* __restrict__ in, float* __restrict__ 
     int jx = min(max(ix - P.px, 0), P.nx - 1);
     int jy = min(max(iy - P.py, 0), P.ny - 1);
     int jz = min(max(iz - P.pz, 0), P.nz - 1) - plane0;
-    out[i] = in[((long long)jz * P.ny + jy) * P.nx + jx];
+    out[i] = (float)in[jz * sz + jy * sy + jx * sx];
   }
 }
 

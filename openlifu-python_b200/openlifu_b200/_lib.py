@@ -104,6 +104,7 @@ def load():
         "lifu_create": (C.c_int, [C.POINTER(lifu_grid), C.c_int, vp, C.POINTER(vp)]),
         "lifu_destroy": (C.c_int, [vp]),
         "lifu_set_medium": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int]),
+        "lifu_set_medium_f64": (C.c_int, [vp, vp, vp, vp, C.POINTER(i64), C.c_float, C.c_int]),
         "lifu_set_elements": (C.c_int, [vp, i32, vp, vp, vp, f64, i32, C.POINTER(i64)]),
         "lifu_set_source_geometry": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32]),
         "lifu_get_source_sizes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
@@ -134,7 +135,7 @@ def load():
 
 
 EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
-            "lifu_set_medium", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
+            "lifu_set_medium", "lifu_set_medium_f64", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
             "lifu_set_medium_planes", "lifu_analysis_create", "lifu_analysis_set_focus", "lifu_analysis_run_focus",
@@ -240,6 +241,19 @@ class LifuSim:
             arrs = [np.array([v if v is not None else 0.0], dtype=np.float32) for v in (c0, rho0, alpha_db)]
             _check(self._lib.lifu_set_medium(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power, mode, 1))
             return
+        if plane0 is None and self.layout is None:
+            # float64 maps of the whole grid (what SimSetup.setup_sim_scene produces): hand them over as they are,
+            # the float32 rounding and the x-fastest re-layout happen on the device
+            maps = [c0, rho0, alpha_db]
+            if all(m is None or (isinstance(m, np.ndarray) and m.dtype == np.float64 and m.shape == self.n) for m in maps):
+                ref = maps[0]
+                dense = ref.flags.c_contiguous or ref.flags.f_contiguous
+                same = all(m is None or m.strides == ref.strides for m in maps)
+                if dense and same:
+                    st = (C.c_int64 * 3)(*[v // 8 for v in ref.strides])
+                    _check(self._lib.lifu_set_medium_f64(self._h, _ptr(maps[0]), _ptr(maps[1]), _ptr(maps[2]), st,
+                                                         alpha_power, mode))
+                    return
         shape = self.n
         if plane0 is not None:
             nzp = max(np.shape(v)[2] for v in (c0, rho0, alpha_db) if np.ndim(v) == 3)

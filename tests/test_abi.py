@@ -17,7 +17,7 @@ ROOT = Path(__file__).resolve().parents[1]
 def declared_symbols():
     text = (ROOT / "include" / "lifusim.h").read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lifu_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(lifu_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_symbols_exported(lifu_lib):
