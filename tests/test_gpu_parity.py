@@ -245,3 +245,62 @@ def test_v2_heterogeneous_absorbing(lifu_lib, alpha_mode):
     v1 = cases.run_cuda_case(case, alpha_mode=alpha_mode, pipeline="v1")
     for k in ("p_max", "p_min"):
         assert cases.rel_l2(got[k], v1[k]) < 2e-5
+
+
+def _c2_case(steps=None, c0=1500.0, rho0=1000.0, alpha=0.0, amplitude=1.0):
+    from openlifu_b200 import configs
+    arr = configs.openlifu_2x_array()
+    half = 53.75
+    pos = np.array([el.position for el in arr.elements])
+    size = np.array([el.size for el in arr.elements])
+    ang = np.array([el.get_angle(units="deg") for el in arr.elements])
+    kw = {}
+    if steps is not None:
+        dt = 0.5 * 0.5e-3 / 1500
+        kw = dict(dt=dt, t_end=steps * dt)
+    return cases.make_case([(-half, half), (-half, half), (-4, 103.5)], 0.5, 0, 0, 0, 0, (0, 0, 50), 400e3, 20,
+                           elem_pos_mm=pos, elem_size_mm=size, angles_deg=ang, sensitivity=None, c0=c0, rho0=rho0,
+                           alpha=alpha, amplitude=amplitude, **kw)
+
+
+def test_c2_full_size_properties(lifu_lib):
+    """BASELINE config C2 at full size (256^3, all 749 steps), size-independent properties:
+    linearity (drive x2 -> fields x2, bit-exact: every operation of the step is linear and scaling by two is exact),
+    run-to-run determinism, agreement of the two independent FFT implementations (fused passes vs cuFFT) over the
+    whole run, and the focus where the geometry puts it."""
+    a = cases.run_cuda_case(_c2_case())
+    assert _is_v2(a) and a["stats"]["steps"] == 749 and tuple(a["stats"]["n_exp"]) == (256, 256, 256)
+    b = cases.run_cuda_case(_c2_case(amplitude=2.0))
+    for k in ("p_max", "p_min"):
+        assert np.array_equal(b[k], 2.0 * a[k]), k
+    again = cases.run_cuda_case(_c2_case())
+    assert np.array_equal(again["p_max"], a["p_max"]) and np.array_equal(again["p_min"], a["p_min"])
+    v1 = cases.run_cuda_case(_c2_case(), pipeline="v1")
+    assert not _is_v2(v1)
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(a[k], v1[k]) < 2e-5, k
+    pm = a["p_max"].reshape(216, 216, 216, order="F")
+    ix, iy, iz = np.unravel_index(np.argmax(pm[:, :, 40:]), pm[:, :, 40:].shape)
+    x = -53.75 + 0.5 * ix
+    y = -53.75 + 0.5 * iy
+    z = -4.0 + 0.5 * (iz + 40)
+    assert abs(x) <= 1.0 and abs(y) <= 1.0 and 40.0 <= z <= 52.0, (x, y, z)   # focal peak just short of the 50 mm geometric focus
+
+
+def test_c3_full_size_linearity_and_pipelines(lifu_lib):
+    """C3 (skull / brain phantom, absorbing) at full size: linearity bit-exact, fused pipeline == cuFFT pipeline."""
+    from openlifu_b200 import configs
+    cfg = configs.c3(216)
+    lab = np.asarray(cfg["volume"].data)
+    mats = list(configs.PHANTOM_MATERIALS.values())
+    c0 = np.array([m.sound_speed for m in mats])[lab]
+    rho0 = np.array([m.density for m in mats])[lab]
+    al = np.array([m.attenuation for m in mats])[lab]
+    a = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al))
+    assert _is_v2(a) and a["stats"]["absorbing"] == 1 and a["stats"]["homogeneous"] == 0
+    b = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al, amplitude=0.5))
+    for k in ("p_max", "p_min"):
+        assert np.array_equal(b[k], 0.5 * a[k]), k
+    v1 = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al), pipeline="v1")
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(a[k], v1[k]) < 5e-5, k
