@@ -490,9 +490,11 @@ def main():
             ds, out = kwave_if.run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=freq, cycles=cycles,
                                               dt=cfg["setup"].dt, t_end=cfg["setup"].t_end, cfl=cfg["setup"].cfl,
                                               amplitude=amp, gpu=True)
-            med = 3 * 4 if homog else 3 * 8 * n_inner_vox      # float64 maps go up as they are (lifu_set_medium_f64)
+            dev_pkg = os.environ.get("LIFU_PACKAGING", "host") == "device"
+            # float64 maps go up as they are (lifu_set_medium_f64); device packaging adds the float64 impedance map
+            med = (3 * 4 + (8 if dev_pkg else 0)) if homog else (3 * 8 + (8 if dev_pkg else 0)) * n_inner_vox
             h2d = med + 4 * base.size + 8 * arr.numelements()
-            d2h = 2 * 4 * n_inner_vox
+            d2h = ((4 + 4 + 8) if dev_pkg else 2 * 4) * n_inner_vox   # p_max, p_min (float32) [, intensity (float64)]
             api_loop_ms.append(out["stats"]["loop_ms"])
             return float(ds["p_min"].data.max())
 

@@ -147,6 +147,14 @@ int lifu_set_drive(lifu_sim* sim, const float* base_signal, int32_t n_base,
  * the raw minimum (the adapter negates it, kwave_if.py:136).  stats may be NULL. */
 int lifu_run(lifu_sim* sim, float* p_max, float* p_min, lifu_stats* stats);
 
+/* Replaces the packaging arithmetic of kwave_if.py:136-141 on the device.  lifu_set_two_z stores
+ * 2 * density * sound_speed of the params maps (float64: ONE value, or one per inner-grid voxel, x fastest;
+ * host or device pointer).  After lifu_run (whose p_max / p_min may then be NULL), lifu_get_packaged writes
+ * p_max, pnp = -p_min (float32) and intensity = 1e-4 * p_min^2 / two_z (float32 square and scale, float64
+ * divide -- the numpy expression, bit for bit) to the caller's buffers; p_max may be NULL. */
+int lifu_set_two_z(lifu_sim* sim, const double* two_z, int64_t n);
+int lifu_get_packaged(lifu_sim* sim, float* p_max, float* pnp, double* intensity);
+
 /* ---- one oversized grid over several GPUs (BASELINE.json config C5) ----
  * k-Wave's binaries are single-device, so nothing in the reference binds these; they extend the
  * kspaceFirstOrder3D replacement (kwave_if.py:117-129) to grids that do not fit one GPU.  One process

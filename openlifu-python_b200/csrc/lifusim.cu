@@ -1318,6 +1318,47 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   return LIFU_OK;
 }
 
+int lifu_set_two_z(lifu_sim* s, const double* two_z, int64_t n) {
+  if (!s || !two_z || (n != 1 && n != s->Vin)) { set_error("lifu_set_two_z: need 1 value or one per inner-grid voxel"); return LIFU_ERR_INVALID; }
+  if (s->sl.on) { set_error("lifu_set_two_z: not available on a slab handle"); return LIFU_ERR_STATE; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  if (n == 1) {
+    LIFU_CUDA(cudaMemcpyAsync(&s->two_z_s, two_z, sizeof(double), cudaMemcpyDefault, s->stream));
+    LIFU_CUDA(cudaStreamSynchronize(s->stream));
+    s->two_z_mode = 1;
+    return LIFU_OK;
+  }
+  if (!s->d_two_z) LIFU_CHECK(dev_alloc(s, (void**)&s->d_two_z, sizeof(double) * (size_t)s->Vin));
+  LIFU_CUDA(cudaMemcpyAsync(s->d_two_z, two_z, sizeof(double) * (size_t)s->Vin, cudaMemcpyDefault, s->stream));
+  LIFU_CUDA(cudaStreamSynchronize(s->stream));
+  s->two_z_mode = 2;
+  return LIFU_OK;
+}
+
+int lifu_get_packaged(lifu_sim* s, float* p_max, float* pnp, double* intensity) {
+  if (!s || !pnp || !intensity) { set_error("lifu_get_packaged: null argument"); return LIFU_ERR_INVALID; }
+  if (s->sl.on) { set_error("lifu_get_packaged: not available on a slab handle"); return LIFU_ERR_STATE; }
+  if (s->last.steps <= 0) { set_error("lifu_get_packaged: call lifu_run first"); return LIFU_ERR_STATE; }
+  if (s->two_z_mode == 0) { set_error("lifu_get_packaged: call lifu_set_two_z first"); return LIFU_ERR_STATE; }
+  LIFU_CUDA(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  // results are staged in the scratch field r3 (idle between runs): [Vin] float, then [Vin] double
+  float* d_pnp = s->P.r3;
+  double* d_int = reinterpret_cast<double*>(s->P.r3 + round_up(s->Vin, 4));
+  if (sizeof(float) * (size_t)round_up(s->Vin, 4) + sizeof(double) * (size_t)s->Vin > sizeof(float) * 3 * (size_t)s->RS) {
+    set_error("lifu_get_packaged: staging area too small");
+    return LIFU_ERR_NOMEM;
+  }
+  k_package<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P.pmin, s->two_z_mode == 2 ? s->d_two_z : nullptr, s->two_z_s,
+                                                         d_pnp, d_int, s->Vin);
+  LIFU_CUDA(cudaGetLastError());
+  if (p_max) LIFU_CUDA(cudaMemcpyAsync(p_max, s->P.pmax, sizeof(float) * (size_t)s->Vin, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaMemcpyAsync(pnp, d_pnp, sizeof(float) * (size_t)s->Vin, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaMemcpyAsync(intensity, d_int, sizeof(double) * (size_t)s->Vin, cudaMemcpyDefault, st));
+  LIFU_CUDA(cudaStreamSynchronize(st));
+  return LIFU_OK;
+}
+
 int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, char* names, int name_stride,
                         double* ms, double* bytes_per_voxel, int* n_stages) {
   if (!s || reps <= 0 || !ms || !n_stages) { set_error("lifu_profile_stages: bad argument"); return LIFU_ERR_INVALID; }

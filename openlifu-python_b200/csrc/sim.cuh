@@ -60,6 +60,9 @@ struct lifu_sim {
   float *d_c0e = nullptr, *d_rho0e = nullptr, *d_alphae = nullptr;
   float c0_s = 0, rho0_s = 0, alpha_s = 0;
   float* d_med = nullptr;      // packed derived maps
+  double* d_two_z = nullptr;   // 2 * density * sound_speed on the inner grid (float64, x fastest) for the intensity
+  double two_z_s = 0.0;        // ... or one value
+  int two_z_mode = 0;          // 0 not set, 1 scalar, 2 map
 
   // source geometry (device)
   long long n_src = 0, nnz = 0;

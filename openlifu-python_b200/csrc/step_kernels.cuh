@@ -347,6 +347,18 @@ __global__ void k_expand_edge(const T* __restrict__ in, float* __restrict__ out,
   }
 }
 
+// Packaging of kwave_if.py:136-141 on the device: p_min -> -p_min (float32) and
+// intensity = 1e-4 * p_min^2 / (2 Z) with the float32 square and scale and the float64 divide of the numpy expression.
+__global__ void k_package(const float* __restrict__ pmin, const double* __restrict__ two_z, double two_z_s,
+                          float* __restrict__ pnp, double* __restrict__ inten, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float p = pmin[i];
+    pnp[i] = -p;
+    const float sq = __fmul_rn(__fmul_rn(p, p), 1e-4f);
+    inten[i] = __ddiv_rn((double)sq, two_z ? two_z[i] : two_z_s);
+  }
+}
+
 // Derived medium maps on the expanded grid.  c0e/rho0e/alphae are the expanded maps;
 // alpha_np_coef = 100*(1e-6/2pi)^y/(20 log10 e) converts dB/(MHz^y cm) to Np/((rad/s)^y m).
 __global__ void k_derive_medium(const float* __restrict__ c0e, const float* __restrict__ rho0e,

@@ -111,6 +111,8 @@ def load():
         "lifu_get_source_geometry": (C.c_int, [vp, vp, vp, vp, vp]),
         "lifu_set_drive": (C.c_int, [vp, vp, i32, vp, vp, i32, C.c_int]),
         "lifu_run": (C.c_int, [vp, vp, vp, C.POINTER(lifu_stats)]),
+        "lifu_set_two_z": (C.c_int, [vp, vp, i64]),
+        "lifu_get_packaged": (C.c_int, [vp, vp, vp, vp]),
         "lifu_get_field": (C.c_int, [vp, C.c_int, vp]),
         "lifu_get_info": (C.c_int, [vp, C.POINTER(lifu_stats)]),
         "lifu_profile_stages": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int, C.POINTER(f64),
@@ -136,7 +138,7 @@ def load():
 
 EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
             "lifu_set_medium", "lifu_set_medium_f64", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
-            "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_get_field", "lifu_get_info",
+            "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_set_two_z", "lifu_get_packaged", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
             "lifu_set_medium_planes", "lifu_analysis_create", "lifu_analysis_set_focus", "lifu_analysis_run_focus",
             "lifu_analysis_destroy"]
@@ -315,6 +317,24 @@ class LifuSim:
         st = lifu_stats()
         _check(self._lib.lifu_run(self._h, _ptr(p_max), _ptr(p_min), C.byref(st)))
         return p_max, p_min, st.as_dict()
+
+    def set_two_z(self, two_z):
+        """2 * density * sound_speed for the intensity: a float, or a float64 array with one value per inner-grid
+        voxel, x fastest."""
+        a = np.ascontiguousarray(two_z, dtype=np.float64).reshape(-1)
+        _check(self._lib.lifu_set_two_z(self._h, _ptr(a), a.size))
+
+    def run_packaged(self):
+        """Time loop + the packaging of kwave_if.py:136-141 on the device: (p_max, -p_min, intensity, stats) as flat
+        x-fastest host arrays (float32, float32, float64)."""
+        st = lifu_stats()
+        _check(self._lib.lifu_run(self._h, None, None, C.byref(st)))
+        nvox = int(np.prod(self.n))
+        p_max = np.empty(nvox, dtype=np.float32)
+        pnp = np.empty(nvox, dtype=np.float32)
+        inten = np.empty(nvox, dtype=np.float64)
+        _check(self._lib.lifu_get_packaged(self._h, _ptr(p_max), _ptr(pnp), _ptr(inten)))
+        return p_max, pnp, inten, st.as_dict()
 
     def get_field(self, which):
         st = lifu_stats()

@@ -108,6 +108,8 @@ class _Session:
         self.geometry_key = None
         self.medium_key = None
         self.uniform = {}              # medium key -> "all three maps are constant" (decided once per maps object)
+        self.two_z_key = None          # which density / sound-speed maps the device-side impedance was made from
+        self.z_uniform = {}
         self.n_src = 0
 
 
@@ -221,6 +223,7 @@ def run_simulation(arr,
                 sim.set_medium(*[m[:, :, lo:lo + nz] for m in maps], alpha_power=0.9, alpha_mode=alpha_mode, plane0=lo)
             else:
                 sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode)
+    medium_changed = ses.medium_key != mkey
     ses.medium_key = mkey
     # source geometry (get_karray + get_array_binary_mask + BLI weights), cached per transducer
     pos, size, ang = element_geometry(arr, array_offset)
@@ -233,15 +236,57 @@ def run_simulation(arr,
     sim.set_drive(input_signal * base_gain, n_delay, gains,
                   source_mode=os.environ.get("LIFU_SOURCE_MODE", "additive"))
     log.info("Running simulation")
-    p_max_flat, p_min_flat, stats = sim.run()
-    if slab:
-        p_max_flat = _gather_planes(p_max_flat, sim.layout, kg["N"], world)
-        p_min_flat = _gather_planes(p_min_flat, sim.layout, kg["N"], world)
+    # LIFU_PACKAGING=device computes -p_min and the intensity on the GPU (lifu_get_packaged, bit-identical); the default
+    # stays on the host: the extra 8 bytes per voxel of device->host copy into fresh pageable memory cost more than the
+    # threaded host expression saves (bench.py e2e on C2: 642 ms vs 761 ms per call)
+    if slab or os.environ.get("LIFU_PACKAGING", "host") != "device":
+        p_max_flat, p_min_flat, stats = sim.run()
+        if slab:
+            p_max_flat = _gather_planes(p_max_flat, sim.layout, kg["N"], world)
+            p_min_flat = _gather_planes(p_min_flat, sim.layout, kg["N"], world)
+        log.info("Simulation Complete")
+        output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
+                  "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
+        return package_fields(params, output["p_max"], output["p_min"]), output
+    # the impedance of the packaging step always comes from the params maps (kwave_if.py:140), whatever medium was used
+    rho, c = params["density"].data, params["sound_speed"].data
+    zkey = (id(rho), id(c), _sample_checksum(rho), _sample_checksum(c))
+    if medium_changed or ses.two_z_key != zkey:
+        if zkey not in ses.z_uniform:
+            ses.z_uniform = {zkey: float(rho.min()) == float(rho.max()) and float(c.min()) == float(c.max())}
+        if ses.z_uniform[zkey]:
+            sim.set_two_z(2 * (rho.flat[0] * c.flat[0]))
+        else:
+            sim.set_two_z(_two_z_flat(params))
+        ses.two_z_key = zkey
+    p_max_flat, pnp_flat, inten_flat, stats = sim.run_packaged()
     log.info("Simulation Complete")
-    output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
-              "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
+    output = _Output({"p_max": p_max_flat, "pnp": pnp_flat, "stats": stats, "n_src": ses.n_src,
+                      "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay})
+    return package_arrays(params, p_max_flat, pnp_flat, inten_flat), output
 
-    return package_fields(params, output["p_max"], output["p_min"]), output
+
+class _Output(dict):
+    """The opaque second return value (callers bind it to ``_``, protocol.py:324).  ``"p_min"`` -- the raw minimum the
+    k-Wave binary would have returned -- is derived from the stored sign-flipped field only when somebody asks."""
+
+    def __missing__(self, key):
+        if key == "p_min":
+            self[key] = -1 * self["pnp"]
+            return self[key]
+        raise KeyError(key)
+
+
+def package_arrays(params, p_max_flat, pnp_flat, inten_flat):
+    """Flat x-fastest vectors already in their final form (device packaging) -> the Dataset of kwave_if.py:131-146."""
+    sz = list(params.coords.sizes.values())
+    p_max = xa.DataArray(p_max_flat.reshape(sz, order="F"), coords=params.coords, name="p_max",
+                         attrs={"units": "Pa", "long_name": "PPP"})
+    p_min = xa.DataArray(pnp_flat.reshape(sz, order="F"), coords=params.coords, name="p_min",
+                         attrs={"units": "Pa", "long_name": "PNP"})
+    intensity = xa.DataArray(inten_flat.reshape(sz, order="F"), coords=params.coords, name="I",
+                             attrs={"units": "W/cm^2", "long_name": "Intensity"})
+    return xa.Dataset({"p_max": p_max, "p_min": p_min, "intensity": intensity})
 
 
 _Z2_CACHE: dict = {}

@@ -34,7 +34,8 @@ def _setup(spacing=1.0, steps=70):
     return arr, setup, params
 
 
-def test_run_simulation_matches_oracle_and_reference_layout(lifu_lib):
+def test_run_simulation_matches_oracle_and_reference_layout(lifu_lib, monkeypatch):
+    monkeypatch.setenv("LIFU_PACKAGING", "device")     # exercise lifu_get_packaged; compared with the host packaging below
     from openlifu_b200.bf import delay_methods
     from openlifu_b200.geo import Point
     from openlifu_b200.sim import run_simulation
@@ -55,13 +56,19 @@ def test_run_simulation_matches_oracle_and_reference_layout(lifu_lib):
         assert da.attrs["units"] == units and da.attrs["long_name"] == long_name
         assert cases.rel_l2(da.data, want[k]) < TOL, k
     assert float(np.asarray(ds["p_min"].data).max()) > 0                          # PNP is stored sign-flipped (:136)
+    # the device packaging (lifu_get_packaged) is the reference's numpy expression bit for bit
+    from openlifu_b200.sim.kwave_if import package_fields
+    host = package_fields(params, out["p_max"], out["p_min"])
+    for k in ("p_max", "p_min", "intensity"):
+        assert np.array_equal(np.asarray(ds[k].data), np.asarray(host[k].data)), k
     # defaults: delays -> zeros, apod -> ones (kwave_if.py:98-99)
     ds0, _ = run_simulation(arr=arr, params=params, freq=400e3, cycles=3, dt=setup.dt, t_end=setup.t_end)
     want0 = osc.run_simulation(_scene(arr, params, 1e5), freq=400e3, cycles=3, dt=setup.dt, t_end=setup.t_end)
     assert cases.rel_l2(ds0["p_max"].data, want0["p_max"]) < TOL
 
 
-def test_run_simulation_heterogeneous_and_ref_values_only(lifu_lib):
+def test_run_simulation_heterogeneous_and_ref_values_only(lifu_lib, monkeypatch):
+    monkeypatch.setenv("LIFU_PACKAGING", "device")
     from openlifu_b200.sim import run_simulation
     arr, setup, params = _setup(steps=80)
     shape = np.asarray(params["sound_speed"].data).shape
@@ -70,10 +77,13 @@ def test_run_simulation_heterogeneous_and_ref_values_only(lifu_lib):
     params["density"].data[...] = rho0
     params["attenuation"].data[...] = al
     kw = dict(freq=400e3, cycles=2, dt=1.5e-7, t_end=80 * 1.5e-7)
-    ds, _ = run_simulation(arr=arr, params=params, **kw)
+    ds, out = run_simulation(arr=arr, params=params, **kw)
     want = osc.run_simulation(_scene(arr, params, 1e5), **kw)
+    from openlifu_b200.sim.kwave_if import package_fields
+    host = package_fields(params, out["p_max"], out["p_min"])
     for k in ("p_max", "p_min", "intensity"):
         assert cases.rel_l2(ds[k].data, want[k]) < TOL, k
+        assert np.array_equal(np.asarray(ds[k].data), np.asarray(host[k].data)), k     # impedance map on the device
     # ref_values_only: the medium is the maps' ref_value scalars (kwave_if.py:52-56), the intensity still uses the maps
     ds_r, _ = run_simulation(arr=arr, params=params, ref_values_only=True, **kw)
     sc = _scene(arr, params, 1e5)

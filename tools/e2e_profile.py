@@ -37,6 +37,10 @@ def main():
     kwave_if.get_kgrid = timed("get_kgrid", kwave_if.get_kgrid)
     kwave_if.element_geometry = timed("element_geometry", kwave_if.element_geometry)
     _lib.LifuSim.run = timed("sim.run", _lib.LifuSim.run)
+    _lib.LifuSim.run_packaged = timed("sim.run_packaged", _lib.LifuSim.run_packaged)
+    _lib.LifuSim.set_two_z = timed("sim.set_two_z", _lib.LifuSim.set_two_z)
+    kwave_if.package_arrays = timed("package_arrays", kwave_if.package_arrays)
+    kwave_if._sample_checksum = timed("checksums", kwave_if._sample_checksum)
     _lib.LifuSim.set_medium = timed("sim.set_medium", _lib.LifuSim.set_medium)
     _lib.LifuSim.set_drive = timed("sim.set_drive", _lib.LifuSim.set_drive)
     _lib.LifuSim.set_elements = timed("sim.set_elements", _lib.LifuSim.set_elements)
