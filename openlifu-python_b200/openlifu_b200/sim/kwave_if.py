@@ -304,6 +304,21 @@ def _two_z_flat(params):
     return hit
 
 
+_THREADS_SET = False
+
+
+def _host_threads(torch):
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the packaging expression is memory-bound host work, so give
+    each rank its share of the host cores (once)."""
+    global _THREADS_SET
+    if _THREADS_SET:
+        return
+    _THREADS_SET = True
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", "0") or 0)
+    if local >= 1 and torch.get_num_threads() == 1:
+        torch.set_num_threads(max(1, min(16, (os.cpu_count() or 1) // local)))
+
+
 def package_fields(params, p_max_flat, p_min_flat):
     """Flat x-fastest float32 sensor vectors -> the Dataset of kwave_if.py:131-146: p_max; p_min = -p_min;
     intensity = 1e-4 * p_min**2 / (2 * density * sound_speed) as float64 named 'I' under the key 'intensity'.
@@ -312,6 +327,7 @@ def package_fields(params, p_max_flat, p_min_flat):
     sz = list(params.coords.sizes.values())
     try:
         import torch
+        _host_threads(torch)
         tp = torch.from_numpy(p_min_flat)
         neg = torch.neg(tp).numpy()
         inten = ((torch.square(tp) * np.float32(1e-4)).double() / torch.from_numpy(_two_z_flat(params))).numpy()
