@@ -30,6 +30,7 @@ class Assumptions:
     alpha_power: float = 0.9             # kwave_if.py:55,61
     staggered_density: bool = True       # A9
     record_start: int = 0                # A8: p_max/p_min sampled from the first step
+    pml_size: tuple | None = None        # explicit PML thickness per axis (known-answer tests; None = pml_auto, A3)
 
 
 @dataclass
@@ -59,7 +60,7 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
     N_in = tuple(int(v) for v in inp.N)
     d = tuple(float(v) for v in inp.d)
     dt = float(inp.dt)
-    pml = kg.optimal_pml_size(N_in, asm.pml_range)
+    pml = tuple(int(v) for v in asm.pml_size) if asm.pml_size is not None else kg.optimal_pml_size(N_in, asm.pml_range)
     N = tuple(N_in[a] + 2 * pml[a] for a in range(3))
 
     homogeneous = np.ndim(inp.c0) == 0 and np.ndim(inp.rho0) == 0 and np.ndim(inp.alpha_db) == 0

@@ -304,3 +304,41 @@ def test_c3_full_size_linearity_and_pipelines(lifu_lib):
     v1 = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al), pipeline="v1")
     for k in ("p_max", "p_min"):
         assert cases.rel_l2(a[k], v1[k]) < 5e-5, k
+
+
+@pytest.mark.parametrize("pipeline,nxy,nz,d,z_src,z_int,t_end", [
+    ("v2", 64, 216, 0.5e-3, 20, 110, 60e-6),        # 64 x 64 x 256 with the z PML: fused-FFT pipeline
+    ("v1", 8, 728, 0.25e-3, 60, 380, 100e-6),       # 8 x 8 x 768: cuFFT pipeline, 12 / 20 points per wavelength
+])
+def test_planar_interface_transmission_known_answer(lifu_lib, pipeline, nxy, nz, d, z_src, z_int, t_end):
+    """Oracle-independent anchor of the CUDA path: a plane wave normally incident on a planar interface between two
+    media (c, rho = 1500, 1000 | 2500, 1800) is transmitted with pressure amplitude 2 Z2 / (Z1 + Z2) = 1.5.  No lateral
+    PML: the periodic solver makes the problem exactly one-dimensional.  Exercises heterogeneous sound speed, the
+    staggered density, explicit source geometry and the float64 map import."""
+    import os
+    from openlifu_b200 import _lib
+    from tests.test_oracle_physics import planar_interface_inputs
+    k = planar_interface_inputs(nxy=nxy, nz=nz, d=d, z_src=z_src, z_int=z_int, t_end=t_end)
+    n_src = k["idx"].size
+    os.environ["LIFU_PIPELINE"] = pipeline
+    try:
+        with _lib.LifuSim(k["N"], (d,) * 3, k["dt"], k["Nt"], pml=(0, 0, 20)) as sim:
+            sim.set_medium(k["c0"], k["rho0"], None)
+            sim.set_source_geometry(k["idx"], np.arange(n_src + 1), np.zeros(n_src), np.ones(n_src), 1)
+            sim.set_drive(k["sig"], [0], [1.0])
+            p_max, p_min, stats = sim.run()
+    finally:
+        os.environ.pop("LIFU_PIPELINE", None)
+    assert (stats["fft_launches"] == 0) == (pipeline == "v2") and stats["homogeneous"] == 0
+    pm = p_max.reshape(nz, nxy, nxy)                       # x fastest
+    assert np.allclose(pm, pm[:, :1, :1], rtol=1e-4, atol=1e-6 * pm.max())        # a plane wave stays a plane wave
+    line = pm[:, 3, 5].astype(np.float64)
+    half_pulse = int(0.5 * 4 / 500e3 * 1500.0 / d)         # cells covered by half the incident burst
+    m1 = line[z_src + half_pulse + 4:z_int - half_pulse - 8]                       # no overlap with the echo here
+    m2 = line[z_int + 12:z_int + 12 + int(0.7 * (nz - z_int))]
+    assert m1.std() / m1.mean() < 0.01 and m2[: m2.size // 2].std() / m2.mean() < 0.01
+    Z1, Z2 = k["Z"]
+    T = 2 * Z2 / (Z1 + Z2)
+    assert abs(m2[: m2.size // 2].mean() / m1.mean() - T) < 0.015 * T
+    # on the far side of the interface the pressure is the transmitted burst from the first cell on: (1 + R) A_i = T A_i
+    assert abs(line[z_int:z_int + 4].max() / m1.mean() - T) < 0.03 * T

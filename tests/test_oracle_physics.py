@@ -6,6 +6,8 @@ reference): they tie the CPU restatement to physics instead of to golden fields.
   * PML: outgoing pulse is absorbed (late-time energy << peak energy)
   * power-law absorption: amplitude ratio follows exp(-alpha * f^y * d)
   * float32 oracle vs float64 oracle: the noise floor quoted next to the 1e-4 GPU tolerance
+  * planar interface between two media (heterogeneous c and rho, staggered density): pressure reflection
+    (Z2-Z1)/(Z2+Z1) and transmission 2 Z2/(Z1+Z2) of a normally incident plane wave
 """
 from __future__ import annotations
 
@@ -100,3 +102,43 @@ def test_kgrid_conventions():
     sg = kg.pml_profile(30, 1e-3, 1e-7, 1500.0, 10, staggered=True)
     assert sg[-1] < p[-1] and sg[0] > p[0]                 # shifted by +1/2 cell
     assert kg.largest_prime_factor(81) == 3 and kg.largest_prime_factor(125) == 5 and kg.largest_prime_factor(97) == 97
+
+
+def planar_interface_inputs(nxy=16, nz=384, d=0.5e-3, z_src=40, z_int=200, c=(1500.0, 2500.0), rho=(1000.0, 1800.0),
+                            f0=500e3, cycles=4, t_end=100e-6, cfl=0.3):
+    """Laterally uniform two-layer medium with a plane source: with no lateral PML the periodic solver makes this an
+    exactly one-dimensional problem.  Shared with the GPU known-answer test (tests/test_gpu_parity.py)."""
+    N = (nxy, nxy, nz)
+    dt = cfl * d / max(c)
+    c0 = np.full(N, c[0]); c0[:, :, z_int:] = c[1]
+    rho0 = np.full(N, rho[0]); rho0[:, :, z_int:] = rho[1]
+    t = np.arange(0, cycles / f0, dt)
+    sig = np.sin(2 * np.pi * f0 * t) * np.hanning(t.size)
+    ix, iy = np.meshgrid(np.arange(nxy), np.arange(nxy), indexing="ij")
+    idx = np.sort((ix + nxy * (iy + nxy * z_src)).ravel().astype(np.int64))
+    return dict(N=N, d=d, dt=dt, Nt=int(round(t_end / dt)), c0=c0, rho0=rho0, sig=sig, idx=idx,
+                Z=(c[0] * rho[0], c[1] * rho[1]))
+
+
+def test_planar_interface_reflection_and_transmission():
+    k = planar_interface_inputs(nxy=4, nz=768, d=0.25e-3, z_src=80, z_int=400)      # 12 / 20 points per wavelength
+    inp = SolverInputs(N=k["N"], d=(k["d"],) * 3, dt=k["dt"], Nt=k["Nt"], c0=k["c0"], rho0=k["rho0"], alpha_db=0.0,
+                       src_idx=k["idx"], src_p=np.repeat(k["sig"][None, :], k["idx"].size, axis=0))
+    trace = []
+    pz = 20
+    simulate(inp, dtype=np.float64, asm=Assumptions(pml_size=(0, 0, pz)),
+             progress=lambda i, p: trace.append(p[1, 2, :].copy()))
+    tr = np.array(trace)                                  # (Nt, Nz_expanded): the field only depends on z
+    tt = np.arange(tr.shape[0]) * k["dt"]
+    a = tr[:, pz + 240]                                    # medium 1, between source and interface
+    b = tr[:, pz + 560]                                    # medium 2
+    # amplitude ratios from the pulse energies (insensitive to the residual dispersion in the layer with c != c_ref)
+    E_i = np.sum(a[tt < 45e-6] ** 2)
+    E_r = np.sum(a[tt > 60e-6] ** 2)
+    E_t = np.sum(b ** 2)
+    Z1, Z2 = k["Z"]
+    R, T = (Z2 - Z1) / (Z2 + Z1), 2 * Z2 / (Z1 + Z2)
+    assert abs(np.sqrt(E_r / E_i) - R) < 0.01 * R
+    assert abs(np.sqrt(E_t / E_i) - T) < 0.01 * T
+    assert abs(E_r / E_i + (E_t / E_i) * Z1 / Z2 - 1.0) < 0.01          # energy flux is conserved
+    assert abs(np.abs(b).max() / np.abs(a[tt < 45e-6]).max() - T) < 0.01 * T
