@@ -342,3 +342,75 @@ def test_planar_interface_transmission_known_answer(lifu_lib, pipeline, nxy, nz,
     assert abs(m2[: m2.size // 2].mean() / m1.mean() - T) < 0.015 * T
     # on the far side of the interface the pressure is the transmitted burst from the first cell on: (1 + R) A_i = T A_i
     assert abs(line[z_int:z_int + 4].max() / m1.mean() - T) < 0.03 * T
+
+
+def _lossy_wavenumber(f, c, alpha_db, y, dispersion=True):
+    from tests.test_oracle_physics import lossy_wavenumber
+    return lossy_wavenumber(f, c, alpha_db, y, dispersion)
+
+
+def _plane_wave_run(pipeline, nxy, nz, d, z_src, t_end, medium, cycles=4, fields=(), f0=500e3, alpha_mode="binary"):
+    """Plane source in a laterally periodic grid (no x / y PML) through the C ABI; returns the p_max line along z,
+    optional final fields, dt and Nt."""
+    import os
+    from openlifu_b200 import _lib
+    from tests.test_oracle_physics import planar_interface_inputs
+    k = planar_interface_inputs(nxy=nxy, nz=nz, d=d, z_src=z_src, z_int=nz, t_end=t_end, cycles=cycles, f0=f0,
+                                c=(1500.0, 1500.0), rho=(1000.0, 1000.0))
+    n_src = k["idx"].size
+    os.environ["LIFU_PIPELINE"] = pipeline
+    try:
+        with _lib.LifuSim(k["N"], (d,) * 3, k["dt"], k["Nt"], pml=(0, 0, 20)) as sim:
+            sim.set_medium(*medium, alpha_power=0.9, alpha_mode=alpha_mode)
+            sim.set_source_geometry(k["idx"], np.arange(n_src + 1), np.zeros(n_src), np.ones(n_src), 1)
+            sim.set_drive(k["sig"], [0], [1.0])
+            p_max, p_min, stats = sim.run()
+            extra = [sim.get_field(w) for w in fields]
+    finally:
+        os.environ.pop("LIFU_PIPELINE", None)
+    assert (stats["fft_launches"] == 0) == (pipeline == "v2")
+    return p_max.reshape(nz, nxy, nxy)[:, 3, 5].astype(np.float64), extra, k["dt"], k["Nt"], stats
+
+
+@pytest.mark.parametrize("pipeline,nxy,nz", [("v2", 64, 216), ("v1", 8, 364)])
+@pytest.mark.parametrize("as_maps,alpha_mode", [(False, "binary"), (True, "binary"), (False, "no_dispersion"), (True, "no_dispersion")])
+def test_plane_wave_power_law_absorption_known_answer(lifu_lib, pipeline, nxy, nz, as_maps, alpha_mode):
+    """Oracle-independent: a narrow-band plane wave in an absorbing medium (alpha = 3 dB / (MHz^0.9 cm)) decays with the
+    imaginary part of the wavenumber that solves the lossy dispersion relation: the nominal alpha f^y = 18.5 Np/m
+    without the dispersion term, 20.6 Np/m with it (tan(pi y / 2) = 6.3 at y = 0.9 makes that term an 11 % change of
+    c^2).  Scalar medium and per-voxel maps (both absorption code paths), both pipelines."""
+    d, z_src, f0, y, alpha_db = 0.5e-3, 20, 500e3, 0.9, 3.0
+    if as_maps:
+        shape = (nxy, nxy, nz)
+        medium = (np.full(shape, 1500.0), np.full(shape, 1000.0), np.full(shape, alpha_db))
+        medium[0][0, 0, 0] = 1500.0000001                       # keep the maps from being recognised as uniform
+    else:
+        medium = (1500.0, 1000.0, alpha_db)
+    t_end = (nz - z_src) * d / 1500.0 + 8 / f0
+    line, _, dt, nt, stats = _plane_wave_run(pipeline, nxy, nz, d, z_src, t_end, medium, cycles=8, alpha_mode=alpha_mode)
+    assert stats["absorbing"] == 1 and stats["homogeneous"] == (0 if as_maps else 1)
+    half_pulse = int(0.5 * 8 / f0 * 1500.0 / d)
+    z = np.arange(z_src + half_pulse + 4, nz - 30)
+    slope = np.polyfit(z * d, np.log(line[z]), 1)[0]
+    nominal = alpha_db * (f0 / 1e6) ** y * 100.0 / 8.685889638
+    expected = _lossy_wavenumber(f0, 1500.0, alpha_db, y, dispersion=alpha_mode == "binary").imag
+    assert abs(expected - (nominal if alpha_mode == "no_dispersion" else 1.1113 * nominal)) < 2e-3 * nominal
+    assert abs(-slope - expected) < 0.025 * expected, (slope, expected)     # peak-amplitude fit of an 8-cycle burst
+
+
+@pytest.mark.parametrize("pipeline,nxy,nz", [("v2", 64, 216), ("v1", 8, 364)])
+def test_plane_wave_phase_speed_known_answer(lifu_lib, pipeline, nxy, nz):
+    """Oracle-independent: the k-space scheme is exact in a homogeneous medium -- the pulse moves c0 * dt per step
+    (two snapshots of the final pressure field, sub-cell shift from the cross-correlation)."""
+    d, z_src = 0.5e-3, 20
+    snaps = []
+    for t_end in (30e-6, 42e-6):
+        _, (p,), dt, nt, _ = _plane_wave_run(pipeline, nxy, nz, d, z_src, t_end, (1500.0, 1000.0, 0.0), fields=(0,))
+        snaps.append((p[3, 5, :].astype(np.float64), nt))
+    (a, n1), (b, n2) = snaps
+    xc = np.correlate(b, a, mode="full")
+    k = int(np.argmax(xc))
+    y0, y1, y2 = xc[k - 1], xc[k], xc[k + 1]
+    shift = (k - (a.size - 1)) + 0.5 * (y0 - y2) / (y0 - 2 * y1 + y2)
+    c_meas = shift * d / ((n2 - n1) * dt)
+    assert abs(c_meas - 1500.0) / 1500.0 < 2e-3, c_meas

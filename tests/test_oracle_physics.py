@@ -142,3 +142,41 @@ def test_planar_interface_reflection_and_transmission():
     assert abs(np.sqrt(E_t / E_i) - T) < 0.01 * T
     assert abs(E_r / E_i + (E_t / E_i) * Z1 / Z2 - 1.0) < 0.01          # energy flux is conserved
     assert abs(np.abs(b).max() / np.abs(a[tt < 45e-6]).max() - T) < 0.01 * T
+
+
+def lossy_wavenumber(f, c, alpha_db, y, dispersion=True):
+    """Root of k-Wave's lossy dispersion relation w^2 = c^2 k^2 (1 + i w tau k^(y-2) - eta k^(y-1)) for a plane wave
+    e^{i(kz - wt)}; Im k is the attenuation the scheme should show, w / Re k the phase speed."""
+    w = 2 * np.pi * f
+    a0 = kg.db2neper(alpha_db, y)
+    tau = -2 * a0 * c ** (y - 1)
+    eta = 2 * a0 * c ** y * np.tan(np.pi * y / 2) if dispersion else 0.0
+
+    def F(k):
+        return w ** 2 - c ** 2 * k ** 2 * (1 + 1j * w * tau * k ** (y - 2) - eta * k ** (y - 1))
+
+    k = w / c + 0j
+    for _ in range(100):
+        h = 1e-7 * k
+        k = k - F(k) * h / (F(k + h) - F(k))
+    return k
+
+
+@pytest.mark.parametrize("dispersion", [True, False])
+def test_plane_wave_attenuation_follows_the_lossy_dispersion_relation(dispersion):
+    """Plane wave (no lateral PML -> exactly 1-D), alpha = 3 dB/(MHz^0.9 cm) at 500 kHz: the peak amplitude decays with
+    Im k of the dispersion relation -- 18.5 Np/m (= alpha f^y) without the dispersion term, 20.6 Np/m with it."""
+    d, z_src, f0, nz, nxy, cycles, y, alpha_db = 0.5e-3, 20, 500e3, 216, 4, 8, 0.9, 3.0
+    t_end = (nz - z_src) * d / 1500.0 + cycles / f0
+    k = planar_interface_inputs(nxy=nxy, nz=nz, d=d, z_src=z_src, z_int=nz, t_end=t_end, cycles=cycles, f0=f0,
+                                c=(1500.0, 1500.0), rho=(1000.0, 1000.0))
+    inp = SolverInputs(N=k["N"], d=(d,) * 3, dt=k["dt"], Nt=k["Nt"], c0=1500.0, rho0=1000.0, alpha_db=alpha_db,
+                       src_idx=k["idx"], src_p=np.repeat(k["sig"][None, :], k["idx"].size, axis=0))
+    out = simulate(inp, dtype=np.float64, asm=Assumptions(pml_size=(0, 0, 20), alpha_power=y, absorb_eta=dispersion))
+    line = out["p_max"].reshape(nz, nxy, nxy)[:, 1, 2]
+    z = np.arange(z_src + int(0.5 * cycles / f0 * 1500 / d) + 4, nz - 30)
+    slope = np.polyfit(z * d, np.log(line[z]), 1)[0]
+    kz = lossy_wavenumber(f0, 1500.0, alpha_db, y, dispersion)
+    assert abs(-slope - kz.imag) < 0.015 * kz.imag
+    nominal = alpha_db * (f0 / 1e6) ** y * 100.0 / 8.685889638
+    assert abs(kz.imag / nominal - (1.1113 if dispersion else 1.0)) < 2e-3
