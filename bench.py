@@ -341,8 +341,12 @@ def run_slab(args, rank, local_rank, world):
 
 
 def main():
-    # stdout carries exactly one JSON line: NCCL's own log lines (NCCL_DEBUG=VERSION/INFO on some boxes) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout carries exactly one JSON line: whatever native libraries print on file descriptor 1 (NCCL's version banner
+    # under NCCL_DEBUG=VERSION) is sent to stderr; Python's own stdout keeps the original descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
