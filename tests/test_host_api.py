@@ -130,3 +130,28 @@ def test_package_fields_matches_reference_expression_bitwise():
     assert ds["intensity"].data.dtype == np.float64 and np.array_equal(ds["intensity"].data, want)
     assert ds["p_min"].attrs == {"units": "Pa", "long_name": "PNP"} and ds["intensity"].attrs["units"] == "W/cm^2"
     ds["p_min"].data *= 2.0          # Solution.scale works in place: the arrays must be writable
+
+
+def test_analysis_engine_selection(monkeypatch):
+    """Solution.analyze(engine=...): explicit value > $LIFU_ANALYZE > auto (device only for the solver's float32 stack)."""
+    from openlifu_b200.plan.solution import _pick_engine
+    from openlifu_b200 import xa
+    f32 = xa.Dataset({"p_min": xa.DataArray(np.zeros((1, 2, 2, 2), np.float32), dims=("focal_point_index", "x", "y", "z"))})
+    f64 = xa.Dataset({"p_min": xa.DataArray(np.zeros((1, 2, 2, 2)), dims=("focal_point_index", "x", "y", "z"))})
+    monkeypatch.delenv("LIFU_ANALYZE", raising=False)
+    assert _pick_engine("host", f32) == "host" and _pick_engine("cuda", f64) == "cuda"
+    assert _pick_engine(None, f64) == "host"                     # not the solver's dtype -> numpy evaluation
+    monkeypatch.setenv("LIFU_ANALYZE", "host")
+    assert _pick_engine(None, f32) == "host"
+    monkeypatch.setenv("LIFU_ANALYZE", "gpu")
+    with pytest.raises(ValueError, match="Unknown analysis engine"):
+        _pick_engine(None, f32)
+
+
+def test_output_dict_derives_raw_p_min_on_demand():
+    from openlifu_b200.sim.kwave_if import _Output
+    out = _Output({"pnp": np.array([1.0, -2.0], np.float32)})
+    assert "p_min" not in out
+    assert np.array_equal(out["p_min"], np.array([-1.0, 2.0], np.float32)) and "p_min" in out
+    with pytest.raises(KeyError):
+        out["nope"]
