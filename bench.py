@@ -20,8 +20,8 @@ Printed JSON (rank 0, one line):
   cpu_baseline  the oracle port (CPU restatement of the k-Wave step) on this box's host cores.
 
 --impl reference times the reference's CPU path.  The real k-Wave OMP binary cannot exist here
-(SURVEY.md 8c), so this is the oracle port (`oracle/`, numpy + scipy.fft with all host threads) on
-a bounded number of time steps of the same workload.
+(SURVEY.md 8c), so this is the oracle port (`oracle/`: the checker's time loop run on torch CPU tensors, i.e. MKL FFTs
+and element-wise operations on all host threads) on a bounded number of time steps of the same workload.
 """
 from __future__ import annotations
 
@@ -41,6 +41,9 @@ for p in (str(ROOT / "openlifu-python_b200"), str(ROOT)):
 
 import numpy as np  # noqa: E402
 
+# CPU arm: the oracle's time loop on torch CPU tensors (MKL FFTs AND element-wise operations on all host threads, the
+# closest stand-in for kspaceFirstOrder-OMP); "numpy" = scipy.fft threads + single-threaded element-wise operations
+ORACLE_BACKEND = os.environ.get("LIFU_ORACLE_BACKEND", "torch")
 METRIC = "k-space sim voxel-updates/s"
 UNIT = "Mvox*step/s"
 
@@ -161,7 +164,8 @@ def oracle_sample(cfg, prep, n_time_steps, workers):
     W[np.searchsorted(idx, ijk[:, 0] + N[0] * (ijk[:, 1] + N[1] * ijk[:, 2])), np.arange(len(pos))] = 1.0
     delays, apod = beams[0]
     out = osc.run_simulation(sc, delays=delays, apod=apod, freq=cfg["pulse"].frequency, cycles=cycles,
-                             amplitude=cfg["pulse"].amplitude, geometry=(idx, W), max_steps=n_time_steps, workers=workers)
+                             amplitude=cfg["pulse"].amplitude, geometry=(idx, W), max_steps=n_time_steps, workers=workers,
+                             backend=ORACLE_BACKEND)
     return out["raw"]["loop_s"], int(np.prod(out["raw"]["N_exp"])), out["raw"]["Nt"]
 
 
@@ -188,7 +192,7 @@ def run_reference(args, rank):
     value = V / per / 1e6
     from openlifu_b200.sim.kwave_if import get_kgrid
     nt_full = get_kgrid(prep[0].coords)["Nt"]
-    sample = f"{n_ts} of the workload's time steps per bench step, time loop only, {V} voxels"
+    sample = f"{n_ts} of the workload's time steps per bench step, time loop only, {V} voxels, {ORACLE_BACKEND} backend"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3 * nt_full, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -528,7 +532,7 @@ def main():
         loop_s, Vc, done = oracle_sample(cfg, prep, n_ts, cores)
         per = max(loop_s, 1e-6) / done
         cpu = {"value": Vc / per / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_ts} time steps of the same workload ({Vc} voxels), scipy.fft + numpy, {cores} threads"}
+               "sample": f"{n_ts} time steps of the same workload ({Vc} voxels), oracle time loop on the {ORACLE_BACKEND} backend, {cores} threads"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

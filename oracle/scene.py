@@ -55,7 +55,7 @@ def source_geometry(scene: Scene, bli_tolerance=0.05, upsampling_rate=5):
 def run_simulation(scene: Scene, delays=None, apod=None, freq=1e6, cycles=20, amplitude=1.0, dt=0.0,
                    t_end=0.0, cfl=0.5, bli_tolerance=0.05, upsampling_rate=5, ref_values_only=False,
                    dtype=np.float32, asm: Assumptions | None = None, geometry=None, max_steps=None,
-                   workers=-1):
+                   workers=-1, backend="numpy"):
     """Returns dict with p_max (PPP), p_min (PNP, sign flipped), intensity on the inner grid in
     (Nx,Ny,Nz) layout plus the raw Fortran-flat solver output and integer geometry."""
     n_el = len(scene.elem_pos_m)
@@ -72,7 +72,7 @@ def run_simulation(scene: Scene, delays=None, apod=None, freq=1e6, cycles=20, am
         c0, rho0, al = scene.sound_speed, scene.density, scene.attenuation
     inp = SolverInputs(N=tuple(N), d=tuple(d), dt=dt_, Nt=Nt, c0=c0, rho0=rho0, alpha_db=al,
                        src_idx=idx, src_p=src_p)
-    raw = simulate(inp, dtype=dtype, asm=asm, max_steps=max_steps, workers=workers)
+    raw = simulate(inp, dtype=dtype, asm=asm, max_steps=max_steps, workers=workers, backend=backend)
     sz = tuple(N)
     p_max = raw["p_max"].reshape(sz, order="F")
     p_min_raw = raw["p_min"].reshape(sz, order="F")

@@ -52,8 +52,12 @@ def _cast(a, dtype):
 
 
 def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None, workers: int = -1,
-             return_p_final: bool = False, max_steps: int | None = None, progress=None):
-    """Run the time loop; returns dict(p_max, p_min [Fortran-flat over inner grid], pml, N_exp, ...)."""
+             return_p_final: bool = False, max_steps: int | None = None, progress=None, backend: str = "numpy"):
+    """Run the time loop; returns dict(p_max, p_min [Fortran-flat over inner grid], pml, N_exp, ...).
+
+    ``backend="torch"`` runs the SAME step with torch CPU tensors (MKL FFTs and element-wise operations on all host
+    threads) -- the k-Wave-OMP-like timing arm of bench.py; ``"numpy"`` (scipy.fft with ``workers`` threads, single-
+    threaded element-wise operations) is the checker the parity tests use."""
     asm = asm or Assumptions()
     rdt = np.dtype(dtype)
     cdt = np.complex64 if rdt == np.float32 else np.complex128
@@ -108,6 +112,11 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
     L = src_p.shape[1]
 
     axes = (0, 1, 2)
+    Nt = int(inp.Nt) if max_steps is None else min(int(inp.Nt), int(max_steps))
+    if backend == "torch":
+        return _loop_torch(locals(), return_p_final, progress)
+    if backend != "numpy":
+        raise ValueError(f"unknown backend {backend!r}")
 
     def fwd(a):
         return sfft.rfftn(a, axes=axes, workers=workers)
@@ -122,7 +131,6 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
     p_max = np.full(N_in, -np.inf, dtype=rdt)
     p_min = np.full(N_in, np.inf, dtype=rdt)
 
-    Nt = int(inp.Nt) if max_steps is None else min(int(inp.Nt), int(max_steps))
     import time as _time
     t_loop0 = _time.perf_counter()
     for t in range(Nt):
@@ -174,4 +182,91 @@ def simulate(inp: SolverInputs, dtype=np.float32, asm: Assumptions | None = None
     if return_p_final:
         out["p_final"] = p
         out["u_final"] = u
+    return out
+
+
+def _loop_torch(v, return_p_final, progress):
+    """The time loop of :func:`simulate` on torch CPU tensors (same operators, same order of operations)."""
+    import time as _time
+
+    import torch
+    if v["workers"] and v["workers"] > 0:
+        torch.set_num_threads(int(v["workers"]))
+    N, N_in, pml, rdt, asm = v["N"], v["N_in"], v["pml"], v["rdt"], v["asm"]
+    tdt = torch.float32 if rdt == np.float32 else torch.float64
+
+    def T(a):
+        if a is None:
+            return None
+        if isinstance(a, (list, tuple)):
+            return [T(x) for x in a]
+        if isinstance(a, np.ndarray):
+            return torch.from_numpy(np.ascontiguousarray(a))
+        return a                                                    # numpy scalars broadcast as Python numbers
+    gp, gn, pml_c, pml_sg = T(v["gp"]), T(v["gn"]), T(v["pml_c"]), T(v["pml_sg"])
+    dt_rho0_sg = [T(x) if isinstance(x, np.ndarray) else float(x) for x in v["dt_rho0_sg"]]
+    dt_rho0 = T(v["dt_rho0"]) if np.ndim(v["dt_rho0"]) else float(v["dt_rho0"])
+    c2 = T(v["c2"]) if np.ndim(v["c2"]) else float(v["c2"])
+    rho0_r = T(v["rho0_r"]) if np.ndim(v["rho0_r"]) else float(v["rho0_r"])
+    src_kappa = T(v["src_kappa"])
+    absorbing = v["absorbing"]
+    if absorbing:
+        tau = v["tau"] if v["tau"] is None else (T(v["tau"]) if np.ndim(v["tau"]) else float(v["tau"]))
+        eta = v["eta"] if v["eta"] is None else (T(v["eta"]) if np.ndim(v["eta"]) else float(v["eta"]))
+        nabla1, nabla2 = T(v["nabla1"]), T(v["nabla2"])
+    si, sj, sk = (torch.from_numpy(np.asarray(a)) for a in (v["si"], v["sj"], v["sk"]))
+    src_p = torch.from_numpy(np.ascontiguousarray(v["src_p"]))
+    L, Nt = v["L"], v["Nt"]
+    dims = (0, 1, 2)
+
+    def fwd(a):
+        return torch.fft.rfftn(a, dim=dims)
+
+    def inv(A):
+        return torch.fft.irfftn(A, s=N, dim=dims)
+
+    p = torch.zeros(N, dtype=tdt)
+    u = [torch.zeros(N, dtype=tdt) for _ in range(3)]
+    rho = [torch.zeros(N, dtype=tdt) for _ in range(3)]
+    inner = tuple(slice(pml[a], pml[a] + N_in[a]) for a in range(3))
+    p_max = torch.full(N_in, -float("inf"), dtype=tdt)
+    p_min = torch.full(N_in, float("inf"), dtype=tdt)
+    t_loop0 = _time.perf_counter()
+    for t in range(Nt):
+        P = fwd(p)
+        for a in range(3):
+            g = inv(gp[a] * P)
+            u[a] = pml_sg[a] * (pml_sg[a] * u[a] - dt_rho0_sg[a] * g)
+        du = [inv(gn[a] * fwd(u[a])) for a in range(3)]
+        for a in range(3):
+            rho[a] = pml_c[a] * (pml_c[a] * rho[a] - dt_rho0 * du[a])
+        if t < L:
+            S = torch.zeros(N, dtype=tdt)
+            S[si, sj, sk] = src_p[:, t]
+            if asm.source_kspace_correction:
+                S = inv(src_kappa * fwd(S))
+            for a in range(3):
+                rho[a] = rho[a] + S
+        rsum = rho[0] + rho[1] + rho[2]
+        if absorbing:
+            acc = rsum
+            if tau is not None:
+                acc = acc + tau * inv(nabla1 * fwd(rho0_r * (du[0] + du[1] + du[2])))
+            if eta is not None:
+                acc = acc - eta * inv(nabla2 * fwd(rsum))
+            p = c2 * acc
+        else:
+            p = c2 * rsum
+        if t >= asm.record_start:
+            pi = p[inner]
+            torch.maximum(p_max, pi, out=p_max)
+            torch.minimum(p_min, pi, out=p_min)
+        if progress is not None:
+            progress(t, p.numpy())
+    loop_s = _time.perf_counter() - t_loop0
+    out = {"loop_s": loop_s, "p_max": p_max.numpy().flatten("F"), "p_min": p_min.numpy().flatten("F"), "pml": pml,
+           "N_exp": N, "c_ref": v["c_ref"], "Nt": Nt, "L": L, "homogeneous": v["homogeneous"], "absorbing": absorbing}
+    if return_p_final:
+        out["p_final"] = p.numpy()
+        out["u_final"] = [x.numpy() for x in u]
     return out

@@ -180,3 +180,19 @@ def test_plane_wave_attenuation_follows_the_lossy_dispersion_relation(dispersion
     assert abs(-slope - kz.imag) < 0.015 * kz.imag
     nominal = alpha_db * (f0 / 1e6) ** y * 100.0 / 8.685889638
     assert abs(kz.imag / nominal - (1.1113 if dispersion else 1.0)) < 2e-3
+
+
+@pytest.mark.parametrize("medium", ["water", "phantom"])
+def test_threaded_backend_is_the_same_time_loop(medium):
+    """bench.py times the oracle's step on torch CPU tensors (all host threads); it must be the checker's arithmetic."""
+    from tests import cases
+    from oracle import scene as osc
+    case = cases.v2_small_case(steps=40)
+    if medium == "phantom":
+        case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))
+        case["dt"], case["t_end"] = 1.5e-7, 40 * 1.5e-7
+    kw = dict(delays=case["delays"], apod=case["apod"], freq=case["freq"], cycles=case["cycles"], dt=case["dt"], t_end=case["t_end"])
+    a = osc.run_simulation(cases.scene_of(case), **kw)
+    b = osc.run_simulation(cases.scene_of(case), backend="torch", workers=4, **kw)
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(b[k], a[k]) < 5e-6, k
