@@ -328,9 +328,21 @@ def package_fields(params, p_max_flat, p_min_flat):
     try:
         import torch
         _host_threads(torch)
-        tp = torch.from_numpy(p_min_flat)
-        neg = torch.neg(tp).numpy()
-        inten = ((torch.square(tp) * np.float32(1e-4)).double() / torch.from_numpy(_two_z_flat(params))).numpy()
+        # chunked, with the results written straight into their final arrays: only the 12 bytes per voxel that are
+        # handed out touch fresh pages (the float32 / float64 intermediates live in a few recycled megabytes)
+        n = p_min_flat.size
+        neg = np.empty(n, dtype=np.float32)
+        inten = np.empty(n, dtype=np.float64)
+        tp, tneg, tint = torch.from_numpy(p_min_flat), torch.from_numpy(neg), torch.from_numpy(inten)
+        tz = torch.from_numpy(_two_z_flat(params))
+        scale = np.float32(1e-4)
+        for lo in range(0, n, 1 << 20):
+            hi = min(n, lo + (1 << 20))
+            x = tp[lo:hi]
+            torch.neg(x, out=tneg[lo:hi])
+            sq = torch.square(x)
+            sq.mul_(scale)
+            torch.div(sq.double(), tz[lo:hi], out=tint[lo:hi])
     except ImportError:
         neg = -1 * p_min_flat
         inten = (np.float32(1e-4) * p_min_flat ** 2) / _two_z_flat(params)
