@@ -430,3 +430,29 @@ def test_anisotropic_spacing(lifu_lib, pipeline):
     assert _is_v2(got) == (pipeline == "v2")
     assert np.array_equal(got["src_idx"], want["src_idx"])
     _check_fields(got, want)
+
+
+def test_edge_cases_clipped_elements_long_drive_silent_array(lifu_lib):
+    """(a) elements hanging over the edge of the grid: the source mask is the union of the BLI supports clipped to the
+    inner grid, bit-exact; (b) a drive signal longer than the run (L > Nt): only the first Nt samples are injected;
+    (c) a single time step; (d) zero apodization: the fields stay exactly zero."""
+    # (a) + (b): 3 x 3 array of 6 mm pitch on a 25 x 23 grid (outer elements overhang), 40 cycles >> 30 steps
+    case = cases.make_case([(-12, 12), (-11, 11), (-3, 27)], 1.0, 3, 3, 11.0, 0.5, (0, 0, 15), 400e3, 40,
+                           dt=3e-7, t_end=30 * 3e-7, name="overhang")
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert got["stats"]["steps"] == 30 and got["stats"]["source_steps"] == 30
+    assert np.array_equal(got["src_idx"], want["src_idx"])
+    n_full = cases.run_oracle_case(cases.make_case([(-30, 30), (-30, 30), (-3, 27)], 1.0, 3, 3, 11.0, 0.5, (0, 0, 15), 400e3, 2,
+                                                    dt=3e-7, t_end=3e-7))["src_idx"].size
+    assert want["src_idx"].size < n_full                                   # really clipped
+    _check_fields(got, want)
+    # (c) one time step
+    one = dict(case, t_end=3e-7)
+    w1, g1 = cases.run_oracle_case(one), cases.run_cuda_case(one)
+    assert g1["stats"]["steps"] == 1
+    _check_fields(g1, w1)
+    # (d) silent array
+    silent = dict(cases.small_water_case(), apod=np.zeros(4))
+    g0 = cases.run_cuda_case(silent)
+    assert not g0["p_max"].any() and not g0["p_min"].any()
