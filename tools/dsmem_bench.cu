@@ -18,7 +18,8 @@
 namespace cg = cooperative_groups;
 
 constexpr int NY = 256, NZ = 256;
-constexpr int U = 8;          // elements per thread per pass
+constexpr int U = 4;          // stores per thread per pass
+constexpr int W = 2;          // float2 elements per store (2 = 16-byte st.shared::cluster)
 constexpr int THREADS = 512;
 
 template <int C, bool REMOTE>
@@ -37,20 +38,23 @@ __global__ void __launch_bounds__(THREADS) k_transpose(float2* out, int iters, i
     // element (zl, y) of my rows goes to CTA q = y / ROWS, position [y % ROWS][rank * ROWS + zl]
     // thread mapping: consecutive threads take consecutive zl (destination-contiguous 8-byte stores)
     for (int r = 0; r < rep; ++r)                       // rep scatters per cluster barrier (rep = 0: barrier cost alone)
-      for (int e0 = threadIdx.x; e0 < ROWS * NY; e0 += blockDim.x * U) {
-        float2 v[U];
+      for (int e0 = threadIdx.x; e0 < ROWS * NY / W; e0 += blockDim.x * U) {
+        float2 v[U][W];
 #pragma unroll
-        for (int k = 0; k < U; ++k) {                       // U independent loads in flight per thread
-          const int e = e0 + k * blockDim.x;
-          v[k] = src[(e % ROWS) * SP + e / ROWS];
+        for (int k = 0; k < U; ++k) {                       // U x W independent loads in flight per thread
+          const int e = (e0 + k * blockDim.x) * W;          // W consecutive z rows of one y column
+#pragma unroll
+          for (int w = 0; w < W; ++w) v[k][w] = src[(e % ROWS + w) * SP + e / ROWS];
         }
 #pragma unroll
         for (int k = 0; k < U; ++k) {
-          const int e = e0 + k * blockDim.x;
+          const int e = (e0 + k * blockDim.x) * W;
           const int zl = e % ROWS, y = e / ROWS;
           const int q = y / ROWS, yl = y % ROWS;
-          float2* pq = REMOTE ? cluster.map_shared_rank(dst, q) : dst;      // one mapa per element
-          pq[yl * NZ + rank * ROWS + zl] = v[k];
+          float2* pq = REMOTE ? cluster.map_shared_rank(dst, q) : dst;      // one mapa per store
+          float2* d = pq + yl * NZ + rank * ROWS + zl;
+          if (W == 2) *reinterpret_cast<float4*>(d) = make_float4(v[k][0].x, v[k][0].y, v[k][W - 1].x, v[k][W - 1].y);
+          else d[0] = v[k][0];
         }
       }
     cluster.sync();
