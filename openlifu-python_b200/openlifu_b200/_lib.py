@@ -311,12 +311,38 @@ class LifuSim:
         float32 arrays of Nx*Ny*Nz; or raw device pointers (ints)."""
         nvox = int(np.prod(self.n)) if self.layout is None else self.n[0] * self.n[1] * self.layout["sensor_nz"]
         own = p_max is None
+        st = lifu_stats()
+        if own and nvox >= (1 << 20):
+            # large results: DMA into page-locked staging buffers kept on the handle, then a threaded copy into the fresh
+            # arrays that are handed out (a pageable device->host copy would fault the fresh pages in one driver thread)
+            stage = self._pinned_stage(nvox)
+            if stage is not None:
+                import torch
+                _check(self._lib.lifu_run(self._h, C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()), C.byref(st)))
+                p_max = np.empty(nvox, dtype=np.float32)
+                p_min = np.empty(nvox, dtype=np.float32)
+                torch.from_numpy(p_max).copy_(stage[0])
+                torch.from_numpy(p_min).copy_(stage[1])
+                return p_max, p_min, st.as_dict()
         if own:
             p_max = np.empty(nvox, dtype=np.float32)
             p_min = np.empty(nvox, dtype=np.float32)
-        st = lifu_stats()
         _check(self._lib.lifu_run(self._h, _ptr(p_max), _ptr(p_min), C.byref(st)))
         return p_max, p_min, st.as_dict()
+
+    def _pinned_stage(self, nvox):
+        """Two page-locked float32 buffers of nvox elements (torch is the allocator); None when torch / CUDA pinning is
+        not available."""
+        cur = getattr(self, "_stage", None)
+        if cur is not None and cur[0].numel() == nvox:
+            return cur
+        try:
+            import torch
+            self._stage = (torch.empty(nvox, dtype=torch.float32, pin_memory=True),
+                           torch.empty(nvox, dtype=torch.float32, pin_memory=True))
+        except Exception:  # noqa: BLE001
+            self._stage = None
+        return self._stage
 
     def set_two_z(self, two_z):
         """2 * density * sound_speed for the intensity: a float, or a float64 array with one value per inner-grid
