@@ -177,8 +177,6 @@ int upload_source_points(lifu_sim* s) {
   // (re)compute expanded-grid indices and the additive-source scale once both the geometry and
   // the medium are known
   if (!s->geometry_set || !s->medium_set) return LIFU_OK;
-  if (s->d_lin_exp) { cudaFree(s->d_lin_exp); s->d_lin_exp = nullptr; }
-  if (s->d_scale) { cudaFree(s->d_scale); s->d_scale = nullptr; }
   long long i0 = 0, i1 = s->n_src;
   if (s->sl.on && s->n_src > 0) {
     // the points are sorted x fastest / z slowest: this rank's planes are one contiguous range
@@ -191,8 +189,16 @@ int upload_source_points(lifu_sim* s) {
   }
   s->sl.src_i0 = i0; s->sl.src_i1 = i1;
   const long long cnt = i1 - i0;
-  LIFU_CUDA(cudaMalloc(&s->d_lin_exp, sizeof(long long) * std::max<long long>(cnt, 1)));
-  LIFU_CUDA(cudaMalloc(&s->d_scale, sizeof(float) * std::max<long long>(cnt, 1)));
+  // the buffers are kept across calls (this runs on every medium change: cudaFree / cudaMalloc synchronise the device
+  // and were seen to stall for hundreds of milliseconds now and then)
+  if (cnt > s->src_pts_cap || !s->d_lin_exp) {
+    if (s->d_lin_exp) { cudaFree(s->d_lin_exp); s->d_lin_exp = nullptr; }
+    if (s->d_scale) { cudaFree(s->d_scale); s->d_scale = nullptr; }
+    s->src_pts_cap = 0;
+    LIFU_CUDA(cudaMalloc(&s->d_lin_exp, sizeof(long long) * std::max<long long>(cnt, 1)));
+    LIFU_CUDA(cudaMalloc(&s->d_scale, sizeof(float) * std::max<long long>(cnt, 1)));
+    s->src_pts_cap = std::max<long long>(cnt, 1);
+  }
   if (cnt > 0) {
     k_source_points<<<grid_blocks(s, cnt, 128), 128, 0, s->stream>>>(
         s->d_idx + i0, cnt, s->P, s->homogeneous ? nullptr : s->d_c0e, s->c0_s, s->grid.dt, s->grid.d[0],

@@ -60,6 +60,7 @@ struct lifu_sim {
   float *d_c0e = nullptr, *d_rho0e = nullptr, *d_alphae = nullptr;
   float c0_s = 0, rho0_s = 0, alpha_s = 0;
   float* d_med = nullptr;      // packed derived maps
+  long long src_pts_cap = 0;   // capacity (points) of d_lin_exp / d_scale
   double* d_two_z = nullptr;   // 2 * density * sound_speed on the inner grid (float64, x fastest) for the intensity
   double two_z_s = 0.0;        // ... or one value
   int two_z_mode = 0;          // 0 not set, 1 scalar, 2 map

@@ -20,7 +20,7 @@ def main():
     ge.build()
     from openlifu_b200 import _lib, configs
     from openlifu_b200.sim import kwave_if
-    cfg = configs.c2(216)
+    cfg = configs.c3(216) if "C3" in sys.argv else configs.c2(216)
     params, foci, beams, cycles = configs.prepare(cfg)
     arr = cfg["arr"]
     T = {}
@@ -42,10 +42,14 @@ def main():
     kwave_if.package_arrays = timed("package_arrays", kwave_if.package_arrays)
     kwave_if._sample_checksum = timed("checksums", kwave_if._sample_checksum)
     _lib.LifuSim.set_medium = timed("sim.set_medium", _lib.LifuSim.set_medium)
+    _lib.LifuSim._pinned_maps = timed("(pinned map copies)", _lib.LifuSim._pinned_maps)
     _lib.LifuSim.set_drive = timed("sim.set_drive", _lib.LifuSim.set_drive)
     _lib.LifuSim.set_elements = timed("sim.set_elements", _lib.LifuSim.set_elements)
     type(arr).drive_plan = timed("drive_plan", type(arr).drive_plan)
-    for it in range(4):
+    if "nogc" in sys.argv:
+        import gc
+        gc.disable()
+    for it in range(7):
         T.clear()
         delays, apod = beams[it % len(beams)]
         ses = next(iter(kwave_if._SESSIONS.values()), None)
