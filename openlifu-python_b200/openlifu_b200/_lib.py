@@ -253,10 +253,11 @@ class LifuSim:
                 same = all(m is None or m.strides == ref.strides for m in maps)
                 if dense and same:
                     st = (C.c_int64 * 3)(*[v // 8 for v in ref.strides])
-                    ptrs = self._pinned_maps(maps)      # threaded copy into page-locked memory, then DMA
-                    if ptrs is None:
-                        ptrs = [_ptr(m) for m in maps]
-                    _check(self._lib.lifu_set_medium_f64(self._h, ptrs[0], ptrs[1], ptrs[2], st, alpha_power, mode))
+                    # host -> device from memory that is already resident is fine as a pageable copy (23 ms against 12 ms
+                    # through page-locked staging for three 216^3 maps); the device -> host side into fresh arrays is
+                    # what needs staging (run())
+                    _check(self._lib.lifu_set_medium_f64(self._h, _ptr(maps[0]), _ptr(maps[1]), _ptr(maps[2]), st,
+                                                         alpha_power, mode))
                     return
         shape = self.n
         if plane0 is not None:
@@ -331,30 +332,6 @@ class LifuSim:
             p_min = np.empty(nvox, dtype=np.float32)
         _check(self._lib.lifu_run(self._h, _ptr(p_max), _ptr(p_min), C.byref(st)))
         return p_max, p_min, st.as_dict()
-
-    def _pinned_maps(self, maps):
-        """The float64 medium maps copied (all host threads) into page-locked buffers kept on the handle, as raw
-        pointers in the same memory layout; None when torch / pinning is unavailable or the maps are small."""
-        n = int(np.prod(self.n))
-        if n < (1 << 20):
-            return None
-        try:
-            import torch
-            bufs = getattr(self, "_map_stage", None)
-            if bufs is None or bufs[0].numel() != n:
-                bufs = self._map_stage = [torch.empty(n, dtype=torch.float64, pin_memory=True) for _ in range(3)]
-            out = []
-            for b, m in zip(bufs, maps):
-                if m is None:
-                    out.append(None)
-                    continue
-                flat = m.reshape(-1, order="C" if m.flags.c_contiguous else "F")     # a view: the array is dense
-                b.copy_(torch.from_numpy(flat))
-                out.append(C.c_void_p(b.data_ptr()))
-            return out
-        except Exception:  # noqa: BLE001
-            self._map_stage = None
-            return None
 
     def _pinned_stage(self, nvox):
         """Two page-locked float32 buffers of nvox elements (torch is the allocator); None when torch / CUDA pinning is

@@ -42,7 +42,6 @@ def main():
     kwave_if.package_arrays = timed("package_arrays", kwave_if.package_arrays)
     kwave_if._sample_checksum = timed("checksums", kwave_if._sample_checksum)
     _lib.LifuSim.set_medium = timed("sim.set_medium", _lib.LifuSim.set_medium)
-    _lib.LifuSim._pinned_maps = timed("(pinned map copies)", _lib.LifuSim._pinned_maps)
     _lib.LifuSim.set_drive = timed("sim.set_drive", _lib.LifuSim.set_drive)
     _lib.LifuSim.set_elements = timed("sim.set_elements", _lib.LifuSim.set_elements)
     type(arr).drive_plan = timed("drive_plan", type(arr).drive_plan)
