@@ -210,11 +210,13 @@ class LifuSim:
             _check(self._lib.lifu_slab_layout_of(self._h, C.byref(lay)))
             self.layout = {k: getattr(lay, k) for k, _ in lay._fields_}
         self._keep = []
+        self._stage = None             # page-locked result staging buffers (run()), allocated on first use
 
     def close(self):
         if self._h:
             self._lib.lifu_destroy(self._h)
             self._h = C.c_void_p()
+        self._stage = None
 
     def __del__(self):
         try:
@@ -336,7 +338,7 @@ class LifuSim:
     def _pinned_stage(self, nvox):
         """Two page-locked float32 buffers of nvox elements (torch is the allocator); None when torch / CUDA pinning is
         not available."""
-        cur = getattr(self, "_stage", None)
+        cur = self._stage
         if cur is not None and cur[0].numel() == nvox:
             return cur
         try:
