@@ -155,3 +155,31 @@ def test_output_dict_derives_raw_p_min_on_demand():
     assert np.array_equal(out["p_min"], np.array([-1.0, 2.0], np.float32)) and "p_min" in out
     with pytest.raises(KeyError):
         out["nope"]
+
+
+def test_stack_of_fortran_ordered_foci_keeps_layout_and_roundtrips(tmp_path):
+    """xa.concat of per-focus Datasets whose arrays are x-fastest (what run_simulation returns): the stack keeps each
+    focus' memory order (block copies, and the layout the device analysis stages directly), equals np.stack, reduces
+    and serialises like any other array."""
+    from openlifu_b200 import xa
+    n = (7, 6, 5)
+    coords = {d: xa.DataArray(np.linspace(0, 1, k), dims=[d], attrs={"units": "mm"}) for d, k in zip("xyz", n)}
+    rng = np.random.default_rng(0)
+    fields = [rng.random(n).astype(np.float32) for _ in range(3)]
+    pieces = []
+    for i, f in enumerate(fields):
+        ds = xa.Dataset({"p_min": xa.DataArray(np.asfortranarray(f), coords=coords, dims=("x", "y", "z"), attrs={"units": "Pa"}),
+                         "intensity": xa.DataArray(np.asfortranarray(f.astype(np.float64)), coords=coords, dims=("x", "y", "z"),
+                                                   attrs={"units": "W/cm^2"})})
+        pieces.append(ds.assign_coords(focal_point_index=i))
+    st = xa.concat(pieces, dim="focal_point_index")
+    data = np.asarray(st["p_min"].data)
+    assert data.shape == (3,) + n and np.array_equal(data, np.stack(fields))
+    if not hasattr(xa, "__version__"):                       # the shim (real xarray makes its own C-ordered copy)
+        assert all(data[i].flags.f_contiguous for i in range(3))
+    assert np.array_equal(np.asarray(st["p_min"].max(dim="focal_point_index").data), np.max(np.stack(fields), axis=0))
+    f = tmp_path / "stack.nc"
+    st.to_netcdf(f, engine="scipy")
+    back = xa.open_dataset(f, engine="scipy")
+    for k in ("p_min", "intensity"):
+        assert np.array_equal(np.asarray(back[k].data), np.asarray(st[k].data)), k
