@@ -159,7 +159,8 @@ class Solution:
         "cuda" when a GPU is visible and the fields have the solver's dtypes, else "host"."""
         engine = _pick_engine(engine, self.simulation_result)
         if engine == "cuda":
-            return self._analyze_cuda(options, param_constraints)
+            # called through the class so that `analyze` can be grafted onto the reference's own Solution by name
+            return Solution._analyze_cuda(self, options, param_constraints)
         out = SolutionAnalysis()
         units = options.distance_units
         dt = 1 / (self.pulse.frequency * 20)
