@@ -256,3 +256,44 @@ def test_protocol_dict_roundtrip_and_fixture_materials():
     back = Protocol.from_json(pr.to_json(compact=False))
     assert back.to_dict() == pr.to_dict()
     assert isinstance(pr.to_table().shape[0], int)
+
+
+@pytest.mark.skipif(not Path("/root/reference/src/openlifu").exists(), reason="needs the reference sources (build container only)")
+def test_analyze_grafts_onto_the_reference_solution_class():
+    """`openlifu.plan.solution.Solution.analyze = openlifu_b200.plan.Solution.analyze` -- our method
+    bound to the REAL reference Solution (reference Transducer / Pulse / Sequence / Point underneath) reproduces the
+    reference's own analysis of the same object."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path[:0] = ["%(root)s/tests/golden", "%(root)s/openlifu-python_b200", "%(root)s"]
+import numpy as np
+import make_reference_plan_goldens as m
+m.install_reference()
+from openlifu.bf import Pulse, Sequence
+from openlifu.bf.focal_patterns import Wheel
+from openlifu.geo import Point
+from openlifu.plan.solution import Solution as RefSolution
+from openlifu.plan.solution_analysis import SolutionAnalysisOptions
+from openlifu.xdc import Transducer
+from openlifu_b200 import xa
+from openlifu_b200.plan import Solution as OurSolution
+mod = {"xa": xa, "Transducer": Transducer, "Point": Point, "Solution": RefSolution, "Pulse": Pulse, "Sequence": Sequence,
+       "SolutionAnalysisOptions": SolutionAnalysisOptions, "Wheel": Wheel}
+sol, opts, _ = m.synthetic_case(mod)
+want = m.analysis_to_plain(sol.analyze(options=opts))
+RefSolution.analyze = OurSolution.analyze
+got = m.analysis_to_plain(sol.analyze(options=opts, engine="host"))
+print(json.dumps({"want": want, "got": got}))
+''' % {"root": str(Path(__file__).resolve().parents[1])}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    for k, w in res["want"].items():
+        g = res["got"][k]
+        if w is None:
+            assert g is None, k
+        else:
+            np.testing.assert_allclose(np.asarray(g, dtype=float), np.asarray(w, dtype=float), rtol=1e-9, atol=1e-12,
+                                       equal_nan=True, err_msg=k)
