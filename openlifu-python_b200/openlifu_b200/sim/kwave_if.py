@@ -171,6 +171,30 @@ def element_geometry(arr, translation_m):
     return pos, size, ang
 
 
+def drive_plan(arr, dt, delays, apod):
+    """Integer delay samples, per-element gains and the base-signal gain that ``Transducer.calc_output`` encodes
+    (xdc/transducer.py:95-112, xdc/element.py:144-154).  Uses ``arr.drive_plan`` when the transducer has it (this
+    package's mirror); a reference ``openlifu.xdc.Transducer`` is read through its public attributes."""
+    if hasattr(arr, "drive_plan"):
+        return arr.drive_plan(dt, delays, apod)
+    if getattr(arr, "impulse_response", None) is not None:
+        raise NotImplementedError("array impulse responses are not supported on the simulation path")
+    n_delay = np.array([int(d / dt) for d in delays], dtype=np.int32)
+    gains = []
+    for a, el in zip(apod, arr.elements):
+        g = float(a)
+        ir = getattr(el, "impulse_response", None)
+        if ir is not None:
+            if len(ir) != 1:
+                raise NotImplementedError("array impulse responses are not supported on the simulation path")
+            g *= float(ir[0])
+        if getattr(el, "sensitivity", None) is not None:
+            g *= float(el.sensitivity)
+        gains.append(g)
+    sens = getattr(arr, "sensitivity", None)
+    return n_delay, np.array(gains, dtype=np.float64), (1.0 if sens is None else float(sens))
+
+
 def run_simulation(arr,
                    params,
                    delays: np.ndarray | None = None,
@@ -194,7 +218,7 @@ def run_simulation(arr,
     kg = get_kgrid(params.coords, dt=dt, t_end=t_end, cfl=cfl)
     t = np.arange(0, cycles / freq, kg["dt"])
     input_signal = amplitude * np.sin(2 * np.pi * freq * t)
-    n_delay, gains, base_gain = arr.drive_plan(kg["dt"], delays, apod)
+    n_delay, gains, base_gain = drive_plan(arr, kg["dt"], delays, apod)
     scl = getunitconversion(_same_units([params[d] for d in params.dims], "dimensions"), "m")
     array_offset: List[float] = [-float(c.mean()) * scl for c in params.coords.values()]
 

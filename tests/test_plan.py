@@ -297,3 +297,44 @@ print(json.dumps({"want": want, "got": got}))
         else:
             np.testing.assert_allclose(np.asarray(g, dtype=float), np.asarray(w, dtype=float), rtol=1e-9, atol=1e-12,
                                        equal_nan=True, err_msg=k)
+
+
+@pytest.mark.skipif(not Path("/root/reference/src/openlifu").exists(), reason="needs the reference sources (build container only)")
+def test_run_simulation_inputs_from_reference_objects():
+    """run_simulation reads a REAL reference Transducer through its public surface -- the drive plan
+    (delay samples, gains) rebuilds the reference's calc_output matrix exactly and the element geometry matches."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path[:0] = ["%(root)s/tests/golden", "%(root)s/openlifu-python_b200", "%(root)s"]
+import numpy as np
+import make_reference_plan_goldens as m
+m.install_reference()
+from openlifu.xdc import Transducer
+from openlifu_b200.sim.kwave_if import drive_plan, element_geometry
+from openlifu_b200.xdc import Transducer as Ours
+arr = Transducer.gen_matrix_array(nx=4, ny=3, pitch=4, kerf=0.5, units="mm", sensitivity=1e5)
+assert not hasattr(arr, "drive_plan")
+for i in (2, 5, 11):     # scalar impulse response + element sensitivity; (an element sensitivity WITHOUT an impulse response
+    arr.elements[i].impulse_response = np.array([0.5 + 0.1 * i]); arr.elements[i].impulse_dt = 1.0   # compounds in the
+    arr.elements[i].sensitivity = 1.0 + 0.1 * i                                                        # reference: SURVEY App. B 4)
+rng = np.random.default_rng(1)
+delays = rng.random(12) * 4e-6
+apod = rng.random(12)
+dt = 1.7e-7
+sig = np.sin(2 * np.pi * 400e3 * np.arange(0, 5 / 400e3, dt))
+want = arr.calc_output(sig.copy(), dt, delays=delays, apod=apod)
+n_delay, gains, base = drive_plan(arr, dt, delays, apod)
+got = np.zeros_like(want)
+for e in range(12):
+    got[e, n_delay[e]:n_delay[e] + sig.size] = gains[e] * (sig * base)
+ours = Ours.gen_matrix_array(nx=4, ny=3, pitch=4, kerf=0.5, units="mm", sensitivity=1e5)
+g_ref = element_geometry(arr, [1e-3, 2e-3, 3e-3]); g_our = element_geometry(ours, [1e-3, 2e-3, 3e-3])
+print(json.dumps({"max_abs": float(np.abs(got - want).max()), "scale": float(np.abs(want).max()),
+                  "geom": float(max(np.abs(a - b).max() for a, b in zip(g_ref, g_our)))}))
+''' % {"root": str(Path(__file__).resolve().parents[1])}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    assert res["max_abs"] <= 1e-12 * res["scale"] and res["geom"] == 0.0, res
