@@ -331,10 +331,25 @@ for e in range(12):
     got[e, n_delay[e]:n_delay[e] + sig.size] = gains[e] * (sig * base)
 ours = Ours.gen_matrix_array(nx=4, ny=3, pitch=4, kerf=0.5, units="mm", sensitivity=1e5)
 g_ref = element_geometry(arr, [1e-3, 2e-3, 3e-3]); g_our = element_geometry(ours, [1e-3, 2e-3, 3e-3])
+# the whole adapter with reference objects (reference SimSetup / UniformWater / Transducer): everything up to the
+# creation of the solver handle must work on them; without a GPU that creation is what fails, loudly
+from openlifu.sim.sim_setup import SimSetup
+from openlifu.seg.seg_methods.uniform import UniformWater
+from openlifu_b200.sim.kwave_if import run_simulation
+from openlifu_b200 import _lib
+import torch
+reached = None
+if not torch.cuda.is_available():
+    params = SimSetup(spacing=1.0, x_extent=(-10, 10), y_extent=(-10, 10), z_extent=(-2, 30)).setup_sim_scene(UniformWater())
+    try:
+        run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=400e3, cycles=3)
+    except _lib.LifuError as e:
+        reached = "lifu_create" in str(e)
 print(json.dumps({"max_abs": float(np.abs(got - want).max()), "scale": float(np.abs(want).max()),
-                  "geom": float(max(np.abs(a - b).max() for a, b in zip(g_ref, g_our)))}))
+                  "geom": float(max(np.abs(a - b).max() for a, b in zip(g_ref, g_our))), "reached": reached}))
 ''' % {"root": str(Path(__file__).resolve().parents[1])}
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["max_abs"] <= 1e-12 * res["scale"] and res["geom"] == 0.0, res
+    assert res["reached"] in (True, None), res
