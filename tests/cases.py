@@ -56,10 +56,12 @@ def scene_of(case):
                      attenuation=case["alpha"], sensitivity=case["sensitivity"])
 
 
-def run_oracle_case(case, dtype=np.float32, asm=None, max_steps=None):
+def run_oracle_case(case, dtype=np.float32, asm=None, max_steps=None, backend="numpy"):
+    """backend "torch": the same time loop on torch CPU tensors (all host threads; equal to the numpy loop to 6e-7,
+    tests/test_oracle_physics.py) -- used by the config-scale comparisons, where the numpy loop would take twice as long."""
     out = osc.run_simulation(scene_of(case), delays=case["delays"], apod=case["apod"], freq=case["freq"],
                              cycles=case["cycles"], amplitude=case["amplitude"], dt=case["dt"], t_end=case["t_end"],
-                             dtype=dtype, asm=asm, max_steps=max_steps)
+                             dtype=dtype, asm=asm, max_steps=max_steps, backend=backend)
     return {"p_max": out["raw"]["p_max"], "p_min": out["raw"]["p_min"], "src_idx": out["src_idx"], "W": out["W"],
             "n_delay": out["n_delay"], "Nt": out["Nt"], "dt": out["dt"], "pml": out["raw"]["pml"],
             "N_exp": out["raw"]["N_exp"]}

@@ -247,20 +247,7 @@ def test_v2_heterogeneous_absorbing(lifu_lib, alpha_mode):
         assert cases.rel_l2(got[k], v1[k]) < 2e-5
 
 
-def _c2_case(steps=None, c0=1500.0, rho0=1000.0, alpha=0.0, amplitude=1.0):
-    from openlifu_b200 import configs
-    arr = configs.openlifu_2x_array()
-    half = 53.75
-    pos = np.array([el.position for el in arr.elements])
-    size = np.array([el.size for el in arr.elements])
-    ang = np.array([el.get_angle(units="deg") for el in arr.elements])
-    kw = {}
-    if steps is not None:
-        dt = 0.5 * 0.5e-3 / 1500
-        kw = dict(dt=dt, t_end=steps * dt)
-    return cases.make_case([(-half, half), (-half, half), (-4, 103.5)], 0.5, 0, 0, 0, 0, (0, 0, 50), 400e3, 20,
-                           elem_pos_mm=pos, elem_size_mm=size, angles_deg=ang, sensitivity=None, c0=c0, rho0=rho0,
-                           alpha=alpha, amplitude=amplitude, **kw)
+from tests.config_cases import c2_case as _c2_case, c3_maps  # noqa: E402
 
 
 def test_c2_full_size_properties(lifu_lib):
@@ -289,13 +276,7 @@ def test_c2_full_size_properties(lifu_lib):
 
 def test_c3_full_size_linearity_and_pipelines(lifu_lib):
     """C3 (skull / brain phantom, absorbing) at full size: linearity bit-exact, fused pipeline == cuFFT pipeline."""
-    from openlifu_b200 import configs
-    cfg = configs.c3(216)
-    lab = np.asarray(cfg["volume"].data)
-    mats = list(configs.PHANTOM_MATERIALS.values())
-    c0 = np.array([m.sound_speed for m in mats])[lab]
-    rho0 = np.array([m.density for m in mats])[lab]
-    al = np.array([m.attenuation for m in mats])[lab]
+    c0, rho0, al = c3_maps()
     a = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al))
     assert _is_v2(a) and a["stats"]["absorbing"] == 1 and a["stats"]["homogeneous"] == 0
     b = cases.run_cuda_case(_c2_case(steps=300, c0=c0, rho0=rho0, alpha=al, amplitude=0.5))
