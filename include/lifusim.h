@@ -92,6 +92,11 @@ int lifu_make_time(const int32_t n[3], const double d[3], double c_ref, double c
 /* get_optimal_pml_size for pml_auto=True (kwave_if.py:118): range [10,40]. */
 int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]);
 
+/* Number of CUDA devices this library can run on (sm_100 only); 0 when there is none or the driver is missing.
+ * Replaces the NVML probe of util/checkgpu.py:6-14 where pynvml is not installed: Protocol.calc_solution(use_gpu=None)
+ * (plan/protocol.py:294-295) asks the library that will do the work.  Never fails. */
+int lifu_device_count(int32_t* count);
+
 /* ---- lifecycle --------------------------------------------------------------------- */
 int lifu_create(const lifu_grid* grid, int device, void* cuda_stream, lifu_sim** out);
 int lifu_destroy(lifu_sim* sim);

@@ -286,6 +286,18 @@ int lifu_make_time(const int32_t n[3], const double d[3], double c_ref, double c
   return LIFU_OK;
 }
 
+int lifu_device_count(int32_t* count) {
+  if (!count) { set_error("lifu_device_count: null argument"); return LIFU_ERR_INVALID; }
+  *count = 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return LIFU_OK; }
+  for (int d = 0; d < ndev; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++*count;
+  }
+  return LIFU_OK;
+}
+
 int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]) {
   if (!n || !pml_out) { set_error("lifu_pml_auto: null argument"); return LIFU_ERR_INVALID; }
   for (int a = 0; a < 3; ++a)

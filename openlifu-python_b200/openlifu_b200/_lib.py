@@ -101,6 +101,7 @@ def load():
         "lifu_last_error": (C.c_char_p, []),
         "lifu_make_time": (C.c_int, [C.POINTER(i32), C.POINTER(f64), f64, f64, C.POINTER(i32), C.POINTER(f64)]),
         "lifu_pml_auto": (C.c_int, [C.POINTER(i32), C.POINTER(i32)]),
+        "lifu_device_count": (C.c_int, [C.POINTER(i32)]),
         "lifu_create": (C.c_int, [C.POINTER(lifu_grid), C.c_int, vp, C.POINTER(vp)]),
         "lifu_destroy": (C.c_int, [vp]),
         "lifu_set_medium": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int]),
@@ -136,7 +137,7 @@ def load():
     return lib
 
 
-EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_create", "lifu_destroy",
+EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_device_count", "lifu_create", "lifu_destroy",
             "lifu_set_medium", "lifu_set_medium_f64", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_set_two_z", "lifu_get_packaged", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
@@ -172,6 +173,13 @@ def pml_auto(n):
     out = (C.c_int32 * 3)()
     _check(load().lifu_pml_auto((C.c_int32 * 3)(*[int(v) for v in n]), out))
     return tuple(out)
+
+
+def device_count() -> int:
+    """B200-class devices the library can run on; 0 without a driver / device (never raises once the library is built)."""
+    n = C.c_int32()
+    _check(load().lifu_device_count(C.byref(n)))
+    return int(n.value)
 
 
 def slab_unique_id() -> bytes:

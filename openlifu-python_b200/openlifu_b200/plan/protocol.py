@@ -87,7 +87,7 @@ def _gather_foci(mine: Dict[int, Any], n_foci: int, world: int, coords) -> list:
     dist.broadcast_object_list(meta, src=0)
     slots = (n_foci + world - 1) // world
     on_gpu = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    dev = torch.device("cuda", kwave_if._device()) if on_gpu else torch.device("cpu")   # the solver's GPU (LOCAL_RANK)
     gathered = {}
     for name, dtype, shape, _, _, _ in meta[0]:
         local = np.zeros((slots,) + shape, dtype=np.dtype(dtype))
@@ -282,6 +282,12 @@ class Protocol:
         the beam analysis (reference semantics, protocol.py:242-398)."""
         if use_gpu is None:
             use_gpu = gpu_available()
+            if not use_gpu and simulate:
+                # the reference falls back to the k-Wave OMP binary here (protocol.py:294-295); this package has no
+                # CPU solver, so say what is missing instead of failing later inside run_simulation
+                raise RuntimeError("Protocol.calc_solution: no B200-class CUDA device was found (NVML and liblifusim "
+                                   "probes) and openlifu_b200 has no CPU simulation path; pass simulate=False to "
+                                   "beamform only")
         sim_options = self.sim_setup if sim_options is None else sim_options
         analysis_options = self.analysis_options if analysis_options is None else analysis_options
         self.check_target(target)

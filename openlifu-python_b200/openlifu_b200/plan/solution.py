@@ -14,9 +14,10 @@ from __future__ import annotations
 
 import base64
 import json
+import logging
 import os
 import tempfile
-from dataclasses import asdict, dataclass, field
+from dataclasses import asdict, dataclass, field, replace
 from datetime import datetime
 from pathlib import Path
 from typing import Dict, List, Tuple
@@ -75,16 +76,27 @@ def _masked_max(values: np.ndarray, mask: np.ndarray) -> float:
 
 
 def _pick_engine(engine, simulation_result) -> str:
+    """``engine`` / ``$LIFU_ANALYZE`` when given; otherwise the device engine when a GPU and the built library are there
+    and the fields have the layout the kernels take, else the host (numpy) evaluation -- announced at WARNING level, it
+    is the reference's own algorithm but 30x slower on a 216^3 grid."""
     engine = engine or os.environ.get("LIFU_ANALYZE") or None
     if engine is None:
         from ..util.checkgpu import gpu_available
-        ok = False
+        why = None
         try:
-            ok = (np.asarray(simulation_result["p_min"].data).dtype == np.float32
-                  and simulation_result["p_min"].ndim == 4 and gpu_available())
-        except Exception:  # noqa: BLE001
-            ok = False
-        engine = "cuda" if ok else "host"
+            if np.asarray(simulation_result["p_min"].data).dtype != np.float32 or simulation_result["p_min"].ndim != 4:
+                why = "the fields are not a float32 (focus, x, y, z) stack"
+            elif not gpu_available():
+                why = "no CUDA device is visible"
+            else:
+                from .. import _lib
+                _lib.load()
+        except Exception as e:  # noqa: BLE001
+            why = f"the device engine is unavailable ({e})"
+        engine = "cuda" if why is None else "host"
+        if why is not None:
+            logging.getLogger(__name__).warning("Solution.analyze: using the host (numpy) engine because %s; pass "
+                                                "engine='host' to select it explicitly", why)
     if engine not in ("cuda", "host"):
         raise ValueError(f"Unknown analysis engine '{engine}' (expected 'cuda' or 'host')")
     return engine
@@ -435,12 +447,11 @@ class Solution:
         return d
 
     def _plain_dict(self) -> dict:
-        d = {f: getattr(self, f) for f in self.__dataclass_fields__ if f != "simulation_result"}
-        d["transducer"] = None if self.transducer is None else self.transducer.to_dict()
-        d["pulse"] = self.pulse.to_dict()
-        d["sequence"] = self.sequence.to_dict()
-        d["foci"] = [p.to_dict() for p in self.foci]
-        d["target"] = None if self.target is None else self.target.to_dict()
+        """The dictionary the reference serialises (``dataclasses.asdict(self)``, plan/solution.py:416): nested
+        dataclasses field by field, ``None`` members included, so that files written here and by the reference have
+        the same layout (tests/golden/ref_solution.json is a reference-written file)."""
+        d = asdict(replace(self, simulation_result=None))
+        d.pop("simulation_result")
         return d
 
     def to_json(self, include_simulation_data: bool, compact: bool) -> str:

@@ -76,10 +76,25 @@ def _device():
     return 0
 
 
-def _sample_checksum(a: np.ndarray) -> int:
-    flat = np.asarray(a).reshape(-1)
-    step = max(1, flat.size // 4096)
-    return zlib.adler32(np.ascontiguousarray(flat[::step]).tobytes()) ^ flat.size
+def _content_key(a: np.ndarray):
+    """Identity of an array's CONTENT for the medium cache: every byte takes part (an in-place edit of a single voxel
+    between two calls changes the key; the reference rebuilds the medium on every call, kwave_if.py:113).  Dense
+    arrays are summed as 64-bit words with wrap-around on all host threads (~5 ms for a float64 216^3 map) next to an
+    Adler-32 of a strided sample, which is sensitive to position; anything else is hashed byte by byte."""
+    a = np.asarray(a)
+    flat = None
+    if a.flags.c_contiguous or a.flags.f_contiguous:
+        flat = a.reshape(-1, order="A")
+    if flat is not None and flat.nbytes % 8 == 0 and flat.nbytes > 0:
+        words = flat.view(np.int64)
+        try:
+            import torch
+            total = int(torch.from_numpy(words).sum().item())
+        except Exception:  # noqa: BLE001 - torch missing or a read-only buffer it refuses
+            total = int(words.sum(dtype=np.int64))
+        step = max(1, flat.size // 4096)
+        return (a.shape, a.dtype.str, total, zlib.adler32(np.ascontiguousarray(flat[::step]).tobytes()))
+    return (a.shape, a.dtype.str, zlib.adler32(np.ascontiguousarray(a).tobytes()))
 
 
 def multi_gpu_mode():
@@ -138,7 +153,7 @@ def _gather_planes(local, layout, n, world):
     import torch.distributed as dist
     plane = n[0] * n[1]
     on_gpu = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    dev = torch.device("cuda", _device()) if on_gpu else torch.device("cpu")    # the solver's GPU, not torch's current one
     meta = torch.tensor([layout["sensor_z0"], layout["sensor_nz"]], dtype=torch.int64, device=dev)
     metas = [torch.empty_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta)
@@ -236,7 +251,7 @@ def run_simulation(arr,
             sim.set_medium(*[float(params[k].attrs["ref_value"]) for k in names], alpha_power=0.9, alpha_mode=alpha_mode)
     else:
         maps = [params[k].data for k in names]
-        mkey = ("map",) + tuple((id(m), _sample_checksum(m)) for m in maps) + (alpha_mode,)
+        mkey = ("map",) + tuple(_content_key(m) for m in maps) + (alpha_mode,)
         if ses.medium_key != mkey:
             if mkey not in ses.uniform:
                 ses.uniform = {mkey: all(float(m.min()) == float(m.max()) for m in maps)}
@@ -274,7 +289,7 @@ def run_simulation(arr,
         return package_fields(params, output["p_max"], output["p_min"]), output
     # the impedance of the packaging step always comes from the params maps (kwave_if.py:140), whatever medium was used
     rho, c = params["density"].data, params["sound_speed"].data
-    zkey = (id(rho), id(c), _sample_checksum(rho), _sample_checksum(c))
+    zkey = (_content_key(rho), _content_key(c))
     if medium_changed or ses.two_z_key != zkey:
         if zkey not in ses.z_uniform:
             ses.z_uniform = {zkey: float(rho.min()) == float(rho.max()) and float(c.min()) == float(c.max())}
@@ -317,9 +332,9 @@ _Z2_CACHE: dict = {}
 
 
 def _two_z_flat(params):
-    """2 * density * sound_speed (float64) flattened x fastest, cached per params maps (identity + sampled checksum)."""
+    """2 * density * sound_speed (float64) flattened x fastest, cached per CONTENT of the params maps."""
     rho, c = params["density"].data, params["sound_speed"].data
-    key = (id(rho), id(c), _sample_checksum(rho), _sample_checksum(c))
+    key = (_content_key(rho), _content_key(c))
     hit = _Z2_CACHE.get(key)
     if hit is None:
         if len(_Z2_CACHE) >= 4:

@@ -8,6 +8,7 @@ API mirror of /root/reference/src/openlifu/xdc/transducer.py (``Transducer:19``,
 from __future__ import annotations
 
 import copy
+import logging
 import json
 from dataclasses import dataclass, field
 from typing import Any, Dict, List
@@ -29,6 +30,19 @@ def _axis_rotation(dim: str, angle_rad: float) -> np.ndarray:
     m[i, j] = -s
     m[j, i] = s
     return m
+
+
+_WARNED_ELEMENT_SENSITIVITY = False
+
+
+def _warn_element_sensitivity():
+    global _WARNED_ELEMENT_SENSITIVITY
+    if not _WARNED_ELEMENT_SENSITIVITY:
+        _WARNED_ELEMENT_SENSITIVITY = True
+        logging.getLogger(__name__).warning(
+            "Transducer has per-element sensitivities: openlifu_b200 applies each element's own sensitivity, whereas the "
+            "reference's in-place multiplication compounds them element after element (xdc/element.py:145-153); source "
+            "amplitudes differ from the reference for such arrays")
 
 
 @dataclass
@@ -72,6 +86,11 @@ class Transducer:
         n_delay = np.array([int(dl / dt) for dl in delays], dtype=np.int32)
         gains = np.array([a * el.scalar_gain() for a, el in zip(apod, self.elements)], dtype=np.float64)
         base_gain = 1.0 if self.sensitivity is None else float(self.sensitivity)
+        if any(el.sensitivity is not None for el in self.elements):
+            # documented deviation (INTEGRATION.md "Per-element sensitivity"): the reference multiplies the SHARED
+            # input array in place (element.py:145-153), so element k is scaled by the product of the sensitivities of
+            # elements 0..k; here every element gets its own sensitivity only
+            _warn_element_sensitivity()
         return n_delay, gains, base_gain
 
     def calc_output(self, input_signal, dt, delays: np.ndarray = None, apod: np.ndarray = None):

@@ -79,6 +79,20 @@ def main():
     mod = {"xa": xa, "Transducer": Transducer, "Point": Point, "Solution": Solution, "Pulse": Pulse, "Sequence": Sequence,
            "SolutionAnalysisOptions": SolutionAnalysisOptions, "Wheel": Wheel}
     sol, opts, pattern = synthetic_case(mod)
+    # the on-disk JSON of a Solution as the reference writes it (plan/solution.py:406-437): ref_solution.json
+    from datetime import datetime
+    import importlib.util
+    import types
+    import openlifu.plan.solution as rsol
+    stub = types.ModuleType("openlifu.db.subject")           # the encoder module imports the database layer for one name
+    stub.Subject = type("Subject", (), {})
+    sys.modules["openlifu.db.subject"] = stub
+    spec = importlib.util.spec_from_file_location("openlifu_util_json_real", "/root/reference/src/openlifu/util/json.py")
+    real_json = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(real_json)
+    rsol.PYFUSEncoder = real_json.PYFUSEncoder               # the reference's own encoder (install_reference stubs it)
+    sol.date_created = datetime(2024, 1, 2, 3, 4, 5)
+    (HERE / "ref_solution.json").write_text(sol.to_json(include_simulation_data=False, compact=False))
     out = {"analysis": analysis_to_plain(sol.analyze(options=opts))}
     ita = sol.get_ita()
     out["ita_sum"] = float(np.asarray(ita.data).sum())

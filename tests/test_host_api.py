@@ -183,3 +183,74 @@ def test_stack_of_fortran_ordered_foci_keeps_layout_and_roundtrips(tmp_path):
     back = xa.open_dataset(f, engine="scipy")
     for k in ("p_min", "intensity"):
         assert np.array_equal(np.asarray(back[k].data), np.asarray(st[k].data)), k
+
+
+def test_medium_cache_key_sees_a_single_voxel_edit():
+    """the medium cache key must change when ONE voxel of a params map is edited in place between two
+    run_simulation calls (the reference rebuilds the medium on every call, kwave_if.py:113)."""
+    from openlifu_b200.sim.kwave_if import _content_key
+    rng = np.random.default_rng(3)
+    a = 1500.0 + rng.random((48, 40, 36))
+    k0 = _content_key(a)
+    assert _content_key(a) == k0 and _content_key(a.copy()) == k0           # content, not identity
+    for idx in [(0, 0, 1), (17, 23, 5), (47, 39, 35)]:                       # none of them on a coarse sampling lattice
+        b = a.copy()
+        b[idx] += 1e-9
+        assert _content_key(b) != k0, idx
+    f = np.asfortranarray(a)
+    assert _content_key(f) != None and _content_key(np.asfortranarray(a)) == _content_key(f)  # noqa: E711
+    g = f.copy(order="F")
+    g[3, 4, 5] = 0.0
+    assert _content_key(g) != _content_key(f)
+    s = a[::2]                                                              # non-contiguous view: hashed byte by byte
+    t = s.copy()
+    t[1, 1, 1] += 1.0
+    assert _content_key(s) != _content_key(t)
+    assert _content_key(a.astype(np.float32)) != _content_key(a)
+
+
+def test_per_element_sensitivity_is_applied_per_element_and_announced(caplog):
+    """intended (non-compounding) behaviour for arrays whose elements carry their own sensitivity, i.e. after
+    Transducer.merge of modules with different sensitivities -- each element's signal is scaled by ITS sensitivity; the
+    reference compounds them through an in-place multiplication of the shared input (element.py:145-153).  The
+    deviation is logged once at WARNING level."""
+    import logging
+    from openlifu_b200.xdc import Transducer
+    from openlifu_b200.xdc import transducer as tmod
+    arr = Transducer.gen_matrix_array(nx=2, ny=2, pitch=4, kerf=0.5, units="mm", sensitivity=2.0)
+    for k, el in enumerate(arr.elements):
+        el.sensitivity = 1.0 + k
+    tmod._WARNED_ELEMENT_SENSITIVITY = False
+    sig = np.sin(np.linspace(0, 6, 20))
+    with caplog.at_level(logging.WARNING):
+        out = arr.calc_output(sig, 1e-7, delays=np.zeros(4), apod=np.ones(4))
+    for k in range(4):
+        assert np.allclose(out[k, :20], (1.0 + k) * 2.0 * sig, rtol=1e-14)
+    assert any("per-element sensitivities" in r.message for r in caplog.records)
+
+
+def test_gpu_probe_falls_back_to_the_library(monkeypatch):
+    """without pynvml the probe asks liblifusim (lifu_device_count) instead of reporting "no GPU"."""
+    from openlifu_b200.util import checkgpu
+    checkgpu._count.cache_clear()
+    monkeypatch.setattr(checkgpu, "_nvml_device_count", lambda: (_ for _ in ()).throw(ImportError("no pynvml")))
+    monkeypatch.setattr(checkgpu, "_library_device_count", lambda: 3)
+    assert checkgpu.gpu_available() is True
+    checkgpu._count.cache_clear()
+    monkeypatch.setattr(checkgpu, "_library_device_count", lambda: 0)
+    assert checkgpu.gpu_available() is False
+    checkgpu._count.cache_clear()
+
+
+def test_calc_solution_default_gpu_choice_names_the_missing_cpu_path(monkeypatch):
+    """use_gpu=None on a box without a B200: an explicit error instead of the reference's CPU fallback."""
+    from openlifu_b200 import configs
+    from openlifu_b200.plan import Protocol
+    from openlifu_b200.plan import protocol as pmod
+    monkeypatch.setattr(pmod, "gpu_available", lambda: False)
+    cfg = configs.c1()
+    proto = Protocol(pulse=cfg["pulse"], sim_setup=cfg["setup"])
+    with pytest.raises(RuntimeError, match="no CPU simulation path"):
+        proto.calc_solution(cfg["target"], cfg["arr"])
+    sol, agg, ana = proto.calc_solution(cfg["target"], cfg["arr"], simulate=False, scale=False)
+    assert agg is None and ana is None and sol.delays.shape == (1, 64)

@@ -353,3 +353,38 @@ print(json.dumps({"max_abs": float(np.abs(got - want).max()), "scale": float(np.
     res = json.loads(r.stdout.strip().splitlines()[-1])
     assert res["max_abs"] <= 1e-12 * res["scale"] and res["geom"] == 0.0, res
     assert res["reached"] in (True, None), res
+
+
+def test_solution_json_layout_equals_reference_written_file():
+    """tests/golden/ref_solution.json was written by the REFERENCE's Solution.to_json (asdict + its own encoder,
+    plan/solution.py:406-437; generator: tests/golden/make_reference_plan_goldens.py).  The same solution built from
+    this package's classes must serialise to the same dictionary (None members included), and the reference-written
+    file must load here."""
+    import json
+    import sys
+    from datetime import datetime
+    from pathlib import Path
+    golden = Path(__file__).resolve().parent / "golden"
+    sys.path.insert(0, str(golden))
+    try:
+        from make_reference_plan_goldens import synthetic_case
+    finally:
+        sys.path.pop(0)
+    from openlifu_b200 import xa
+    from openlifu_b200.bf import Pulse, Sequence
+    from openlifu_b200.bf.focal_patterns import Wheel
+    from openlifu_b200.geo import Point
+    from openlifu_b200.plan.solution import Solution
+    from openlifu_b200.plan.solution_analysis import SolutionAnalysisOptions
+    from openlifu_b200.xdc import Transducer
+    mod = {"xa": xa, "Transducer": Transducer, "Point": Point, "Solution": Solution, "Pulse": Pulse, "Sequence": Sequence,
+           "SolutionAnalysisOptions": SolutionAnalysisOptions, "Wheel": Wheel}
+    sol, _, _ = synthetic_case(mod)
+    sol.date_created = datetime(2024, 1, 2, 3, 4, 5)
+    ref_text = (golden / "ref_solution.json").read_text()
+    ref = json.loads(ref_text)
+    assert json.loads(sol.to_json(include_simulation_data=False, compact=False)) == ref
+    assert json.loads(sol.to_json(include_simulation_data=False, compact=True)) == ref
+    back = Solution.from_json(ref_text)
+    assert back.id == "g" and back.transducer.numelements() == 16 and back.delays.shape == (2, 16)
+    assert json.loads(back.to_json(include_simulation_data=False, compact=False)) == ref
