@@ -123,6 +123,35 @@ struct V2Params {
   float2* HSslab;                   // [nzs][Ny][PH]
   int store_p;                      // write the real-space pressure (last step / debugging)
   int bx0;                          // added to blockIdx.x by the strided passes (nxt: a 1-wide grid does the Nyquist column only)
+  int xrev;                         // persistent x kernels walk their row pairs from the last one down (L2 reuse across passes)
+  int zmajor;                       // batched y passes: grid (tiles, ncomp, Nz) instead of (tiles, Nz, ncomp)
+  int pm_always;                    // write the sensor pair back even when it did not change (measurement switch)
+};
+
+// Pipeline v3 (fft_gen.cuh): generic-radix fused passes.
+struct GenPlan {
+  int N, ns;
+  int radix[8];
+  const float2* tw;          // exp(-2 pi i m / N), m < N
+};
+
+struct GParams {
+  int Nx, Ny, Nz, Nxh, PH, My;
+  long long HS, ZS;           // strides between batched H / Z fields
+  GenPlan px, py, pz;
+  float2* ZP;                 // x-spectrum of the pressure (row pairs)
+  float2* Z4;                 // [4][ZS]
+  float2* H4;                 // [4][HS]
+  float2* pm;                 // [Nz][Ny][Nx] running (p_max, p_min) on the expanded grid
+  float norm;                 // 1 / (2 Nx Ny Nz)
+  int z0s, nzs;               // source slab planes
+  float* Sslab;               // [nzs][Ny][Nx]
+  float2* ZSslab;             // [nzs][My][Nx]
+  float2* HSslab;             // [nzs][Ny][PH]
+  int store_p;
+  int Ls, lsh_s;              // lanes per tile of the strided passes (power of two) and its log2
+  int Lx, lsh_x;              // row pairs per batch of the x passes
+  int pm_always;
 };
 
 

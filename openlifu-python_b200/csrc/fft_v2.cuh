@@ -162,13 +162,22 @@ struct Strided {
 
 // lane -> (kx, other index) of a strided-pass CTA; false when the CTA has no work.
 // grid.x = nxt regular tiles + 1 Nyquist slot; grid.y runs over the other index (regular) or its 16-blocks.
-__device__ __forceinline__ bool lane_map(const V2Params& Q, int n_other, int l, int& kx, int& o) {
+__device__ __forceinline__ bool lane_map(const V2Params& Q, int n_other, int l, int& kx, int& o, int by) {
   const int bx = (int)blockIdx.x + Q.bx0;
-  if (bx < Q.nxt) { kx = bx * 16 + l; o = blockIdx.y; return true; }
-  if ((int)blockIdx.y * 16 >= n_other) return false;
+  if (bx < Q.nxt) { kx = bx * 16 + l; o = by; return true; }
+  if (by * 16 >= n_other) return false;
   kx = Q.Nx >> 1;
-  o = blockIdx.y * 16 + l;
+  o = by * 16 + l;
   return true;
+}
+__device__ __forceinline__ bool lane_map(const V2Params& Q, int n_other, int l, int& kx, int& o) {
+  return lane_map(Q, n_other, l, kx, o, (int)blockIdx.y);
+}
+// Batched y passes: grid (tiles, Nz, ncomp), or with Q.zmajor (tiles, ncomp, Nz) so that the components of one plane are
+// scheduled together -- the order in which the neighbouring x passes produce / consume them.
+__device__ __forceinline__ void comp_plane(const V2Params& Q, int& comp, int& by) {
+  comp = Q.zmajor ? (int)blockIdx.y : (int)blockIdx.z;
+  by = Q.zmajor ? (int)blockIdx.z : (int)blockIdx.y;
 }
 
 // Merge the two rows of a pair (adjacent registers A = row y_lo, B = row y_lo + R) into the packed
@@ -197,10 +206,11 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
   extern __shared__ __align__(16) unsigned char smraw[];
   using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int comp = blockIdx.z;
+  int comp, by;
+  comp_plane(Q, comp, by);
   const int nz = MODE == 2 ? Q.nzs : Q.Nz;
   int kx, z;
-  if (!lane_map(Q, nz, l, kx, z)) return;
+  if (!lane_map(Q, nz, l, kx, z, by)) return;
   const bool live = z < nz;                       // only a slab's Nyquist tile can run past the end
   const int zc = live ? z : nz - 1;
   float2* xa = reinterpret_cast<float2*>(smraw);
@@ -416,9 +426,10 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_inv(StepParams P
   extern __shared__ __align__(16) unsigned char smraw[];
   using S = Strided<R>;
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int comp = blockIdx.z;
+  int comp, by;
+  comp_plane(Q, comp, by);
   int kx, z;
-  if (!lane_map(Q, Q.Nz, l, kx, z)) return;
+  if (!lane_map(Q, Q.Nz, l, kx, z, by)) return;
   float2* xa = reinterpret_cast<float2*>(smraw);
   const float2* hp = Q.H4 + comp * Q.HS + ((long long)z * Q.Ny + t) * Q.PH + kx;
   const int kstep = R * Q.PH;
@@ -471,6 +482,14 @@ __device__ __forceinline__ void line_fft_sw(float2 (&v)[R], const float4* __rest
   dft<R, INV>(v);
 }
 
+// Running maximum / minimum of one sensor voxel.  The pair is written back only when it changed: away from the passing
+// burst neither extreme moves, so most of the 8 bytes per sensor voxel and step of write traffic never reaches DRAM
+// (the stored values are the same either way).
+__device__ __forceinline__ void sensor_update(float2* dst, float2 old, float p, int always) {
+  const float2 nv = make_float2(fmaxf(old.x, p), fminf(old.y, p));
+  if (always || nv.x != old.x || nv.y != old.y) *dst = nv;
+}
+
 // One group's staging: a stage is SB*N bytes = [ N float2 spectrum line | row lo (N floats) | row hi (N floats) ]
 // or [ sensor row lo (N float2) | sensor row hi (N float2) ]; heterogeneous media append the two rows of the medium
 // map the item needs (SB = 24) so that they arrive with the fields instead of being loaded after the transform.
@@ -498,6 +517,13 @@ struct XStage {
 template <int R, bool HOMOG> using XStageU = XStage<R, HOMOG ? 16 : 24, 0>;
 template <int R, bool HOMOG> using XStageRho = XStage<R, 16, HOMOG ? 0 : 16>;
 
+// Traversal order of the persistent x kernels.  With Q.xrev the batches are walked from the LAST row pair down: the
+// kernel then starts on the part of its input that the preceding y pass wrote last (still in the 126 MB L2) and ends on
+// the low-z planes, which the following y pass reads first.
+__device__ __forceinline__ int phys_pair(const V2Params& Q, int pair) {
+  return Q.xrev ? Q.Nz * (Q.Ny >> 1) - 1 - pair : pair;
+}
+
 // row pair index (z*Ny/2 + m) -> z and the lower row y_lo of the pair (Ny/2 and Ry are powers of two)
 __device__ __forceinline__ void pair_rows(const V2Params& Q, int pair, int& z, int& ylo) {
   const int m = pair & ((Q.Ny >> 1) - 1);
@@ -524,8 +550,9 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_u(StepParams P, V2Par
   const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int pstep = gridDim.x * G;
 
-  auto issue = [&](int pair, int c, int stage, bool valid) {
+  auto issue = [&](int lpair, int c, int stage, bool valid) {
     if (valid) {
+      const int pair = phys_pair(Q, lpair);
       int z, ylo;
       pair_rows(Q, pair, z, ylo);
       const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -540,10 +567,11 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_u(StepParams P, V2Par
     }
     cp_async_commit();
   };
-  int pair = blockIdx.x * G + g;
-  issue(pair, 0, 0, iters > 0);
-  issue(pair, 1, 1, iters > 0);
-  for (int it = 0; it < iters; ++it, pair += pstep) {
+  int lpair = blockIdx.x * G + g;
+  issue(lpair, 0, 0, iters > 0);
+  issue(lpair, 1, 1, iters > 0);
+  for (int it = 0; it < iters; ++it, lpair += pstep) {
+    const int pair = phys_pair(Q, lpair);
     int z, ylo;
     pair_rows(Q, pair, z, ylo);
     const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -582,8 +610,8 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_u(StepParams P, V2Par
 #pragma unroll
       for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = v[k1];
       __syncwarp();
-      if (c == 0) issue(pair, 2, stage, true);
-      else issue(pair + pstep, c - 1, stage, it + 1 < iters);
+      if (c == 0) issue(lpair, 2, stage, true);
+      else issue(lpair + pstep, c - 1, stage, it + 1 < iters);
     }
   }
   cp_async_wait<0>();
@@ -612,8 +640,9 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
   const int pstep = gridDim.x * G;
 
   // c: -1 source item, 0..2 rho_x, rho_y, rho_z, 3 sensor rows; slot: parity of the pair's iteration
-  auto issue = [&](int pair, int c, int stage, bool valid, int slot) {
+  auto issue = [&](int lpair, int c, int stage, bool valid, int slot) {
     if (valid) {
+      const int pair = phys_pair(Q, lpair);
       int z, ylo;
       pair_rows(Q, pair, z, ylo);
       const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -640,12 +669,13 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
     }
     cp_async_commit();
   };
-  int pair = blockIdx.x * G + g;
-  issue(pair, 0 - C0, 0, iters > 0, 0);
-  issue(pair, 1 - C0, 1, iters > 0, 0);
+  int lpair = blockIdx.x * G + g;
+  issue(lpair, 0 - C0, 0, iters > 0, 0);
+  issue(lpair, 1 - C0, 1, iters > 0, 0);
   float2 src[R], sum[R];
   float2 dsum[ABS ? R : 1];
-  for (int it = 0; it < iters; ++it, pair += pstep) {
+  for (int it = 0; it < iters; ++it, lpair += pstep) {
+    const int pair = phys_pair(Q, lpair);
     int z, ylo;
     pair_rows(Q, pair, z, ylo);
     const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -740,16 +770,14 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int x = t + R * j;
-            const float2 o = zb[x];
-            pmg[x] = make_float2(fmaxf(o.x, sum[j].x), fminf(o.y, sum[j].x));
+            sensor_update(pmg + x, zb[x], sum[j].x, Q.pm_always);
           }
         }
         if (in1) {
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int x = t + R * j;
-            const float2 o = zb[N + x];
-            pmg[hi + x] = make_float2(fmaxf(o.x, sum[j].y), fminf(o.y, sum[j].y));
+            sensor_update(pmg + hi + x, zb[N + x], sum[j].y, Q.pm_always);
           }
         }
         __syncwarp();
@@ -759,8 +787,8 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
         for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = sum[k1];
       }
       __syncwarp();
-      if (ci + 2 < NI) issue(pair, ci + 2 - C0, stage, true, it & 1);
-      else issue(pair + pstep, ci + 2 - NI - C0, stage, it + 1 < iters, (it + 1) & 1);
+      if (ci + 2 < NI) issue(lpair, ci + 2 - C0, stage, true, it & 1);
+      else issue(lpair + pstep, ci + 2 - NI - C0, stage, it + 1 < iters, (it + 1) & 1);
     }
   }
   cp_async_wait<0>();
@@ -783,8 +811,9 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_p(StepParams P, V2Par
   const int nbatch = Q.Nz * (Q.Ny / 2) / G;
   const int iters = (int)blockIdx.x < nbatch ? (nbatch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int pstep = gridDim.x * G;
-  auto issue = [&](int pair, int c, int stage, bool valid) {
+  auto issue = [&](int lpair, int c, int stage, bool valid) {
     if (valid) {
+      const int pair = phys_pair(Q, lpair);
       int z, ylo;
       pair_rows(Q, pair, z, ylo);
       const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -814,11 +843,12 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_p(StepParams P, V2Par
     }
     cp_async_commit();
   };
-  int pair = blockIdx.x * G + g;
-  issue(pair, 0, 0, iters > 0);
-  issue(pair, 1, 1, iters > 0);
+  int lpair = blockIdx.x * G + g;
+  issue(lpair, 0, 0, iters > 0);
+  issue(lpair, 1, 1, iters > 0);
   float2 acc[R];
-  for (int it = 0; it < iters; ++it, pair += pstep) {
+  for (int it = 0; it < iters; ++it, lpair += pstep) {
+    const int pair = phys_pair(Q, lpair);
     int z, ylo;
     pair_rows(Q, pair, z, ylo);
     const long long r0 = ((long long)z * Q.Ny + ylo) * N;
@@ -862,16 +892,14 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_p(StepParams P, V2Par
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int x = t + R * j;
-            const float2 o = zb[x];
-            pmg[x] = make_float2(fmaxf(o.x, acc[j].x), fminf(o.y, acc[j].x));
+            sensor_update(pmg + x, zb[x], acc[j].x, Q.pm_always);
           }
         }
         if (in1) {
 #pragma unroll
           for (int j = 0; j < R; ++j) {
             const int x = t + R * j;
-            const float2 o = zb[N + x];
-            pmg[hi + x] = make_float2(fmaxf(o.x, acc[j].y), fminf(o.y, acc[j].y));
+            sensor_update(pmg + hi + x, zb[N + x], acc[j].y, Q.pm_always);
           }
         }
         __syncwarp();
@@ -881,8 +909,8 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_p(StepParams P, V2Par
         for (int k1 = 0; k1 < R; ++k1) zo[t + R * k1] = acc[k1];
       }
       __syncwarp();
-      if (c + 2 < NI) issue(pair, c + 2, stage, true);
-      else issue(pair + pstep, c + 2 - NI, stage, it + 1 < iters);
+      if (c + 2 < NI) issue(lpair, c + 2, stage, true);
+      else issue(lpair + pstep, c + 2 - NI, stage, it + 1 < iters);
     }
   }
   cp_async_wait<0>();

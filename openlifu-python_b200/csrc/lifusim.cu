@@ -11,6 +11,7 @@
 #include "step_kernels.cuh"
 #include "fft_v2.cuh"
 #include "fft_z_tma.cuh"
+#include "fft_gen.cuh"
 #include "slab.cuh"
 
 namespace lifu {
@@ -344,7 +345,7 @@ static int create_impl(const lifu_grid* g, int device, void* cuda_stream, const 
   const char* ng = getenv("LIFU_NO_GRAPH");
   s->use_graph = !(ng && ng[0] == '1');
   const char* pl = getenv("LIFU_PIPELINE");
-  s->pipeline = (pl && !strcmp(pl, "v1")) ? 1 : ((pl && !strcmp(pl, "v2")) ? 2 : 0);
+  s->pipeline = (pl && !strcmp(pl, "v1")) ? 1 : ((pl && !strcmp(pl, "v2")) ? 2 : ((pl && !strcmp(pl, "v3")) ? 3 : 0));
   s->Nxh = s->N[0] / 2 + 1;
   s->V = (long long)s->N[0] * s->N[1] * s->N[2];
   s->Vin = (long long)s->n[0] * s->n[1] * s->n[2];
@@ -722,7 +723,7 @@ static void launch_rho_p(lifu_sim* s, int gb) {
 static int radix_of(int n) { return n == 64 ? 8 : (n == 256 ? 16 : 0); }
 
 static bool v2_eligible(const lifu_sim* s) {
-  if (s->pipeline == 1) return false;
+  if (s->pipeline == 1 || s->pipeline == 3) return false;
   for (int a = 0; a < 3; ++a) if (radix_of(s->N[a]) == 0) return false;
   return true;
 }
@@ -835,6 +836,16 @@ static int v2_setup(lifu_sim* s) {
   Q.z0s = z0; Q.nzs = nz;
   Q.store_p = 0;
   Q.bx0 = 0;
+  // traversal-order switches (LIFU_V2_ORDER bit 0: x kernels from the last row pair down -- on by default, bit 1:
+  // plane-major batched y passes -- off, measured slower; LIFU_PM_ALWAYS=1: unconditional sensor write-back);
+  // measurements in profiles/r2_order_experiments.md
+  {
+    const char* ord = getenv("LIFU_V2_ORDER");
+    const int o = ord ? atoi(ord) : 1;
+    Q.xrev = o & 1; Q.zmajor = (o >> 1) & 1;
+    const char* pa = getenv("LIFU_PM_ALWAYS");
+    Q.pm_always = (pa && pa[0] == '1') ? 1 : 0;
+  }
   // TMA descriptors of the z passes.  Opt-in (LIFU_Z_TMA=1): on C2 the persistent TMA-fed kernels measure 3 % slower
   // than the per-thread-load kernels (profiles/r1_z_tma.md) -- the z passes are bound by their two 256-point
   // transforms per element, not by load latency.
@@ -881,11 +892,12 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   const unsigned tx = Q.nxt + 1;                                   // regular kx tiles + the Nyquist slot
   const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (128 / Rx));   // row-pair batches of the persistent x kernels
   int nk = 0;
+  auto ygrid = [&](unsigned planes, unsigned ncomp_) { return Q.zmajor ? dim3(tx, ncomp_, planes) : dim3(tx, planes, ncomp_); };
   const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
   const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
   const int poly = s->P.poly_ok;
   // (1) pressure gradient
-  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 0>, dim3(tx, Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 0>, ygrid(Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_p", 8);
   // z passes: regular kx tiles through the persistent TMA-fed kernel, the Nyquist column through the per-thread-load
   // kernel on a 1-wide grid (zx = grid.x of that launch, Qn.bx0 selects the column)
@@ -913,7 +925,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   // (2) velocity update + forward x transform of the new velocity
   V2_R(Rx, (v2_launch_x_u<RR>(s, gx)));
   ++nk; mark("k2_x_u", s->homogeneous ? 48 : 60);
-  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 1>, dim3(tx, Q.Nz, 3), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_fwd<RR, 1>, ygrid(Q.Nz, 3), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_u", 24);
   // (3) source field on its slab
   if (src != 0) {
@@ -923,7 +935,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
       const int gs = (int)(((long long)Q.nzs * (Q.Ny / 2) + (256 / Rx) - 1) / (256 / Rx));
       V2_R(Rx, (v2_launch(k2_x_src<RR>, dim3(gs), 256, (size_t)(256 / RR) * RR * RR * 8 + 16 * (RR * RR + 1), st, s->P, Q)));
       ++nk; mark("k2_x_src", 8 * srcf);
-      V2_R(Ry, (v2_launch(k2_y_fwd<RR, 2>, dim3(tx, Q.nzs, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+      V2_R(Ry, (v2_launch(k2_y_fwd<RR, 2>, ygrid(Q.nzs, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
       ++nk; mark("k2_y_fwd_src", 8 * srcf);
     }
   }
@@ -934,7 +946,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_div<RR, 1>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn, ncomp)));
   else V2_R(Rz, (v2_launch(k2_z_div<RR, 0>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn, ncomp)));
   ++nk; mark("k2_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
-  V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, ncomp), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+  V2_R(Ry, (v2_launch(k2_y_inv<RR>, ygrid(Q.Nz, ncomp), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
   if (src == 0) V2_R(Rx, (v2_launch_x_rho_p<RR, 0>(s, gx)));
@@ -947,15 +959,176 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   } else {
     // (6) absorbing medium: the two fractional Laplacians, then the equation of state
     mark("k2_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
-    V2_R(Ry, (v2_launch(k2_y_fwd<RR, 3>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+    V2_R(Ry, (v2_launch(k2_y_fwd<RR, 3>, ygrid(Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
     ++nk; mark("k2_y_fwd_abs", 16);
     if (ztma) V2_ZTMA(ZOP_ABS, 2);
     V2_R(Rz, (v2_launch(k2_z_absorb<RR>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
     ++nk; mark("k2_z_absorb", 16);
-    V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+    V2_R(Ry, (v2_launch(k2_y_inv<RR>, ygrid(Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
     ++nk; mark("k2_y_inv_abs", 16);
     V2_R(Rx, (v2_launch_x_p<RR>(s, gx)));
     ++nk; mark("k2_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
+  }
+  LIFU_CUDA(cudaGetLastError());
+  if (n_kernels) *n_kernels = nk;
+  return LIFU_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// pipeline v3: the same fused passes for any 2/3/5/7-smooth axis length (fft_gen.cuh)
+static bool gen_factor(int n, int* radix, int* ns) {
+  static const int cand[8] = {16, 9, 8, 7, 5, 4, 3, 2};
+  int k = 0;
+  for (int c = 0; c < 8 && n > 1; ++c) {
+    const int r = cand[c];
+    while (n % r == 0 && n > 1) {
+      if (r == 16 && n / 16 == 2) break;          // 32 -> 8 x 4 rather than 16 x 2
+      if (k >= 8) return false;
+      radix[k++] = r;
+      n /= r;
+    }
+  }
+  if (ns) *ns = k;
+  return n == 1 && k >= 1;
+}
+
+static const size_t kV3SmemCap = 200 * 1024;
+
+static bool v3_eligible(const lifu_sim* s) {
+  if (s->pipeline == 1) return false;
+  int rad[8], ns;
+  for (int a = 0; a < 3; ++a) {
+    if (s->N[a] < 4 || !gen_factor(s->N[a], rad, &ns)) return false;
+    if ((size_t)2 * s->N[a] * 3 * sizeof(float2) > kV3SmemCap) return false;     // two tile buffers of two lanes must fit
+  }
+  return true;
+}
+
+static int v3_lanes(int n, int nbuf, size_t budget, int lmax) {
+  int L = lmax;
+  while (L > 1 && (size_t)nbuf * n * (L + 1) * sizeof(float2) > budget) L >>= 1;
+  return L;
+}
+
+static int v3_setup(lifu_sim* s) {
+  GParams& G = s->G;
+  const int Nx = s->N[0], Ny = s->N[1], Nz = s->N[2];
+  if (!s->v3_ready) {
+    G.Nx = Nx; G.Ny = Ny; G.Nz = Nz; G.Nxh = s->Nxh;
+    G.PH = (int)round_up(s->Nxh, 4);
+    G.My = (Ny + 1) / 2;
+    G.HS = (long long)Nz * Ny * G.PH;
+    G.ZS = (long long)Nz * G.My * Nx;
+    G.norm = (float)(1.0 / (2.0 * (double)s->V));
+    GenPlan* pl[3] = {&G.px, &G.py, &G.pz};
+    for (int a = 0; a < 3; ++a) {
+      const int n = s->N[a];
+      pl[a]->N = n;
+      if (!gen_factor(n, pl[a]->radix, &pl[a]->ns)) { set_error("v3: axis length %d is not 2/3/5/7-smooth", n); return LIFU_ERR_STATE; }
+      std::vector<float2> tw(n);
+      for (int m = 0; m < n; ++m) {
+        const double ang = -2.0 * M_PI * (double)m / (double)n;
+        tw[m] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+      }
+      LIFU_CHECK(dev_alloc(s, (void**)&s->d_gtw[a], sizeof(float2) * n));
+      LIFU_CUDA(cudaMemcpyAsync(s->d_gtw[a], tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice, s->stream));
+      LIFU_CUDA(cudaStreamSynchronize(s->stream));
+      pl[a]->tw = s->d_gtw[a];
+    }
+    LIFU_CHECK(dev_alloc(s, (void**)&G.ZP, sizeof(float2) * G.ZS));
+    LIFU_CHECK(dev_alloc(s, (void**)&G.Z4, sizeof(float2) * 4 * G.ZS));
+    LIFU_CHECK(dev_alloc(s, (void**)&G.H4, sizeof(float2) * 4 * G.HS));
+    LIFU_CHECK(dev_alloc(s, (void**)&G.pm, sizeof(float2) * s->V));
+    // tile widths: as wide as two CTAs per SM allow (strided passes: two buffers; x passes: up to five)
+    G.Ls = v3_lanes(std::max(Ny, Nz), 2, 108 * 1024, 16);
+    G.lsh_s = 0; while ((1 << G.lsh_s) < G.Ls) ++G.lsh_s;
+    s->v3_ready = true;
+  }
+  // the x passes need 3 buffers (+1 with a filtered source, +1 in an absorbing medium)
+  const int nbx = 3 + (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 0) + (s->absorbing ? 1 : 0);
+  G.Lx = v3_lanes(Nx, nbx, (size_t)nbx * Nx * 17 * sizeof(float2) <= 100 * 1024 ? 100 * 1024 : kV3SmemCap, 16);
+  G.lsh_x = 0; while ((1 << G.lsh_x) < G.Lx) ++G.lsh_x;
+  int z0 = 0, nz = 1;
+  if (s->n_src > 0) {
+    long long first = 0, last = 0;
+    LIFU_CUDA(cudaMemcpyAsync(&first, s->d_lin_exp, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaMemcpyAsync(&last, s->d_lin_exp + (s->n_src - 1), sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaStreamSynchronize(s->stream));
+    const long long plane = (long long)Nx * Ny;
+    z0 = (int)(first / plane);
+    nz = (int)(last / plane) - z0 + 1;
+  }
+  if (nz > s->v3_slab_planes) {
+    LIFU_CHECK(dev_alloc(s, (void**)&G.Sslab, sizeof(float) * (size_t)nz * Ny * Nx));
+    LIFU_CHECK(dev_alloc(s, (void**)&G.ZSslab, sizeof(float2) * (size_t)nz * G.My * Nx));
+    LIFU_CHECK(dev_alloc(s, (void**)&G.HSslab, sizeof(float2) * (size_t)nz * Ny * G.PH));
+    s->v3_slab_planes = nz;
+  }
+  G.z0s = z0; G.nzs = nz;
+  G.store_p = 0;
+  const char* pa = getenv("LIFU_PM_ALWAYS");
+  G.pm_always = (pa && pa[0] == '1') ? 1 : 0;
+  return LIFU_OK;
+}
+
+static int enqueue_step_v3(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
+  const GParams& G = s->G;
+  cudaStream_t st = s->stream;
+  const unsigned tx = (unsigned)((G.Nxh + G.Ls - 1) / G.Ls);
+  const size_t smy = (size_t)2 * G.Ny * (G.Ls + 1) * sizeof(float2);
+  const size_t smz = (size_t)2 * G.Nz * (G.Ls + 1) * sizeof(float2);
+  const size_t smx = (size_t)G.Nx * (G.Lx + 1) * sizeof(float2);      // one x tile buffer
+  const unsigned gx = (unsigned)(((long long)G.Nz * G.My + G.Lx - 1) / G.Lx);
+  const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
+  const double srcf = (double)G.nzs / G.Nz;
+  const int TS = 256;                                                  // threads of the strided passes
+  const int TX = (size_t)5 * smx > 100 * 1024 ? 512 : 256;             // fat x tiles run one CTA per SM: more threads
+  int nk = 0;
+  // (1) pressure gradient
+  v2_launch(g3_y_fwd<0>, dim3(tx, G.Nz, 1), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_p", 8);
+  v2_launch(g3_z_grad, dim3(tx, G.Ny), TS, smz, st, s->P, G); ++nk; mark("g3_z_grad", 12);
+  v2_launch(g3_y_inv_grad, dim3(tx, G.Nz), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv_grad", 20);
+  // (2) velocity update + forward x transform of the new velocity
+  if (s->homogeneous) v2_launch(g3_x_u<true>, dim3(gx), TX, 2 * smx, st, s->P, G);
+  else v2_launch(g3_x_u<false>, dim3(gx), TX, 2 * smx, st, s->P, G);
+  ++nk; mark("g3_x_u", s->homogeneous ? 48 : 60);
+  v2_launch(g3_y_fwd<1>, dim3(tx, G.Nz, 3), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_u", 24);
+  // (3) source field on its slab
+  if (src != 0) {
+    g3_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, G, s->S);
+    ++nk; mark("g3_source_scatter", 0);
+    if (src == 1) {
+      const unsigned gs = (unsigned)(((long long)G.nzs * G.My + G.Lx - 1) / G.Lx);
+      v2_launch(g3_x_src, dim3(gs), TX, 2 * smx, st, s->P, G); ++nk; mark("g3_x_src", 8 * srcf);
+      v2_launch(g3_y_fwd<2>, dim3(tx, G.nzs, 1), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_src", 8 * srcf);
+    }
+  }
+  // (4) divergence (+ filtered source) through z and back through y
+  const int ncomp = src == 1 ? 4 : 3;
+  v2_launch(g3_z_pass<0>, dim3(tx, G.Ny), TS, smz, st, s->P, G, ncomp); ++nk;
+  mark("g3_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
+  v2_launch(g3_y_inv, dim3(tx, G.Nz, ncomp), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv", 8 * ncomp);
+  // (5) density update, source, equation of state, sensor, forward x transform of p
+  const int nbx = 3 + (src == 1 ? 1 : 0) + (s->absorbing ? 1 : 0);
+#define V3_RHO(H, SRCV, A) v2_launch(g3_x_rho_p<H, SRCV, A>, dim3(gx), TX, nbx * smx, st, s->P, G)
+#define V3_RHO_SRC(H, A) do { if (src == 0) V3_RHO(H, 0, A); else if (src == 1) V3_RHO(H, 1, A); else V3_RHO(H, 2, A); } while (0)
+  if (s->homogeneous) { if (s->absorbing) V3_RHO_SRC(true, true); else V3_RHO_SRC(true, false); }
+  else { if (s->absorbing) V3_RHO_SRC(false, true); else V3_RHO_SRC(false, false); }
+#undef V3_RHO_SRC
+#undef V3_RHO
+  ++nk;
+  const double sens = (double)s->Vin / (double)s->V;
+  if (!s->absorbing) {
+    mark("g3_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+  } else {
+    mark("g3_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+    v2_launch(g3_y_fwd<3>, dim3(tx, G.Nz, 2), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_abs", 16);
+    v2_launch(g3_z_pass<1>, dim3(tx, G.Ny), TS, smz, st, s->P, G, 2); ++nk; mark("g3_z_absorb", 16);
+    v2_launch(g3_y_inv, dim3(tx, G.Nz, 2), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv_abs", 16);
+    const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
+    if (s->homogeneous) v2_launch(g3_x_p<true>, dim3(gx), TX, 3 * smx, st, s->P, G, use_tau, use_eta);
+    else v2_launch(g3_x_p<false>, dim3(gx), TX, 3 * smx, st, s->P, G, use_tau, use_eta);
+    ++nk; mark("g3_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
   }
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
@@ -1121,6 +1294,11 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
     if (n_ffts) *n_ffts = 0;
     return rc2;
   }
+  if (s->last_used_v3) {
+    int rc3 = enqueue_step_v3(s, src_active, n_kernels, mark);
+    if (n_ffts) *n_ffts = 0;
+    return rc3;
+  }
   const int gbh = grid_blocks(s, s->Vh, 256);
   const int gbr = grid_blocks(s, s->V, 256);
   int nk = 0, nf = 0;
@@ -1239,11 +1417,18 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
               s->N[0], s->N[1], s->N[2]);
     return LIFU_ERR_STATE;
   }
+  if (s->pipeline == 3 && !v3_eligible(s)) {
+    set_error("lifu_run: LIFU_PIPELINE=v3 needs 2/3/5/7-smooth axes (grid is %dx%dx%d)", s->N[0], s->N[1], s->N[2]);
+    return LIFU_ERR_STATE;
+  }
   s->last_used_v2 = !s->sl.on && v2_eligible(s);
+  s->last_used_v3 = !s->sl.on && !s->last_used_v2 && v3_eligible(s);
   if (s->sl.on) {
     LIFU_CHECK(slab_plans(s));
   } else if (s->last_used_v2) {
     LIFU_CHECK(v2_setup(s));
+  } else if (s->last_used_v3) {
+    LIFU_CHECK(v3_setup(s));
   } else {
     LIFU_CHECK(build_plans(s));
     cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
@@ -1265,6 +1450,11 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     LIFU_CUDA(cudaMemsetAsync(s->Q.ZP, 0, sizeof(float2) * s->Q.ZS, st));
     LIFU_CUDA(cudaMemsetAsync(s->Q.Sslab, 0, sizeof(float) * (size_t)s->Q.nzs * s->N[1] * s->N[0], st));
     k2_pm_init<<<grid_blocks(s, s->V, 256), 256, 0, st>>>(s->Q.pm, s->V);
+  }
+  if (s->last_used_v3) {
+    LIFU_CUDA(cudaMemsetAsync(s->G.ZP, 0, sizeof(float2) * s->G.ZS, st));
+    LIFU_CUDA(cudaMemsetAsync(s->G.Sslab, 0, sizeof(float) * (size_t)s->G.nzs * s->N[1] * s->N[0], st));
+    k2_pm_init<<<grid_blocks(s, s->V, 256), 256, 0, st>>>(s->G.pm, s->V);
   }
   k_fill<<<grid_blocks(s, s->Vsens, 256), 256, 0, st>>>(P.pmax, s->Vsens, -INFINITY);
   k_fill<<<grid_blocks(s, s->Vsens, 256), 256, 0, st>>>(P.pmin, s->Vsens, INFINITY);
@@ -1297,11 +1487,11 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   int rc = LIFU_OK;
   for (int t = 0; t < nt && rc == LIFU_OK; ++t) {
     const int v = t < L ? 0 : 1;
-    if (s->last_used_v2 && t == nt - 1) {   // last step also materialises the real-space pressure
-      s->Q.store_p = 1;
+    if ((s->last_used_v2 || s->last_used_v3) && t == nt - 1) {   // last step also materialises the real-space pressure
+      s->Q.store_p = 1; s->G.store_p = 1;
       int k1 = 0, f1 = 0;
       rc = enqueue_step(s, v == 0, &k1, &f1);
-      s->Q.store_p = 0;
+      s->Q.store_p = 0; s->G.store_p = 0;
       if (nk[v] == 0) { nk[v] = k1; nf[v] = f1; }
     } else if (graphs) {
       if (cudaGraphLaunch(gexec[v], st) != cudaSuccess) { set_error("cudaGraphLaunch failed at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); rc = LIFU_ERR_CUDA; }
@@ -1311,6 +1501,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && s->last_used_v2) k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
+  if (rc == LIFU_OK && s->last_used_v3) g3_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->G.pm);
   if (rc == LIFU_OK && p_max && s->Vsens) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && p_min && s->Vsens) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   cudaError_t se = cudaStreamSynchronize(st);
@@ -1380,7 +1571,7 @@ int lifu_get_packaged(lifu_sim* s, float* p_max, float* pnp, double* intensity) 
 int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, char* names, int name_stride,
                         double* ms, double* bytes_per_voxel, int* n_stages) {
   if (!s || reps <= 0 || !ms || !n_stages) { set_error("lifu_profile_stages: bad argument"); return LIFU_ERR_INVALID; }
-  if (!(s->plans_ready || s->v2_ready || s->sl.plans) || !s->medium_set || !s->geometry_set || !s->drive_set) {
+  if (!(s->plans_ready || s->v2_ready || s->v3_ready || s->sl.plans) || !s->medium_set || !s->geometry_set || !s->drive_set) {
     set_error("lifu_profile_stages: call lifu_run once first");
     return LIFU_ERR_STATE;
   }

@@ -109,6 +109,12 @@ struct lifu_sim {
   unsigned char tmS[128] __attribute__((aligned(64))) = {};   // CUtensorMap of the source slab spectrum
   bool last_used_v2 = false;
 
+  // pipeline v3 (fft_gen.cuh): the fused passes for any 2/3/5/7-smooth grid
+  bool v3_ready = false, last_used_v3 = false;
+  lifu::GParams G{};
+  float2* d_gtw[3] = {nullptr, nullptr, nullptr};
+  long long v3_slab_planes = 0;
+
   // per-stage profiling (lifu_profile_stages)
   bool prof_on = false;
   int prof_used = 0;

@@ -68,7 +68,7 @@ def run_oracle_case(case, dtype=np.float32, asm=None, max_steps=None, backend="n
 
 
 def run_cuda_case(case, alpha_mode="binary", source_mode="additive", geometry=None, max_steps=None, device=0,
-                  pipeline=None, fields=()):
+                  pipeline=None, fields=(), pml=(-1, -1, -1)):
     """Drive the C ABI exactly like openlifu_b200.sim.run_simulation does, from plain data.
     pipeline: None (auto) | "v1" (cuFFT) | "v2" (fused FFT passes); read by lifu_create from LIFU_PIPELINE."""
     import os
@@ -89,7 +89,7 @@ def run_cuda_case(case, alpha_mode="binary", source_mode="additive", geometry=No
     if case["sensitivity"] is not None:
         base = base * case["sensitivity"]
     n_delay = np.array([int(dl / dt) for dl in case["delays"]], dtype=np.int32)
-    with _lib.LifuSim(N, d, dt, Nt, device=device) as sim:
+    with _lib.LifuSim(N, d, dt, Nt, device=device, pml=pml) as sim:
         sim.set_medium(case["c0"], case["rho0"], case["alpha"], alpha_power=0.9, alpha_mode=alpha_mode)
         if geometry is None:
             sim.set_elements(case["pos_m"] + offset, case["size_m"], case["angles_deg"], 0.05, 5)
