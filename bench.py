@@ -378,7 +378,7 @@ def slab_measure(rank, local_rank, world, n, time_steps, steps, warmup, exchange
             "fields": fields, "n": n}
 
 
-def single_measure(local_rank, n, time_steps, steps, warmup, homogeneous=False):
+def single_measure(local_rank, n, time_steps, steps, warmup, homogeneous=False, profile=False):
     """The same C5-class scene on ONE GPU through the ordinary (non-slab) handle: the n = 1 point of the slab leg and
     the field the slab result is compared with."""
     import torch
@@ -407,6 +407,8 @@ def single_measure(local_rank, n, time_steps, steps, warmup, homogeneous=False):
     ms = ev0.elapsed_time(ev1)
     out = {"value": st["voxels"] * st["steps"] * steps / (ms * 1e-3) / 1e6, "p_max": d_pmax.cpu().numpy(),
            "p_min": d_pmin.cpu().numpy(), "fft_launches": st["fft_launches"], "ms_per_time_step": ms / steps / st["steps"]}
+    if profile:
+        out["stages"] = {nm: round(t, 4) for nm, t, _ in sim.profile_stages(reps=2, with_source=True)}
     sim.close()
     return out
 

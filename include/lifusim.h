@@ -79,6 +79,8 @@ typedef struct lifu_stats {
   double bytes_per_voxel_step; /* algorithmic bytes model, averaged over steps */
   int32_t homogeneous;
   int32_t absorbing;
+  int32_t steady_source_steps; /* steps on which the source ran as q1(t) F1 + q2(t) F2 (filtered once) */
+  int32_t reserved;
 } lifu_stats;
 
 typedef struct lifu_sim lifu_sim; /* opaque */
@@ -268,6 +270,26 @@ int lifu_analysis_set_focus(lifu_analysis* a, int32_t focus, const float* pnp, c
 int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_query* q, const double* line_pts,
                             lifu_focus_metrics* out, double* line_vals);
 int lifu_analysis_destroy(lifu_analysis* a);
+
+/* ---- plan stack: the fields of every focus of one plan kept on the device ---------------
+ * Replaces, on the device, the per-focus packaging of run_simulation (kwave_if.py:131-146), the xa.concat over foci
+ * (plan/protocol.py:340-347), the in-place rescaling of Solution.scale (plan/solution.py:334-336) and the
+ * aggregation over foci (plan/protocol.py:382-392).  Layout per variable: [focus][z][y][x] (x fastest); p_max and
+ * pnp = -p_min float32, intensity float64 -- the arrays of the returned Dataset, bit for bit. */
+typedef struct lifu_stack lifu_stack; /* opaque */
+int lifu_stack_create(int device, void* cuda_stream, const int32_t n[3], int32_t n_foci, lifu_stack** out);
+int lifu_stack_destroy(lifu_stack* stack);
+/* Package the result of the solver's last lifu_run into slot `focus` (needs lifu_set_two_z): no host round trip. */
+int lifu_stack_put(lifu_stack* stack, int32_t focus, lifu_sim* sim);
+/* Solution.scale on one focus: pressures *= s (product in float64, rounded to float32: numpy >= 2 semantics of
+ * `float32_array *= np.float64(s)`), intensity *= s*s. */
+int lifu_stack_scale(lifu_stack* stack, int32_t focus, double s);
+/* Device pointers of one focus (for lifu_analysis_set_focus with strides (1, Nx, Nx*Ny)). */
+int lifu_stack_pointers(lifu_stack* stack, int32_t focus, float** p_max, float** pnp, double** intensity);
+/* Copy out one focus (focus >= 0) or the whole stack (focus = -1); host or device destinations, any may be NULL. */
+int lifu_stack_get(lifu_stack* stack, int32_t focus, float* p_max, float* pnp, double* intensity);
+/* max over foci of p_max and pnp (NaN-skipping), mean over foci of the intensity (sum in focus order, one division). */
+int lifu_stack_aggregate(lifu_stack* stack, float* p_max_max, float* pnp_max, double* intensity_mean);
 
 #ifdef __cplusplus
 }

@@ -126,6 +126,14 @@ struct V2Params {
   int xrev;                         // persistent x kernels walk their row pairs from the last one down (L2 reuse across passes)
   int zmajor;                       // batched y passes: grid (tiles, ncomp, Nz) instead of (tiles, Nz, ncomp)
   int pm_always;                    // write the sensor pair back even when it did not change (measurement switch)
+  // steady-state source (see v2_build_steady in lifusim.cu): while every element is driven, the delayed drive signals
+  // span a space of rank <= 2 in time, S_t = q_1(t) F_1 + q_2(t) F_2, and the k-space source filter is applied ONCE to
+  // the two spatial fields instead of to S_t on every step
+  const float* FK;                  // [2][RS] filtered basis fields (real, expanded grid)
+  const float* qsrc;                // [2][nws] time coefficients q_k(t0s + i)
+  float* qcur;                      // [2] coefficients of the current step (written by the first kernel of the step)
+  int t0s, nws;                     // first step and length of the steady window (nws = 0: off)
+  int comp0;                        // component offset of k2_y_inv, first component of k2_z_div
 };
 
 // Pipeline v3 (fft_gen.cuh): generic-radix fused passes.

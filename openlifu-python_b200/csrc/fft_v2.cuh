@@ -216,6 +216,11 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_fwd(StepParams P
   float2* xa = reinterpret_cast<float2*>(smraw);
   const float2* Zin = MODE == 0 ? Q.ZP : ((MODE == 1 || MODE == 3) ? Q.Z4 + comp * Q.ZS : Q.ZSslab);
   float2* Hout = MODE == 2 ? Q.HSslab : Q.H4 + comp * Q.HS;
+  if (MODE == 0 && Q.nws > 0 && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    // first kernel of the step: the steady-source coefficients of this step, read by k2_x_rho_p<SRC = 3>
+    const int ts = *P.step - Q.t0s;
+    if (ts >= 0 && ts < Q.nws) { Q.qcur[0] = Q.qsrc[ts]; Q.qcur[1] = Q.qsrc[Q.nws + ts]; }
+  }
   const int km = (Q.Nx - kx) & (Q.Nx - 1);
   const float2* zp = Zin + ((long long)zc * (Q.Ny / 2) + t) * Q.Nx;     // packed line m = q*R + t
   const int qstep = R * Q.Nx;
@@ -337,8 +342,16 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P
   float2* hp = Q.H4 + (long long)t * zs + ky * Q.PH + kx;
   const float2* sp = Q.HSslab + (long long)(t - Q.z0s) * zs + ky * Q.PH + kx;
   float2 v[R], nx[R];
+  if (Q.comp0 < 3) {
 #pragma unroll
-  for (int j = 0; j < R; ++j) v[j] = hp[j * jstep];
+    for (int j = 0; j < R; ++j) v[j] = hp[Q.comp0 * Q.HS + j * jstep];
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int zr = t + R * j - Q.z0s;
+      v[j] = (zr >= 0 && zr < Q.nzs) ? sp[j * jstep] : make_float2(0.f, 0.f);
+    }
+  }
   const float axy = P.ax2[kx] + P.ay2[ky];
   float kap[R];
 #pragma unroll
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_z_div(StepParams P
 #pragma unroll
   for (int k1 = 0; k1 < R; ++k1) kap[k1] = kappa_sel<POLY>(axy + kap[k1]) * Q.norm;
 #pragma unroll 1
-  for (int comp = 0; comp < ncomp; ++comp) {
+  for (int comp = Q.comp0; comp < ncomp; ++comp) {
     // prefetch the next component
     if (comp + 1 < 3) {
       const float2* np = hp + (comp + 1) * Q.HS;
@@ -428,6 +441,7 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_inv(StepParams P
   const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
   int comp, by;
   comp_plane(Q, comp, by);
+  comp += Q.comp0;
   int kx, z;
   if (!lane_map(Q, Q.Nz, l, kx, z, by)) return;
   float2* xa = reinterpret_cast<float2*>(smraw);
@@ -617,7 +631,7 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_u(StepParams P, V2Par
   cp_async_wait<0>();
 }
 
-// SRC: 0 none, 1 filtered source in Z4[3], 2 unfiltered dense slab
+// SRC: 0 none, 1 filtered source in Z4[3], 2 unfiltered dense slab, 3 steady-state source q1 F1 + q2 F2 (real fields Q.FK)
 // Items per row pair: [source spectrum], rho_x, rho_y, rho_z, sensor rows (pm = interleaved (p_max, p_min)
 // on the expanded grid; rows in the PML are skipped).
 // ABS (absorbing medium): no equation of state here.  The kernel forms the operands of the two fractional
@@ -627,8 +641,8 @@ template <int R, bool HOMOG, int SRC, bool ABS = false>
 __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V2Params Q) {
   using XS = XStageRho<R, HOMOG>;
   constexpr int N = R * R, G = XS::GROUPS;
-  constexpr int NI = (SRC == 1 ? 5 : 4) - (ABS ? 1 : 0);
-  constexpr int C0 = SRC == 1 ? 1 : 0;                  // item index of rho_x
+  constexpr int NI = ((SRC == 1 || SRC == 3) ? 5 : 4) - (ABS ? 1 : 0);
+  constexpr int C0 = (SRC == 1 || SRC == 3) ? 1 : 0;    // item index of rho_x
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
   const int g = threadIdx.x / R, t = threadIdx.x % R;
@@ -647,7 +661,13 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
       pair_rows(Q, pair, z, ylo);
       const long long r0 = ((long long)z * Q.Ny + ylo) * N;
       char* st = gbase + stage * XS::BYTES;
-      if (c < 3) {
+      if (SRC == 3 && c < 0) {
+        // source item of the steady window: rows lo / hi of the two filtered basis fields
+        XS::copy(st, reinterpret_cast<const char*>(Q.FK + r0), 4 * N, t);
+        XS::copy(st + 4 * N, reinterpret_cast<const char*>(Q.FK + r0 + hi), 4 * N, t);
+        XS::copy(st + 8 * N, reinterpret_cast<const char*>(Q.FK + P.RS + r0), 4 * N, t);
+        XS::copy(st + 12 * N, reinterpret_cast<const char*>(Q.FK + P.RS + r0 + hi), 4 * N, t);
+      } else if (c < 3) {
         XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + (c < 0 ? 3 : c) * Q.ZS + (long long)pair * N), 8 * N, t);
         if (c >= 0) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0), 4 * N, t);
@@ -674,6 +694,8 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
   issue(lpair, 1 - C0, 1, iters > 0, 0);
   float2 src[R], sum[R];
   float2 dsum[ABS ? R : 1];
+  float2 q1 = make_float2(0.f, 0.f), q2 = q1;
+  if (SRC == 3) { q1.x = q1.y = Q.qcur[0]; q2.x = q2.y = Q.qcur[1]; }
   for (int it = 0; it < iters; ++it, lpair += pstep) {
     const int pair = phys_pair(Q, lpair);
     int z, ylo;
@@ -689,7 +711,14 @@ __global__ void __launch_bounds__(128, HOMOG ? 3 : 2) k2_x_rho_p(StepParams P, V
       float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
       const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
       const float* mb = reinterpret_cast<const float*>(mbase + (it & 1) * 8 * N);
-      if (c < 3) {
+      if (SRC == 3 && c < 0) {
+        const float* fb = reinterpret_cast<const float*>(zb);     // [F1 lo | F1 hi | F2 lo | F2 hi]
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          const int x = t + R * j;
+          src[j] = __ffma2_rn(q2, make_float2(fb[2 * N + x], fb[3 * N + x]), __fmul2_rn(q1, make_float2(fb[x], fb[N + x])));
+        }
+      } else if (c < 3) {
         float2 v[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) v[j] = zb[t + R * j];
@@ -953,6 +982,39 @@ __global__ void __launch_bounds__(128) k2_source_scatter(StepParams P, V2Params 
     }
     Q.Sslab[S.lin_exp[i] - slab0] = acc * S.scale[i];
   }
+}
+
+// Steady-state source, set-up: dense slab of one spatial basis field, sum_e W[i,e] coef_e (coef_e = gain_e * c_{k,e}).
+__global__ void __launch_bounds__(128) k2_source_basis(StepParams P, V2Params Q, SourceParams S, const float* __restrict__ coef) {
+  const long long slab0 = (long long)Q.z0s * P.Ny * P.Nx;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.n_src;
+       i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int j = S.row_ptr[i]; j < S.row_ptr[i + 1]; ++j) acc = fmaf(S.w[j], coef[S.col[j]], acc);
+    Q.Sslab[S.lin_exp[i] - slab0] = acc * S.scale[i];
+  }
+}
+
+// x inverse of one packed spectrum field back to a real field (row pairs -> two rows).  grid = Nz*(Ny/2)/G, G = 256/R
+template <int R>
+__global__ void __launch_bounds__(256) k2_x_inv_real(StepParams P, V2Params Q, const float2* __restrict__ Zin, float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int G = 256 / R, N = R * R;
+  float4* tws = reinterpret_cast<float4*>(smraw + G * N * 8);
+  for (int i = threadIdx.x; i <= N; i += 256) tws[i] = Q.tw4x[i];
+  __syncthreads();
+  const int g = threadIdx.x / R, t = threadIdx.x % R;
+  float2* sm = reinterpret_cast<float2*>(smraw) + g * N;
+  const int pair = blockIdx.x * G + g;
+  int z, ylo;
+  pair_rows(Q, pair, z, ylo);
+  const long long r0 = ((long long)z * Q.Ny + ylo) * N, hi = (long long)Q.Ry * N;
+  float2 v[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) v[j] = Zin[(long long)pair * N + t + R * j];
+  line_fft_sw<R, true>(v, tws, sm, t);
+#pragma unroll
+  for (int j = 0; j < R; ++j) { out[r0 + t + R * j] = v[j].x; out[r0 + hi + t + R * j] = v[j].y; }
 }
 
 // sensor field helpers: pm = interleaved (p_max, p_min) on the expanded grid

@@ -836,6 +836,7 @@ static int v2_setup(lifu_sim* s) {
   Q.z0s = z0; Q.nzs = nz;
   Q.store_p = 0;
   Q.bx0 = 0;
+  Q.comp0 = 0; Q.nws = 0; Q.t0s = 0;
   // traversal-order switches (LIFU_V2_ORDER bit 0: x kernels from the last row pair down -- on by default, bit 1:
   // plane-major batched y passes -- off, measured slower; LIFU_PM_ALWAYS=1: unconditional sensor write-back);
   // measurements in profiles/r2_order_experiments.md
@@ -885,7 +886,117 @@ template <int R> static void v2_launch_x_p(lifu_sim* s, int nbatch) {
   else v2_launch(k2_x_p<R, false>, grid, 128, XStageU<R, false>::SMEM, s->stream, s->P, s->Q, use_tau, use_eta);
 }
 
-static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const std::function<void(const char*, double)>& mark) {
+// ------------------------------------------------------------------------------------------
+// Steady-state source.  S_t = sum_e W_e gain_e s(t - n_e) (A.7); while every element is inside its burst,
+// t in [max n_e, min n_e + n_base), the delayed copies s(t - n) of the base signal span a space of rank <= 2 for the
+// sinusoidal bursts OpenLIFU drives (kwave_if.py:101-102) -- checked numerically here, not assumed: pivoted Gram-Schmidt
+// over the distinct delays, accepted only when the residual is below 5e-7 of the signal norm.  Then
+// S_t = q_1(t) F_1 + q_2(t) F_2 with F_k = sum_e W_e gain_e c_{k,e}, and the k-space source filter cos(c_ref k dt/2),
+// being linear and time-invariant, is applied once to F_1 and F_2 (set-up: four small launches each) instead of to S_t on
+// every step: on those steps the source costs 8 B per voxel of reads in k2_x_rho_p and nothing else.
+static int v2_build_steady(lifu_sim* s, int nt) {
+  V2Params& Q = s->Q;
+  Q.nws = 0; Q.t0s = 0;
+  const char* env = getenv("LIFU_SOURCE_STEADY");
+  if ((env && env[0] == '0') || s->source_mode != LIFU_SOURCE_ADDITIVE || s->n_src <= 0) return LIFU_OK;
+  const int n_el = s->n_el, nb = s->n_base;
+  std::vector<float> base(nb), gain(n_el);
+  std::vector<int> delay(n_el);
+  cudaStream_t st = s->stream;
+  LIFU_CUDA(cudaMemcpyAsync(base.data(), s->d_base, sizeof(float) * nb, cudaMemcpyDeviceToHost, st));
+  LIFU_CUDA(cudaMemcpyAsync(gain.data(), s->d_gain, sizeof(float) * n_el, cudaMemcpyDeviceToHost, st));
+  LIFU_CUDA(cudaMemcpyAsync(delay.data(), s->d_delay, sizeof(int) * n_el, cudaMemcpyDeviceToHost, st));
+  LIFU_CUDA(cudaStreamSynchronize(st));
+  int dmin = INT32_MAX, dmax = 0;
+  for (int d : delay) { dmin = std::min(dmin, d); dmax = std::max(dmax, d); }
+  const int t0 = dmax, t1 = std::min(dmin + nb, nt);
+  const int nw = t1 - t0;
+  if (nw < 24) return LIFU_OK;
+  std::vector<int> dd(delay);
+  std::sort(dd.begin(), dd.end());
+  dd.erase(std::unique(dd.begin(), dd.end()), dd.end());
+  const int m = (int)dd.size();
+  // rows A_j[i] = s(t0 + i - dd[j]); pivoted Gram-Schmidt in float64
+  auto A = [&](int j, int i) { return (double)base[t0 + i - dd[j]]; };
+  auto dot = [&](const std::vector<double>& a, const std::vector<double>& b) { double r = 0; for (int i = 0; i < nw; ++i) r += a[i] * b[i]; return r; };
+  std::vector<std::vector<double>> R(m, std::vector<double>(nw));
+  double top = 0; int p1 = 0;
+  for (int j = 0; j < m; ++j) {
+    for (int i = 0; i < nw; ++i) R[j][i] = A(j, i);
+    const double n2 = dot(R[j], R[j]);
+    if (n2 > top) { top = n2; p1 = j; }
+  }
+  if (!(top > 0)) return LIFU_OK;
+  std::vector<double> q1(R[p1]), q2(nw, 0.0);
+  { const double inv = 1.0 / std::sqrt(top); for (double& v : q1) v *= inv; }
+  std::vector<double> c1(m), c2(m, 0.0);
+  double top2 = 0; int p2 = -1;
+  for (int j = 0; j < m; ++j) {
+    c1[j] = dot(R[j], q1);
+    for (int i = 0; i < nw; ++i) R[j][i] -= c1[j] * q1[i];
+    const double n2 = dot(R[j], R[j]);
+    if (n2 > top2) { top2 = n2; p2 = j; }
+  }
+  const double tol2 = 5e-7 * 5e-7 * top;
+  if (p2 >= 0 && top2 > tol2) {
+    q2 = R[p2];
+    const double inv = 1.0 / std::sqrt(top2);
+    for (double& v : q2) v *= inv;
+    for (int j = 0; j < m; ++j) {
+      c2[j] = dot(R[j], q2);
+      for (int i = 0; i < nw; ++i) R[j][i] -= c2[j] * q2[i];
+      if (dot(R[j], R[j]) > tol2) return LIFU_OK;          // rank > 2: keep the generic path on every step
+    }
+  }
+  // device side: coefficients per element, time coefficients, the two filtered basis fields
+  std::vector<float> coef(2 * (size_t)n_el), qs(2 * (size_t)nw);
+  for (int e = 0; e < n_el; ++e) {
+    const int j = (int)(std::lower_bound(dd.begin(), dd.end(), delay[e]) - dd.begin());
+    coef[e] = (float)((double)gain[e] * c1[j]);
+    coef[n_el + e] = (float)((double)gain[e] * c2[j]);
+  }
+  for (int i = 0; i < nw; ++i) { qs[i] = (float)q1[i]; qs[nw + i] = (float)q2[i]; }
+  if (!s->d_fk) LIFU_CHECK(dev_alloc(s, (void**)&s->d_fk, sizeof(float) * 2 * (size_t)s->RS));
+  if (!s->d_qcur) LIFU_CHECK(dev_alloc(s, (void**)&s->d_qcur, sizeof(float) * 4));
+  if ((size_t)nw > s->qsrc_cap || !s->d_qsrc) {
+    LIFU_CHECK(dev_alloc(s, (void**)&s->d_qsrc, sizeof(float) * 2 * (size_t)nw));
+    s->qsrc_cap = nw;
+  }
+  if ((size_t)n_el > s->coef_cap || !s->d_coef) {
+    LIFU_CHECK(dev_alloc(s, (void**)&s->d_coef, sizeof(float) * 2 * (size_t)n_el));
+    s->coef_cap = n_el;
+  }
+  LIFU_CUDA(cudaMemcpyAsync(s->d_qsrc, qs.data(), sizeof(float) * qs.size(), cudaMemcpyHostToDevice, st));
+  LIFU_CUDA(cudaMemcpyAsync(s->d_coef, coef.data(), sizeof(float) * coef.size(), cudaMemcpyHostToDevice, st));
+  LIFU_CUDA(cudaStreamSynchronize(st));                      // the host vectors go out of scope
+  const int Rx = s->R[0], Ry = s->R[1], Rz = s->R[2];
+  const unsigned tx = Q.nxt + 1;
+  V2Params Qs = Q;
+  Qs.comp0 = 3; Qs.zmajor = 0;
+  const int poly = s->P.poly_ok;
+  const int gs = (int)(((long long)Q.nzs * (Q.Ny / 2) + (256 / Rx) - 1) / (256 / Rx));
+  const int gall = (int)((long long)Q.Nz * (Q.Ny / 2) / (256 / Rx));
+  const size_t smx = (size_t)(256 / Rx) * Rx * Rx * 8 + 16 * (Rx * Rx + 1);
+  for (int k = 0; k < 2; ++k) {
+    LIFU_CUDA(cudaMemsetAsync(Q.Sslab, 0, sizeof(float) * (size_t)Q.nzs * s->N[1] * s->N[0], st));
+    k2_source_basis<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, Qs, s->S, s->d_coef + (size_t)k * n_el);
+    V2_R(Rx, (v2_launch(k2_x_src<RR>, dim3(gs), 256, smx, st, s->P, Qs)));
+    V2_R(Ry, (v2_launch(k2_y_fwd<RR, 2>, dim3(tx, Q.nzs, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Qs)));
+    if (poly == 2) V2_R(Rz, (v2_launch(k2_z_div<RR, 2>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qs, 4)));
+    else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_div<RR, 1>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qs, 4)));
+    else V2_R(Rz, (v2_launch(k2_z_div<RR, 0>, dim3(tx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qs, 4)));
+    V2_R(Ry, (v2_launch(k2_y_inv<RR>, dim3(tx, Q.Nz, 1), 16 * RR, Strided<RR>::smem(1), st, s->P, Qs)));
+    V2_R(Rx, (v2_launch(k2_x_inv_real<RR>, dim3(gall), 256, smx, st, s->P, Qs, (const float2*)(Q.Z4 + 3 * Q.ZS), s->d_fk + (size_t)k * s->RS)));
+  }
+  LIFU_CUDA(cudaMemsetAsync(Q.Sslab, 0, sizeof(float) * (size_t)Q.nzs * s->N[1] * s->N[0], st));
+  LIFU_CUDA(cudaGetLastError());
+  Q.FK = s->d_fk; Q.qsrc = s->d_qsrc; Q.qcur = s->d_qcur;
+  Q.t0s = t0; Q.nws = nw;
+  return LIFU_OK;
+}
+
+// kind: 0 no source, 1 source active (generic path), 2 steady window (rank-2 source, k2_x_rho_p<SRC = 3>)
+static int enqueue_step_v2(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark) {
   const V2Params& Q = s->Q;
   cudaStream_t st = s->stream;
   const int Rx = s->R[0], Ry = s->R[1], Rz = s->R[2];
@@ -893,7 +1004,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   const int gx = (int)((long long)Q.Nz * (Q.Ny / 2) / (128 / Rx));   // row-pair batches of the persistent x kernels
   int nk = 0;
   auto ygrid = [&](unsigned planes, unsigned ncomp_) { return Q.zmajor ? dim3(tx, ncomp_, planes) : dim3(tx, planes, ncomp_); };
-  const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
+  const int src = kind == 0 ? 0 : (kind == 2 ? 3 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2));
   const double srcf = (double)Q.nzs / Q.Nz;   // slab share of a full pass
   const int poly = s->P.poly_ok;
   // (1) pressure gradient
@@ -928,7 +1039,7 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   V2_R(Ry, (v2_launch(k2_y_fwd<RR, 1>, ygrid(Q.Nz, 3), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
   ++nk; mark("k2_y_fwd_u", 24);
   // (3) source field on its slab
-  if (src != 0) {
+  if (src == 1 || src == 2) {
     k2_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, Q, s->S);
     ++nk; mark("k2_source_scatter", 0);
     if (src == 1) {
@@ -951,14 +1062,15 @@ static int enqueue_step_v2(lifu_sim* s, bool src_active, int* n_kernels, const s
   // (5) density update, source, equation of state, sensor, forward x transform of p
   if (src == 0) V2_R(Rx, (v2_launch_x_rho_p<RR, 0>(s, gx)));
   else if (src == 1) V2_R(Rx, (v2_launch_x_rho_p<RR, 1>(s, gx)));
-  else V2_R(Rx, (v2_launch_x_rho_p<RR, 2>(s, gx)));
+  else if (src == 2) V2_R(Rx, (v2_launch_x_rho_p<RR, 2>(s, gx)));
+  else V2_R(Rx, (v2_launch_x_rho_p<RR, 3>(s, gx)));
   ++nk;
   const double sens = (double)s->n[1] * s->n[2] / ((double)s->N[1] * s->N[2]);   // sensor rows are full x lines
   if (!s->absorbing) {
-    mark("k2_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+    mark("k2_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : (src == 3 ? 8 : 0)));
   } else {
     // (6) absorbing medium: the two fractional Laplacians, then the equation of state
-    mark("k2_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
+    mark("k2_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : (src == 3 ? 8 : 0)));
     V2_R(Ry, (v2_launch(k2_y_fwd<RR, 3>, ygrid(Q.Nz, 2), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
     ++nk; mark("k2_y_fwd_abs", 16);
     if (ztma) V2_ZTMA(ZOP_ABS, 2);
@@ -1002,6 +1114,12 @@ static bool v3_eligible(const lifu_sim* s) {
     if ((size_t)2 * s->N[a] * 3 * sizeof(float2) > kV3SmemCap) return false;     // two tile buffers of two lanes must fit
   }
   return true;
+}
+
+static bool v3_auto(const lifu_sim* s) {
+  const char* e = getenv("LIFU_V3_AUTO");
+  if (e) return e[0] == '1';
+  return false;
 }
 
 static int v3_lanes(int n, int nbuf, size_t budget, int lmax) {
@@ -1274,7 +1392,9 @@ static int enqueue_step_slab(lifu_sim* s, bool src_active, int* n_kernels, int* 
 }
 
 // Enqueue one time step on the handle's stream.  Counts hand-written kernels / FFT executions.
-static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_ffts) {
+// kind: 0 no source, 1 source active, 2 steady window of the v2 pipeline (v2_build_steady)
+static int enqueue_step(lifu_sim* s, int kind, int* n_kernels, int* n_ffts) {
+  const bool src_active = kind != 0;
   StepParams& P = s->P;
   cudaStream_t st = s->stream;
   // optional per-stage timing (lifu_profile_stages): an event after every stage
@@ -1290,7 +1410,7 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
   mark("begin", 0);
   if (s->sl.on) return enqueue_step_slab(s, src_active, n_kernels, n_ffts, mark);
   if (s->last_used_v2) {
-    int rc2 = enqueue_step_v2(s, src_active, n_kernels, mark);
+    int rc2 = enqueue_step_v2(s, kind, n_kernels, mark);
     if (n_ffts) *n_ffts = 0;
     return rc2;
   }
@@ -1365,6 +1485,7 @@ static int enqueue_step(lifu_sim* s, bool src_active, int* n_kernels, int* n_fft
 }
 
 static double bytes_model(const lifu_sim* s, bool src_active) {
+  // (steps of the steady window are counted like any other source-active step: the model is the reference algorithm's)
   // algorithmic bytes per voxel-step (DESIGN.md section 4 / SURVEY.md 8d)
   double ffts = 10, k1 = 16, k3 = 24;
   double k2 = s->homogeneous ? 36 : 48;
@@ -1422,7 +1543,9 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     return LIFU_ERR_STATE;
   }
   s->last_used_v2 = !s->sl.on && v2_eligible(s);
-  s->last_used_v3 = !s->sl.on && !s->last_used_v2 && v3_eligible(s);
+  // v3 (generic radices) is taken when asked for (LIFU_PIPELINE=v3) or, automatically, on the grids where it has been
+  // measured faster than the library-FFT pipeline (profiles/r2_v3_summary.md): LIFU_V3_AUTO=0 / 1 overrides
+  s->last_used_v3 = !s->sl.on && !s->last_used_v2 && v3_eligible(s) && (s->pipeline == 3 || v3_auto(s));
   if (s->sl.on) {
     LIFU_CHECK(slab_plans(s));
   } else if (s->last_used_v2) {
@@ -1462,16 +1585,25 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
 
   const int nt = s->grid.nt;
   const int L = s->n_src > 0 ? std::min(nt, s->max_delay + s->n_base) : 0;
-  int nk[2] = {0, 0}, nf[2] = {0, 0};
-  // capture one step with and one without the source as CUDA graphs (launch-bound at C1 sizes)
-  cudaGraphExec_t gexec[2] = {nullptr, nullptr};
+  // steady window of the source (v2 pipeline): steps [w0, w1) run the rank-2 source path
+  int w0 = 0, w1 = 0;
+  if (s->last_used_v2 && L > 0) {
+    LIFU_CHECK(v2_build_steady(s, nt));
+    if (s->Q.nws > 0) { w0 = s->Q.t0s; w1 = s->Q.t0s + s->Q.nws; }
+  }
+  auto kind_of = [&](int t) { return t >= L ? 0 : ((t >= w0 && t < w1) ? 2 : 1); };
+  int nk[3] = {0, 0, 0}, nf[3] = {0, 0, 0};
+  long long cnt[3] = {0, 0, 0};
+  for (int t = 0; t < nt; ++t) ++cnt[kind_of(t)];
+  // capture one step of every kind that occurs as a CUDA graph (launch-bound at C1 sizes)
+  cudaGraphExec_t gexec[3] = {nullptr, nullptr, nullptr};
   bool graphs = s->use_graph;
   if (graphs) {
-    for (int v = 0; v < 2 && graphs; ++v) {
-      if ((v == 0 && L == 0) || (v == 1 && L >= nt)) continue;
+    for (int v = 0; v < 3 && graphs; ++v) {
+      if (cnt[v] == 0) continue;
       cudaGraph_t g = nullptr;
       if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { graphs = false; break; }
-      int rc = enqueue_step(s, v == 0, &nk[v], &nf[v]);
+      int rc = enqueue_step(s, v, &nk[v], &nf[v]);
       cudaError_t ce = cudaStreamEndCapture(st, &g);
       if (rc != LIFU_OK || ce != cudaSuccess || g == nullptr) { graphs = false; if (g) cudaGraphDestroy(g); break; }
       ce = cudaGraphInstantiate(&gexec[v], g, 0);
@@ -1480,23 +1612,23 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     }
     if (!graphs) {
       cudaGetLastError();   // clear the sticky-free capture error and run without graphs
-      for (int v = 0; v < 2; ++v) if (gexec[v]) { cudaGraphExecDestroy(gexec[v]); gexec[v] = nullptr; }
+      for (int v = 0; v < 3; ++v) if (gexec[v]) { cudaGraphExecDestroy(gexec[v]); gexec[v] = nullptr; }
     }
   }
   LIFU_CUDA(cudaEventRecord(s->ev[1], st));
   int rc = LIFU_OK;
   for (int t = 0; t < nt && rc == LIFU_OK; ++t) {
-    const int v = t < L ? 0 : 1;
+    const int v = kind_of(t);
     if ((s->last_used_v2 || s->last_used_v3) && t == nt - 1) {   // last step also materialises the real-space pressure
       s->Q.store_p = 1; s->G.store_p = 1;
       int k1 = 0, f1 = 0;
-      rc = enqueue_step(s, v == 0, &k1, &f1);
+      rc = enqueue_step(s, v, &k1, &f1);
       s->Q.store_p = 0; s->G.store_p = 0;
       if (nk[v] == 0) { nk[v] = k1; nf[v] = f1; }
     } else if (graphs) {
       if (cudaGraphLaunch(gexec[v], st) != cudaSuccess) { set_error("cudaGraphLaunch failed at step %d: %s", t, cudaGetErrorString(cudaGetLastError())); rc = LIFU_ERR_CUDA; }
     } else {
-      rc = enqueue_step(s, v == 0, &nk[v], &nf[v]);
+      rc = enqueue_step(s, v, &nk[v], &nf[v]);
     }
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
@@ -1505,7 +1637,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   if (rc == LIFU_OK && p_max && s->Vsens) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && p_min && s->Vsens) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   cudaError_t se = cudaStreamSynchronize(st);
-  for (int v = 0; v < 2; ++v) if (gexec[v]) cudaGraphExecDestroy(gexec[v]);
+  for (int v = 0; v < 3; ++v) if (gexec[v]) cudaGraphExecDestroy(gexec[v]);
   if (rc == LIFU_ERR_CUDA && g_err.empty()) set_error("lifu_run: CUDA failure: %s", cudaGetErrorString(cudaGetLastError()));
   if (rc != LIFU_OK) return rc;
   if (se != cudaSuccess) { set_error("lifu_run: time loop failed: %s", cudaGetErrorString(se)); return LIFU_ERR_CUDA; }
@@ -1516,8 +1648,9 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   for (int a = 0; a < 3; ++a) { r.n_exp[a] = s->N[a]; r.pml[a] = s->pml[a]; }
   r.steps = nt;
   r.source_steps = L;
-  r.kernel_launches = (int64_t)L * nk[0] + (int64_t)(nt - L) * nk[1];
-  r.fft_launches = (int64_t)L * nf[0] + (int64_t)(nt - L) * nf[1];
+  r.kernel_launches = cnt[0] * nk[0] + cnt[1] * nk[1] + cnt[2] * nk[2];
+  r.fft_launches = cnt[0] * nf[0] + cnt[1] * nf[1] + cnt[2] * nf[2];
+  r.steady_source_steps = (int32_t)cnt[2];
   float ms = 0;
   cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]); r.loop_ms = ms;
   cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]); r.setup_ms = ms;
@@ -1586,7 +1719,13 @@ int lifu_profile_stages(lifu_sim* s, int reps, int with_source, int max_stages, 
   for (int r = 0; r < reps && rc == LIFU_OK; ++r) {
     if (with_source) cudaMemsetAsync(s->P.step, 0, sizeof(int), s->stream);
     s->prof_on = true; s->prof_used = 0;
-    rc = enqueue_step(s, with_source != 0 && s->n_src > 0, nullptr, nullptr);
+    // with_source: 0 no source, 1 generic source step, 2 step of the steady window (v2 pipeline after a run that had one)
+    int kind = (with_source != 0 && s->n_src > 0) ? 1 : 0;
+    if (with_source == 2 && s->last_used_v2 && s->Q.nws > 0) {
+      kind = 2;
+      cudaMemcpyAsync(s->P.step, &s->Q.t0s, sizeof(int), cudaMemcpyHostToDevice, s->stream);
+    }
+    rc = enqueue_step(s, kind, nullptr, nullptr);
     s->prof_on = false;
     if (cudaStreamSynchronize(s->stream) != cudaSuccess) { set_error("lifu_profile_stages: step failed"); rc = LIFU_ERR_CUDA; }
     if (rc != LIFU_OK) break;

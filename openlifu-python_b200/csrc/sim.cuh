@@ -108,6 +108,11 @@ struct lifu_sim {
   unsigned char tmH[128] __attribute__((aligned(64))) = {};   // CUtensorMap of H4[comp][z][ky][kx]
   unsigned char tmS[128] __attribute__((aligned(64))) = {};   // CUtensorMap of the source slab spectrum
   bool last_used_v2 = false;
+  float* d_fk = nullptr;       // steady-state source: [2][RS] filtered basis fields
+  float* d_qsrc = nullptr;     // [2][nws] time coefficients
+  float* d_qcur = nullptr;     // coefficients of the current step
+  float* d_coef = nullptr;     // [2][n_el] per-element spatial coefficients (set-up)
+  size_t qsrc_cap = 0, coef_cap = 0;
 
   // pipeline v3 (fft_gen.cuh): the fused passes for any 2/3/5/7-smooth grid
   bool v3_ready = false, last_used_v3 = false;

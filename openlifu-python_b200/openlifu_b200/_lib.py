@@ -29,7 +29,8 @@ class lifu_stats(C.Structure):
     _fields_ = [("voxels", C.c_int64), ("n_exp", C.c_int32 * 3), ("pml", C.c_int32 * 3), ("steps", C.c_int32),
                 ("source_steps", C.c_int32), ("kernel_launches", C.c_int64), ("fft_launches", C.c_int64),
                 ("loop_ms", C.c_double), ("setup_ms", C.c_double), ("bytes_per_voxel_step", C.c_double),
-                ("homogeneous", C.c_int32), ("absorbing", C.c_int32)]
+                ("homogeneous", C.c_int32), ("absorbing", C.c_int32), ("steady_source_steps", C.c_int32),
+                ("reserved", C.c_int32)]
 
     def as_dict(self):
         out = {}
@@ -126,6 +127,13 @@ def load():
         "lifu_analysis_set_focus": (C.c_int, [vp, i32, vp, vp, C.POINTER(i64)]),
         "lifu_analysis_run_focus": (C.c_int, [vp, i32, C.POINTER(lifu_focus_query), vp, C.POINTER(lifu_focus_metrics), vp]),
         "lifu_analysis_destroy": (C.c_int, [vp]),
+        "lifu_stack_create": (C.c_int, [C.c_int, vp, C.POINTER(i32), i32, C.POINTER(vp)]),
+        "lifu_stack_destroy": (C.c_int, [vp]),
+        "lifu_stack_put": (C.c_int, [vp, i32, vp]),
+        "lifu_stack_scale": (C.c_int, [vp, i32, f64]),
+        "lifu_stack_pointers": (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+        "lifu_stack_get": (C.c_int, [vp, i32, vp, vp, vp]),
+        "lifu_stack_aggregate": (C.c_int, [vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -142,7 +150,8 @@ EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_a
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_set_two_z", "lifu_get_packaged", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
             "lifu_set_medium_planes", "lifu_analysis_create", "lifu_analysis_set_focus", "lifu_analysis_run_focus",
-            "lifu_analysis_destroy"]
+            "lifu_analysis_destroy", "lifu_stack_create", "lifu_stack_destroy", "lifu_stack_put", "lifu_stack_scale",
+            "lifu_stack_pointers", "lifu_stack_get", "lifu_stack_aggregate"]
 
 
 def _check(rc):
@@ -343,6 +352,12 @@ class LifuSim:
         _check(self._lib.lifu_run(self._h, _ptr(p_max), _ptr(p_min), C.byref(st)))
         return p_max, p_min, st.as_dict()
 
+    def run_resident(self):
+        """Run the time loop and leave p_max / p_min on the device (``FieldStack.put`` / ``run_packaged`` pick them up)."""
+        st = lifu_stats()
+        _check(self._lib.lifu_run(self._h, None, None, C.byref(st)))
+        return st.as_dict()
+
     def _pinned_stage(self, nvox):
         """Two page-locked float32 buffers of nvox elements (torch is the allocator); None when torch / CUDA pinning is
         not available."""
@@ -386,13 +401,14 @@ class LifuSim:
         return out.reshape(N[2], N[1], N[0]).transpose(2, 1, 0)
 
     def profile_stages(self, reps=5, with_source=True, max_stages=32):
-        """Mean CUDA-event time per stage of one time step: list of (name, ms, bytes_per_voxel)."""
+        """Mean CUDA-event time per stage of one time step: list of (name, ms, bytes_per_voxel).
+        with_source: False / 0 no source, True / 1 source-active step, 2 step of the steady source window."""
         stride = 32
         names = C.create_string_buffer(max_stages * stride)
         ms = (C.c_double * max_stages)()
         bpv = (C.c_double * max_stages)()
         n = C.c_int()
-        _check(self._lib.lifu_profile_stages(self._h, int(reps), int(bool(with_source)), max_stages, names, stride,
+        _check(self._lib.lifu_profile_stages(self._h, int(reps), int(with_source), max_stages, names, stride,
                                              ms, bpv, C.byref(n)))
         raw = names.raw
         return [(raw[i * stride:(i + 1) * stride].split(b"\0", 1)[0].decode(), ms[i], bpv[i]) for i in range(n.value)]
@@ -486,3 +502,82 @@ class BeamAnalysis:
                 lines.append(vals[o:o + k])
                 o += k
         return m.as_dict(), lines
+
+
+class FieldStack:
+    """The fields of every focus of one plan, resident on the device (``lifu_stack_*``): device-side packaging,
+    ``Solution.scale``, aggregation over foci and the hand-over to ``BeamAnalysis`` without a host round trip.
+    Host arrays come out as (n_foci, Nx, Ny, Nz) views of x-fastest storage -- the layout ``run_simulation`` returns."""
+
+    def __init__(self, n, n_foci, device=0, stream=0):
+        self._h = C.c_void_p()
+        self._lib = load()
+        self.n = tuple(int(v) for v in n)
+        self.n_foci = int(n_foci)
+        self.device = int(device)
+        _check(self._lib.lifu_stack_create(self.device, C.c_void_p(int(stream) or None), (C.c_int32 * 3)(*self.n),
+                                           self.n_foci, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.lifu_stack_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def put(self, focus, sim: "LifuSim"):
+        """Package the last run of ``sim`` (which needs ``set_two_z``) into slot ``focus``."""
+        _check(self._lib.lifu_stack_put(self._h, int(focus), sim._h))
+
+    def scale(self, focus, s):
+        _check(self._lib.lifu_stack_scale(self._h, int(focus), float(s)))
+
+    def pointers(self, focus):
+        """(p_max, pnp, intensity) device pointers of one focus, and the element strides of (x, y, z)."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self._lib.lifu_stack_pointers(self._h, int(focus), C.byref(a), C.byref(b), C.byref(c)))
+        return (a.value, b.value, c.value), (1, self.n[0], self.n[0] * self.n[1])
+
+    def _host(self, count):
+        """Fresh host arrays for `count` foci, pages touched by all host threads before the device -> host copy."""
+        nv = int(np.prod(self.n))
+        out = [np.empty(count * nv, dtype=np.float32), np.empty(count * nv, dtype=np.float32),
+               np.empty(count * nv, dtype=np.float64)]
+        try:
+            import torch
+            for a in out:
+                torch.from_numpy(a).zero_()
+        except ImportError:
+            pass
+        return out
+
+    def _view(self, flat, count):
+        nx, ny, nz = self.n
+        a = flat.reshape(count, nz, ny, nx).transpose(0, 3, 2, 1)
+        return a[0] if count == 1 else a
+
+    def get(self, focus=None):
+        """Host copies (p_max, pnp, intensity) of one focus -- (Nx, Ny, Nz) -- or of all of them -- (F, Nx, Ny, Nz)."""
+        count = 1 if focus is not None else self.n_foci
+        pm, pn, it = self._host(count)
+        _check(self._lib.lifu_stack_get(self._h, -1 if focus is None else int(focus), _ptr(pm), _ptr(pn), _ptr(it)))
+        if focus is None:
+            nx, ny, nz = self.n
+            return tuple(a.reshape(count, nz, ny, nx).transpose(0, 3, 2, 1) for a in (pm, pn, it))
+        return tuple(self._view(a, 1) for a in (pm, pn, it))
+
+    def aggregate(self):
+        """(max over foci of p_max, max over foci of pnp, mean over foci of the intensity) as (Nx, Ny, Nz) host arrays."""
+        pm, pn, it = self._host(1)
+        _check(self._lib.lifu_stack_aggregate(self._h, _ptr(pm), _ptr(pn), _ptr(it)))
+        return tuple(self._view(a, 1) for a in (pm, pn, it))

@@ -273,13 +273,44 @@ class Protocol:
                 f.result()
         return results
 
+    def _on_device_ok(self, use_gpu, n_foci) -> bool:
+        """Can the whole plan stay on one GPU?  (stock ``run_simulation``, one process, one worker device)"""
+        if not use_gpu or run_simulation is not kwave_if.run_simulation:
+            return False
+        if _dist_world()[0] > 1:
+            return False
+        return n_foci <= 1 or _visible_devices() <= 1 or os.environ.get("LIFU_FOCI_GPUS", "") == "1"
+
+    def _simulate_foci_on_device(self, transducer, params, beams, cycles, sim_options, voltage):
+        """One simulation per focus, every result packaged by the GPU into a device-resident stack (no host copies)."""
+        from .. import _lib
+        n = [len(c) for c in params.coords.values()]
+        stack = _lib.FieldStack(n, len(beams), device=kwave_if._device())
+        try:
+            for i, (delays, apod) in enumerate(beams):
+                self.logger.info(f"Simulate focus {i} (fields stay on the device)...")
+                kwave_if.run_simulation_into(stack, i, arr=transducer, params=params, delays=delays, apod=apod,
+                                             freq=self.pulse.frequency, cycles=cycles, dt=sim_options.dt,
+                                             t_end=sim_options.t_end, cfl=sim_options.cfl,
+                                             amplitude=self.pulse.amplitude * voltage, gpu=True)
+        except Exception:
+            stack.close()
+            raise
+        return stack
+
     def calc_solution(self, target: Point, transducer: Transducer, volume=None, session=None, simulate: bool = True,
                       scale: bool = True, sim_options: sim.SimSetup | None = None,
                       analysis_options: SolutionAnalysisOptions | None = None,
                       on_pulse_mismatch: OnPulseMismatchAction = OnPulseMismatchAction.ERROR,
-                      use_gpu: bool | None = None, voltage: float = 1.0) -> Tuple[Solution, Any, SolutionAnalysis]:
+                      use_gpu: bool | None = None, voltage: float = 1.0,
+                      on_device: bool | None = None) -> Tuple[Solution, Any, SolutionAnalysis]:
         """Delays/apodizations per focus, simulated fields, scaling to the target pressure and
-        the beam analysis (reference semantics, protocol.py:242-398)."""
+        the beam analysis (reference semantics, protocol.py:242-398).
+
+        ``on_device`` (not in the reference; ``None`` -> ``$LIFU_PLAN_ON_DEVICE`` == "1"): keep the fields of every
+        focus in HBM from the solver through stacking, ``Solution.scale``, the aggregation over foci and both beam
+        analyses (``_lib.FieldStack``, csrc/stack.cu), and copy the finished stack to the host once.  Same numbers, bit
+        for bit, as the host route (tests/test_gpu_api.py); used when one GPU runs the whole plan."""
         if use_gpu is None:
             use_gpu = gpu_available()
             if not use_gpu and simulate:
@@ -302,8 +333,18 @@ class Protocol:
         for focus in foci:
             self.logger.info(f"Beamform for focus {focus}...")
             beams.append(self.beamform(arr=transducer, target=focus, params=params))
+        if on_device is None:
+            on_device = os.environ.get("LIFU_PLAN_ON_DEVICE", "0") == "1"
         stacked = xa.Dataset()
-        if simulate:
+        stack = None
+        if simulate and on_device and self._on_device_ok(use_gpu, len(foci)):
+            stack = self._simulate_foci_on_device(transducer, params, beams, simulation_cycles, sim_options, voltage)
+            # metadata-only stand-in (zero-stride arrays) until the finished stack is copied out below
+            shape = (len(foci),) + tuple(len(c) for c in params.coords.values())
+            blank = kwave_if.result_dataset(params, np.broadcast_to(np.float32(0), shape), np.broadcast_to(np.float32(0), shape),
+                                            np.broadcast_to(np.float64(0), shape), leading=("focal_point_index",))
+            stacked = blank.assign_coords(focal_point_index=np.arange(len(foci)))
+        elif simulate:
             outputs = self._simulate_foci(transducer, params, beams, simulation_cycles, sim_options, voltage, use_gpu)
             stacked = xa.concat([o.assign_coords(focal_point_index=i) for i, o in enumerate(outputs)],
                                 dim="focal_point_index")
@@ -319,21 +360,40 @@ class Protocol:
                             apodizations=np.stack([b[1] for b in beams], axis=0), pulse=self.pulse, voltage=voltage,
                             sequence=self.sequence, foci=foci, target=target, simulation_result=stacked, approved=False,
                             description=description)
-        if scale:
-            if not simulate:
-                msg = f"Cannot scale solution {solution.id} if simulation is not enabled!"
-                self.logger.error(msg=msg)
-                raise ValueError(msg)
-            self.logger.info(f"Scaling solution {solution.id}...")
-            solution.scale(self.focal_pattern, analysis_options=analysis_options)
+        if stack is not None:
+            solution._stack = stack                 # Solution.scale / analyze read and rescale the device-resident fields
+        try:
+            if scale:
+                if not simulate:
+                    msg = f"Cannot scale solution {solution.id} if simulation is not enabled!"
+                    self.logger.error(msg=msg)
+                    raise ValueError(msg)
+                self.logger.info(f"Scaling solution {solution.id}...")
+                solution.scale(self.focal_pattern, analysis_options=analysis_options)
 
-        if not simulate:
-            return solution, None, None
-        # pressures: max over foci; intensity: mean over foci (protocol.py:382-392)
-        res = solution.simulation_result
-        aggregated = deepcopy(res.drop_dims("focal_point_index"))     # every field carries the dim: copy what is left
-        aggregated["p_min"] = res["p_min"].max(dim="focal_point_index", keep_attrs=True)
-        aggregated["p_max"] = res["p_max"].max(dim="focal_point_index", keep_attrs=True)
-        aggregated["intensity"] = res["intensity"].mean(dim="focal_point_index", keep_attrs=True)
-        analysis = solution.analyze(options=analysis_options, param_constraints=self.param_constraints)
-        return solution, aggregated, analysis
+            if not simulate:
+                return solution, None, None
+            # pressures: max over foci; intensity: mean over foci (protocol.py:382-392)
+            res = solution.simulation_result
+            aggregated = deepcopy(res.drop_dims("focal_point_index"))     # every field carries the dim: copy what is left
+            if stack is not None:
+                agg_pmax, agg_pnp, agg_int = stack.aggregate()
+                for name, data in (("p_min", agg_pnp), ("p_max", agg_pmax), ("intensity", agg_int)):
+                    v = res[name]
+                    aggregated[name] = xa.DataArray(data, coords=params.coords, dims=tuple(params.dims), name=v.name,
+                                                    attrs=dict(v.attrs))
+            else:
+                aggregated["p_min"] = res["p_min"].max(dim="focal_point_index", keep_attrs=True)
+                aggregated["p_max"] = res["p_max"].max(dim="focal_point_index", keep_attrs=True)
+                aggregated["intensity"] = res["intensity"].mean(dim="focal_point_index", keep_attrs=True)
+            analysis = solution.analyze(options=analysis_options, param_constraints=self.param_constraints)
+            if stack is not None:
+                # the one device -> host copy of the plan: the finished (scaled) stack replaces the stand-in
+                pm, pn, it = stack.get()
+                full = kwave_if.result_dataset(params, pm, pn, it, leading=("focal_point_index",))
+                solution.simulation_result = full.assign_coords(focal_point_index=np.arange(len(foci)))
+            return solution, aggregated, analysis
+        finally:
+            if stack is not None:
+                solution._stack = None
+                stack.close()

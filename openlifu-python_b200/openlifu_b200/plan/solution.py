@@ -169,6 +169,8 @@ class Solution:
         kernels of liblifusim and raises if the library or a GPU is missing; ``"host"`` is the
         numpy evaluation the reference's own analysis corresponds to.  ``None``: ``$LIFU_ANALYZE`` if set, else
         "cuda" when a GPU is visible and the fields have the solver's dtypes, else "host"."""
+        if getattr(self, "_stack", None) is not None:
+            engine = "cuda"        # the fields live on the device (Protocol.calc_solution(on_device=True))
         engine = _pick_engine(engine, self.simulation_result)
         if engine == "cuda":
             # called through the class so that `analyze` can be grafted onto the reference's own Solution by name
@@ -340,9 +342,14 @@ class Solution:
         TIC = np.zeros(nf)
         to_mm = getunitconversion(units, "mm")
         global_all = np.nan
-        with _lib.BeamAnalysis(axes, nf, z_ok=z_ok, device=_device()) as ana:
+        stack = getattr(self, "_stack", None)
+        with _lib.BeamAnalysis(axes, nf, z_ok=z_ok, device=_device() if stack is None else stack.device) as ana:
             for i in range(nf):
-                ana.set_focus(i, pnp_raw[i], ipa_raw[i])
+                if stack is not None:
+                    (_, d_pnp, d_ipa), strides = stack.pointers(i)       # device -> device, no host staging
+                    ana.set_focus(i, d_pnp, d_ipa, strides=strides)
+                else:
+                    ana.set_focus(i, pnp_raw[i], ipa_raw[i])
             for i in range(nf):
                 focus = self.foci[i].get_position(units=units)
                 focus_mm = self.foci[i].get_position(units="mm")
@@ -416,11 +423,15 @@ class Solution:
         """Rescale apodizations, voltage and the stored fields in place to the target pressure."""
         analysis = self.analyze(options=analysis_options)
         apod_factors, v0, v1 = self.compute_scaling_factors(focal_pattern, analysis)
+        stack = getattr(self, "_stack", None)
         for i in range(self.num_foci()):
             s = v1 / v0 * apod_factors[i]
-            self.simulation_result["p_min"][i].data *= s
-            self.simulation_result["p_max"][i].data *= s
-            self.simulation_result["intensity"][i].data *= s ** 2
+            if stack is not None:
+                stack.scale(i, s)            # same IEEE operations on the device-resident fields (csrc/stack.cu)
+            else:
+                self.simulation_result["p_min"][i].data *= s
+                self.simulation_result["p_max"][i].data *= s
+                self.simulation_result["intensity"][i].data *= s ** 2
             self.apodizations[i] = self.apodizations[i] * apod_factors[i]
         self.voltage = v1
 

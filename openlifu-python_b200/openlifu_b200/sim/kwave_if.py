@@ -210,20 +210,10 @@ def drive_plan(arr, dt, delays, apod):
     return n_delay, np.array(gains, dtype=np.float64), (1.0 if sens is None else float(sens))
 
 
-def run_simulation(arr,
-                   params,
-                   delays: np.ndarray | None = None,
-                   apod: np.ndarray | None = None,
-                   freq: float = 1e6,
-                   cycles: float = 20,
-                   amplitude: float = 1,
-                   dt: float = 0,
-                   t_end: float = 0,
-                   cfl: float = 0.5,
-                   bli_tolerance: float = 0.05,
-                   upsampling_rate: int = 5,
-                   gpu: bool = True,
-                   ref_values_only: bool = False):
+def _setup_run(arr, params, delays, apod, freq, cycles, amplitude, dt, t_end, cfl, bli_tolerance, upsampling_rate, gpu,
+               ref_values_only):
+    """Everything of ``run_simulation`` up to the solve: grid + time axis, drive, medium, source geometry on the cached
+    solver handle.  Returns (session, kgrid dict, delay samples, slab?, world, medium_changed)."""
     if not gpu:
         raise RuntimeError("openlifu_b200.run_simulation has no CPU path (gpu=False): the solve runs on a B200 "
                            "through liblifusim.so only")
@@ -274,6 +264,41 @@ def run_simulation(arr,
         ses.geometry_key = gkey
     sim.set_drive(input_signal * base_gain, n_delay, gains,
                   source_mode=os.environ.get("LIFU_SOURCE_MODE", "additive"))
+    return ses, kg, n_delay, slab, world, medium_changed
+
+
+def _set_impedance(ses, params, medium_changed):
+    """2 * density * sound_speed of the packaging step on the device: always from the params maps (kwave_if.py:140),
+    whatever medium was used."""
+    rho, c = params["density"].data, params["sound_speed"].data
+    zkey = (_content_key(rho), _content_key(c))
+    if medium_changed or ses.two_z_key != zkey:
+        if zkey not in ses.z_uniform:
+            ses.z_uniform = {zkey: float(rho.min()) == float(rho.max()) and float(c.min()) == float(c.max())}
+        if ses.z_uniform[zkey]:
+            ses.sim.set_two_z(2 * (rho.flat[0] * c.flat[0]))
+        else:
+            ses.sim.set_two_z(_two_z_flat(params))
+        ses.two_z_key = zkey
+
+
+def run_simulation(arr,
+                   params,
+                   delays: np.ndarray | None = None,
+                   apod: np.ndarray | None = None,
+                   freq: float = 1e6,
+                   cycles: float = 20,
+                   amplitude: float = 1,
+                   dt: float = 0,
+                   t_end: float = 0,
+                   cfl: float = 0.5,
+                   bli_tolerance: float = 0.05,
+                   upsampling_rate: int = 5,
+                   gpu: bool = True,
+                   ref_values_only: bool = False):
+    ses, kg, n_delay, slab, world, medium_changed = _setup_run(arr, params, delays, apod, freq, cycles, amplitude, dt, t_end,
+                                                               cfl, bli_tolerance, upsampling_rate, gpu, ref_values_only)
+    sim = ses.sim
     log.info("Running simulation")
     # LIFU_PACKAGING=device computes -p_min and the intensity on the GPU (lifu_get_packaged, bit-identical); the default
     # stays on the host: the extra 8 bytes per voxel of device->host copy into fresh pageable memory cost more than the
@@ -287,22 +312,42 @@ def run_simulation(arr,
         output = {"p_max": p_max_flat, "p_min": p_min_flat, "stats": stats, "n_src": ses.n_src,
                   "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
         return package_fields(params, output["p_max"], output["p_min"]), output
-    # the impedance of the packaging step always comes from the params maps (kwave_if.py:140), whatever medium was used
-    rho, c = params["density"].data, params["sound_speed"].data
-    zkey = (_content_key(rho), _content_key(c))
-    if medium_changed or ses.two_z_key != zkey:
-        if zkey not in ses.z_uniform:
-            ses.z_uniform = {zkey: float(rho.min()) == float(rho.max()) and float(c.min()) == float(c.max())}
-        if ses.z_uniform[zkey]:
-            sim.set_two_z(2 * (rho.flat[0] * c.flat[0]))
-        else:
-            sim.set_two_z(_two_z_flat(params))
-        ses.two_z_key = zkey
+    _set_impedance(ses, params, medium_changed)
     p_max_flat, pnp_flat, inten_flat, stats = sim.run_packaged()
     log.info("Simulation Complete")
     output = _Output({"p_max": p_max_flat, "pnp": pnp_flat, "stats": stats, "n_src": ses.n_src,
                       "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay})
     return package_arrays(params, p_max_flat, pnp_flat, inten_flat), output
+
+
+def run_simulation_into(stack, focus: int, *, arr, params, delays=None, apod=None, freq=1e6, cycles=20, amplitude=1, dt=0,
+                        t_end=0, cfl=0.5, bli_tolerance=0.05, upsampling_rate=5, gpu=True, ref_values_only=False):
+    """``run_simulation`` whose result stays on the device: the same solve, packaged by the GPU into slot ``focus`` of a
+    ``_lib.FieldStack`` (p_max, -p_min, intensity -- the arrays of the Dataset ``run_simulation`` returns, bit for bit)
+    instead of being copied to the host.  Used by ``Protocol.calc_solution(on_device=True)``; returns the solver stats."""
+    ses, kg, n_delay, slab, world, medium_changed = _setup_run(arr, params, delays, apod, freq, cycles, amplitude, dt, t_end,
+                                                               cfl, bli_tolerance, upsampling_rate, gpu, ref_values_only)
+    if slab:
+        raise RuntimeError("run_simulation_into: not available for slab-decomposed solves")
+    if stack.device != _device():
+        raise ValueError(f"run_simulation_into: the stack lives on device {stack.device}, the solver on {_device()}")
+    _set_impedance(ses, params, medium_changed)
+    log.info("Running simulation")
+    stats = ses.sim.run_resident()                      # no host copy of the raw sensor vectors
+    stack.put(focus, ses.sim)
+    log.info("Simulation Complete")
+    return {"stats": stats, "n_src": ses.n_src, "Nt": kg["Nt"], "dt": kg["dt"], "delay_samples": n_delay}
+
+
+def result_dataset(params, p_max, pnp, intensity, leading=()):
+    """The Dataset of kwave_if.py:131-146 from arrays already in their final form; ``leading``: extra leading dims
+    (e.g. ("focal_point_index",) for a stack of foci)."""
+    dims = tuple(leading) + tuple(params.dims)
+    return xa.Dataset({
+        "p_max": xa.DataArray(p_max, coords=params.coords, dims=dims, name="p_max", attrs={"units": "Pa", "long_name": "PPP"}),
+        "p_min": xa.DataArray(pnp, coords=params.coords, dims=dims, name="p_min", attrs={"units": "Pa", "long_name": "PNP"}),
+        "intensity": xa.DataArray(intensity, coords=params.coords, dims=dims, name="I",
+                                  attrs={"units": "W/cm^2", "long_name": "Intensity"})})
 
 
 class _Output(dict):

@@ -132,3 +132,110 @@ def test_calc_solution_wheel_on_gpu(lifu_lib):
     r = sol.simulation_result
     assert np.array_equal(agg["p_min"].data, np.max(r["p_min"].data, axis=0))
     np.testing.assert_allclose(agg["intensity"].data, np.mean(r["intensity"].data, axis=0), rtol=1e-12)
+
+
+def _wheel_protocol(heterogeneous=False):
+    from openlifu_b200.bf import Pulse, Sequence, focal_patterns
+    from openlifu_b200.geo import Point
+    from openlifu_b200.plan import Protocol, SolutionAnalysisOptions
+    from openlifu_b200.sim import SimSetup
+    from openlifu_b200.xdc import Transducer
+    arr = Transducer.gen_matrix_array(nx=4, ny=4, pitch=3, kerf=0.5, units="mm", sensitivity=1e5)
+    setup = SimSetup(spacing=1.0, x_extent=(-15, 15), y_extent=(-15, 15), z_extent=(-3, 36), dt=2.5e-7, t_end=110 * 2.5e-7)
+    pattern = focal_patterns.Wheel(center=True, num_spokes=3, spoke_radius=3, distance_units="mm", target_pressure=0.3, units="MPa")
+    pr = Protocol(pulse=Pulse(frequency=400e3, duration=3 / 400e3), sequence=Sequence(pulse_interval=0.01, pulse_count=4, pulse_train_interval=0),
+                  focal_pattern=pattern, sim_setup=setup)
+    target = Point(position=np.array([0.0, 0.0, 22.0]), units="mm", id="tgt")
+    opts = SolutionAnalysisOptions(mainlobe_radius=2.5, beamwidth_radius=5.0, sidelobe_radius=3.0, sidelobe_zmin=1.0, distance_units="mm")
+    volume = None
+    if heterogeneous:
+        from openlifu_b200 import configs
+        pr.seg_method = configs.seg_methods.LabelVolume(materials=dict(configs.PHANTOM_MATERIALS), ref_material="water")
+        volume = configs.skull_phantom_labels(setup.get_coords(), centre_mm=(0.0, 0.0, 40.0), r_in=24.0, r_out=28.0)
+    return pr, arr, target, opts, volume
+
+
+@pytest.mark.parametrize("heterogeneous", [False, True])
+def test_plan_on_device_is_the_host_plan_bit_for_bit(lifu_lib, heterogeneous):
+    """Protocol.calc_solution(on_device=True) keeps every focus' fields in HBM from the solver through
+    stacking, Solution.scale, the aggregation over foci and both analyses (csrc/stack.cu) and copies the finished stack
+    out once.  Every array and every metric equals the host route exactly."""
+    pr, arr, target, opts, volume = _wheel_protocol(heterogeneous)
+    sol_h, agg_h, ana_h = pr.calc_solution(target, arr, volume=volume, simulate=True, scale=True, analysis_options=opts,
+                                           use_gpu=True, on_device=False)
+    sol_d, agg_d, ana_d = pr.calc_solution(target, arr, volume=volume, simulate=True, scale=True, analysis_options=opts,
+                                           use_gpu=True, on_device=True)
+    assert getattr(sol_d, "_stack", None) is None                      # released
+    rh, rd = sol_h.simulation_result, sol_d.simulation_result
+    assert tuple(rd["p_min"].dims) == tuple(rh["p_min"].dims) == ("focal_point_index", "x", "y", "z")
+    assert list(rd.coords) == list(rh.coords)
+    for k in ("p_max", "p_min", "intensity"):
+        assert rd[k].data.dtype == rh[k].data.dtype and rd[k].data.shape == rh[k].data.shape
+        assert rd[k].attrs == rh[k].attrs and rd[k].name == rh[k].name
+        assert np.array_equal(rd[k].data, rh[k].data), k
+        assert agg_d[k].data.dtype == agg_h[k].data.dtype and np.array_equal(agg_d[k].data, agg_h[k].data), "aggregated " + k
+        assert agg_d[k].attrs == agg_h[k].attrs
+    assert sol_d.voltage == sol_h.voltage and np.array_equal(sol_d.apodizations, sol_h.apodizations)
+    for k, v in ana_h.__dict__.items():
+        if k == "param_constraints" or v is None:
+            continue
+        assert np.array_equal(np.asarray(getattr(ana_d, k), dtype=float), np.asarray(v, dtype=float), equal_nan=True), k
+    # the returned arrays are ordinary writable numpy arrays (Solution.scale can be applied again, in place, on the host)
+    rd["p_min"][1].data *= 2.0
+    assert rd["p_min"].data[1].max() == 2.0 * rh["p_min"].data[1].max()
+    # unscaled route too
+    sol_u, _, _ = pr.calc_solution(target, arr, volume=volume, simulate=True, scale=False, analysis_options=opts,
+                                   use_gpu=True, on_device=True)
+    sol_v, _, _ = pr.calc_solution(target, arr, volume=volume, simulate=True, scale=False, analysis_options=opts,
+                                   use_gpu=True, on_device=False)
+    for k in ("p_max", "p_min", "intensity"):
+        assert np.array_equal(sol_u.simulation_result[k].data, sol_v.simulation_result[k].data), k
+
+
+def test_field_stack_errors_and_numpy_semantics(lifu_lib):
+    """lifu_stack_*: argument / state errors, and the scaling and aggregation arithmetic against numpy on the same data."""
+    from openlifu_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.FieldStack([0, 4, 4], 2)
+    case = cases.small_water_case()
+    N, d, Nt, dt = osc.time_axis(cases.scene_of(case), case["dt"], case["t_end"], 0.5)
+    offset = np.array([-float(np.mean(c)) * 1e-3 for c in case["coords"]])
+    base = 1e5 * np.sin(2 * np.pi * case["freq"] * np.arange(0, case["cycles"] / case["freq"], dt))
+    with _lib.LifuSim(N, d, dt, Nt) as sim, _lib.FieldStack(N, 3) as st:
+        sim.set_medium(1500.0, 1000.0, 0.0)
+        sim.set_elements(case["pos_m"] + offset, case["size_m"], case["angles_deg"], 0.05, 5)
+        with pytest.raises(_lib.LifuError, match="lifu_run first"):
+            st.put(0, sim)
+        host = []
+        for f, g in enumerate(([1, 1, 1, 1], [1, 0.5, 0.2, 0], [0.3, 1, 1, 0.7])):
+            sim.set_drive(base, [0, 1, 2, 3], g)
+            p_max, p_min, _ = sim.run()
+            if f == 0:
+                with pytest.raises(_lib.LifuError, match="lifu_set_two_z"):
+                    st.put(f, sim)
+                sim.set_two_z(2 * 1000.0 * 1500.0)
+            st.put(f, sim)
+            pm = p_max.reshape(N, order="F")
+            pn = (-1 * p_min).reshape(N, order="F")
+            it = ((np.float32(1e-4) * p_min ** 2) / (2 * 1000.0 * 1500.0)).reshape(N, order="F")
+            host.append([pm.copy(), pn.copy(), it.copy()])
+            if f < 2:
+                with pytest.raises(_lib.LifuError, match="no fields yet"):
+                    st.aggregate()
+        for f in range(3):
+            got = st.get(f)
+            for a, b in zip(got, host[f]):
+                assert a.dtype == b.dtype and np.array_equal(a, b)
+        s = np.float64(1.7320508075688772) / 3.0 * np.float64(1.1)
+        st.scale(1, s)
+        host[1][0] *= s
+        host[1][1] *= s
+        host[1][2] *= s ** 2
+        pm, pn, it = st.get()
+        for k, arr in enumerate((pm, pn, it)):
+            want = np.stack([h[k] for h in host])
+            assert arr.shape == want.shape and np.array_equal(arr, want), k
+        a_pm, a_pn, a_it = st.aggregate()
+        assert np.array_equal(a_pm, np.max(np.stack([h[0] for h in host]), axis=0))
+        assert np.array_equal(a_pn, np.max(np.stack([h[1] for h in host]), axis=0))
+        assert np.array_equal(a_it, np.mean(np.stack([h[2] for h in host]), axis=0))

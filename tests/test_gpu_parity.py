@@ -437,3 +437,71 @@ def test_edge_cases_clipped_elements_long_drive_silent_array(lifu_lib):
     silent = dict(cases.small_water_case(), apod=np.zeros(4))
     g0 = cases.run_cuda_case(silent)
     assert not g0["p_max"].any() and not g0["p_min"].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# steady-state source of the fused pipeline: while every element is inside its burst the delayed drive signals have
+# rank <= 2 in time, and the k-space source filter is applied once to two spatial basis fields (lifusim.cu: v2_build_steady)
+def _steady_case(steps=140):
+    case = cases.make_case([(-20, 19), (-22, 21), (-3, 32)], 1.0, 3, 3, 4.0, 0.5, (3, -2, 18), 400e3, 10,
+                           dt=3e-7, t_end=steps * 3e-7, name="v2_steady")
+    case["apod"] = np.linspace(0.4, 1.0, 9)
+    return case
+
+
+def test_v2_steady_source_matches_generic_path_and_oracle(lifu_lib, monkeypatch):
+    case = _steady_case()
+    want = cases.run_oracle_case(case)
+    assert tuple(want["N_exp"]) == (64, 64, 64) and np.ptp(want["n_delay"]) >= 2       # several distinct delays
+    monkeypatch.setenv("LIFU_SOURCE_STEADY", "1")
+    on = cases.run_cuda_case(case)
+    monkeypatch.setenv("LIFU_SOURCE_STEADY", "0")
+    off = cases.run_cuda_case(case)
+    monkeypatch.delenv("LIFU_SOURCE_STEADY")
+    assert _is_v2(on) and _is_v2(off)
+    n_base = int(np.ceil(10 / 400e3 / 3e-7))
+    expect = int(want["n_delay"].min()) + n_base - int(want["n_delay"].max())
+    assert on["stats"]["steady_source_steps"] == expect > 24 and off["stats"]["steady_source_steps"] == 0
+    assert on["stats"]["kernel_launches"] < off["stats"]["kernel_launches"]
+    _check_fields(on, want)
+    _check_fields(off, want)
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(on[k], off[k]) < 3e-6, k
+
+
+@pytest.mark.parametrize("medium", ["heterogeneous", "absorbing"])
+def test_v2_steady_source_other_media(lifu_lib, medium):
+    case = _steady_case(steps=110)
+    c0, rho0, al = _phantom(tuple(case["N"]))
+    case["c0"], case["rho0"], case["alpha"] = c0, rho0, (al if medium == "absorbing" else 0.0)
+    case["dt"], case["t_end"] = 1.5e-7, 150 * 1.5e-7
+    want = cases.run_oracle_case(case)
+    got = cases.run_cuda_case(case)
+    assert _is_v2(got) and got["stats"]["steady_source_steps"] > 24 and got["stats"]["homogeneous"] == 0
+    _check_fields(got, want)
+
+
+def test_v2_steady_source_needs_a_rank_two_drive(lifu_lib):
+    """A drive that is not a sinusoidal burst (random samples) on three distinct delays: the rank test rejects it and every
+    source step takes the generic path; a chirp likewise.  A constant-frequency burst of any phase is accepted, and so is
+    ANY waveform when the array has only two distinct delays (two shifted copies always span a rank-2 space)."""
+    from openlifu_b200 import _lib
+    rng = np.random.default_rng(5)
+    n_base = 90
+    t = np.arange(n_base)
+    drives = {"random": rng.standard_normal(n_base), "chirp": np.sin(0.02 * t * t),
+              "tone": np.cos(0.31 * t + 0.4)}
+    got = {}
+    for name, base in drives.items():
+        with _lib.LifuSim([44, 44, 44], [1e-3] * 3, 3e-7, 130, pml=(10, 10, 10)) as sim:
+            sim.set_medium(1500.0, 1000.0, 0.0)
+            idx = np.array([22 + 44 * (20 + 44 * 5), 23 + 44 * (24 + 44 * 6), 20 + 44 * (21 + 44 * 7)], dtype=np.int64)
+            sim.set_source_geometry(idx, [0, 1, 2, 3], [0, 1, 2], [1.0, 0.7, 0.9], 3)
+            sim.set_drive(base, [0, 3, 5], [1.0, 1.0, 0.5])
+            _, _, st = sim.run()
+            assert st["fft_launches"] == 0
+            got[name] = st["steady_source_steps"]
+            if name == "random":
+                sim.set_drive(base, [0, 5, 5], [1.0, 1.0, 0.5])
+                got["random, two delays"] = sim.run()[2]["steady_source_steps"]
+    assert got["random"] == 0 and got["chirp"] == 0 and got["tone"] == n_base - 5 and got["random, two delays"] == n_base - 5

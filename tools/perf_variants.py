@@ -50,10 +50,13 @@ for var in variants:
     rec = {"variant": var or "default", "workload": wl, "steps": st["steps"], "source_steps": st["source_steps"],
            "loop_ms": best, "ms_per_step": best / st["steps"], "checksum": float(np.abs(pm).sum(dtype=np.float64)),
            "fft_launches": st["fft_launches"]}
-    for ws in (1, 0):
-        prof = sim.profile_stages(reps=5, with_source=bool(ws))
-        rec["stages_src" if ws else "stages_nosrc"] = {n: round(ms, 4) for n, ms, b in prof}
-        rec["step_src_ms" if ws else "step_nosrc_ms"] = round(sum(ms for _, ms, _ in prof), 4)
+    rec["steady_source_steps"] = st.get("steady_source_steps", 0)
+    for ws, tag in ((1, "src"), (0, "nosrc"), (2, "steady")):
+        if ws == 2 and not rec["steady_source_steps"]:
+            continue
+        prof = sim.profile_stages(reps=5, with_source=ws)
+        rec["stages_" + tag] = {n: round(ms, 4) for n, ms, b in prof}
+        rec["step_%s_ms" % tag] = round(sum(ms for _, ms, _ in prof), 4)
     sim.close()
     for k in env:
         os.environ.pop(k, None)

@@ -15,9 +15,9 @@ for pipe in (sys.argv[3:] or ["auto"]):
         os.environ.pop("LIFU_PIPELINE", None)
     else:
         os.environ["LIFU_PIPELINE"] = pipe
-    r = bench.single_measure(0, n, ts, steps=2, warmup=1)
+    r = bench.single_measure(0, n, ts, steps=2, warmup=1, profile=True)
     rec = {"pipeline": pipe, "n_inner": n, "time_steps": ts, "Mvox_step_per_s": r["value"], "ms_per_time_step": r["ms_per_time_step"],
-           "fft_launches": r["fft_launches"]}
+           "fft_launches": r["fft_launches"], "stages": r["stages"]}
     if ref is None:
         ref = r
     else:
