@@ -117,6 +117,15 @@ int lifu_set_medium(lifu_sim* sim, const float* c0, const float* rho0, const flo
 int lifu_set_medium_f64(lifu_sim* sim, const double* c0, const double* rho0, const double* alpha_db,
                         const int64_t stride[3], float alpha_power, int alpha_mode);
 
+/* Heterogeneous medium from a LABEL volume and per-label tables: what SegmentationMethod._map_params
+ * (seg/seg_method.py:84-97) expands on the host into three float64 maps, expanded on the device instead -- one byte
+ * per voxel is uploaded.  labels: uint8, inner grid, element strides of (x, y, z) (dense); tables: n_labels <= 32
+ * float64 entries, rounded to float32 (data_cast='single'); labels >= n_labels give 0 like the reference's initial
+ * value (and are then rejected: the sound speed must be positive).  alpha_db may be NULL.  Not for slab handles. */
+int lifu_set_medium_labels(lifu_sim* sim, const uint8_t* labels, const int64_t stride[3], int32_t n_labels,
+                           const double* c0, const double* rho0, const double* alpha_db, float alpha_power,
+                           int alpha_mode);
+
 /* Replaces get_karray + get_array_binary_mask + the weight half of
  * get_distributed_source_signal (kwave_if.py:29-47,75-77): off-grid rectangular elements
  * spread with the truncated-sinc band-limited interpolant, computed on the GPU.

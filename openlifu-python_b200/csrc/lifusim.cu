@@ -457,8 +457,9 @@ int lifu_destroy(lifu_sim* s) {
 // stride64 != NULL: the maps are float64 arrays of the whole inner grid with those element strides (x, y, z).
 static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,
                            float alpha_power, int alpha_mode, int homogeneous, int plane0, int n_planes,
-                           const int64_t* stride64 = nullptr) {
-  if (!s || !c0 || !rho0) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
+                           const int64_t* stride64 = nullptr, const unsigned char* labels = nullptr,
+                           const MediumLut* lut = nullptr) {
+  if (!s || (!labels && (!c0 || !rho0))) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
   if (alpha_mode < 0 || alpha_mode > 2) { set_error("lifu_set_medium: alpha_mode %d unknown", alpha_mode); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = s->stream;
@@ -518,7 +519,13 @@ static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, cons
     const int gb = grid_blocks(s, s->Vloc, 256);
     const float* src[3] = {c0, rho0, alpha_db};
     float* dst[3] = {s->d_c0e, s->d_rho0e, s->d_alphae};
-    for (int m = 0; m < 3; ++m) {
+    if (labels) {
+      // label volume (one byte per voxel, the caller's layout) + per-label tables: expanded maps in one pass
+      LIFU_CUDA(cudaMemcpyAsync(stage, labels, (size_t)s->Vin, cudaMemcpyDefault, st));
+      k_expand_edge_lut<<<gbe, 256, 0, st>>>(reinterpret_cast<const unsigned char*>(stage), dst[0], dst[1], dst[2], P, n_exp,
+                                             stride64[0], stride64[1], stride64[2], *lut);
+    }
+    for (int m = 0; m < 3 && !labels; ++m) {
       if (src[m] && stride64) {
         // float64 maps in the caller's layout: one block copy, conversion + re-layout on the device
         LIFU_CUDA(cudaMemcpyAsync(stage, src[m], sizeof(double) * (size_t)s->Vin, cudaMemcpyDefault, st));
@@ -588,6 +595,34 @@ int lifu_set_medium_f64(lifu_sim* s, const double* c0, const double* rho0, const
   if (sizeof(double) * (size_t)s->Vin > sizeof(float) * 3 * (size_t)s->RS) { set_error("lifu_set_medium_f64: staging area too small"); return LIFU_ERR_NOMEM; }
   return set_medium_impl(s, reinterpret_cast<const float*>(c0), reinterpret_cast<const float*>(rho0),
                          reinterpret_cast<const float*>(alpha_db), alpha_power, alpha_mode, 0, 0, s->n[2], stride);
+}
+
+int lifu_set_medium_labels(lifu_sim* s, const uint8_t* labels, const int64_t stride[3], int32_t n_labels,
+                           const double* c0, const double* rho0, const double* alpha_db, float alpha_power, int alpha_mode) {
+  if (!s || !labels || !stride || !c0 || !rho0 || n_labels <= 0 || n_labels > 32) {
+    set_error("lifu_set_medium_labels: bad argument (1 to 32 labels)");
+    return LIFU_ERR_INVALID;
+  }
+  if (s->sl.on) { set_error("lifu_set_medium_labels: not available on a slab handle"); return LIFU_ERR_STATE; }
+  int order[3] = {0, 1, 2};
+  std::sort(order, order + 3, [&](int a, int b) { return stride[a] < stride[b] || (stride[a] == stride[b] && s->n[a] < s->n[b]); });
+  int64_t expect = 1;
+  for (int k = 0; k < 3; ++k) {
+    if (s->n[order[k]] > 1 && stride[order[k]] != expect) {
+      set_error("lifu_set_medium_labels: strides (%lld, %lld, %lld) do not describe a dense (%d, %d, %d) array",
+                (long long)stride[0], (long long)stride[1], (long long)stride[2], s->n[0], s->n[1], s->n[2]);
+      return LIFU_ERR_INVALID;
+    }
+    expect *= s->n[order[k]];
+  }
+  MediumLut lut;
+  lut.n = n_labels;
+  for (int i = 0; i < 32; ++i) {
+    lut.c0[i] = i < n_labels ? (float)c0[i] : 0.f;               // data_cast='single'
+    lut.rho0[i] = i < n_labels ? (float)rho0[i] : 0.f;
+    lut.alpha[i] = (i < n_labels && alpha_db) ? (float)alpha_db[i] : 0.f;
+  }
+  return set_medium_impl(s, nullptr, nullptr, nullptr, alpha_power, alpha_mode, 0, 0, s->n[2], stride, labels, &lut);
 }
 
 int lifu_set_medium_planes(lifu_sim* s, const float* c0, const float* rho0, const float* alpha_db,

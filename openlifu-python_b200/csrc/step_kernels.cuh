@@ -347,6 +347,31 @@ __global__ void k_expand_edge(const T* __restrict__ in, float* __restrict__ out,
   }
 }
 
+// The same expansion from a LABEL volume and per-label tables (SegmentationMethod._map_params, seg_method.py:84-97, done
+// on the device: one byte per voxel crosses PCIe instead of three float64 maps).  Labels outside the table give 0,
+// the reference's initial value.
+struct MediumLut { int n; float c0[32], rho0[32], alpha[32]; };
+__global__ void k_expand_edge_lut(const unsigned char* __restrict__ lab, float* __restrict__ c0e, float* __restrict__ rho0e,
+                                  float* __restrict__ alphae, StepParams P, int n_planes, long long sx, long long sy,
+                                  long long sz, MediumLut lut) {
+  const long long n = (long long)P.Nx * P.Ny * n_planes;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    int ix = (int)(i % P.Nx);
+    long long t = i / P.Nx;
+    int iy = (int)(t % P.Ny);
+    int iz = min((int)(t / P.Ny) + P.z0, P.NzG - 1);
+    int jx = min(max(ix - P.px, 0), P.nx - 1);
+    int jy = min(max(iy - P.py, 0), P.ny - 1);
+    int jz = min(max(iz - P.pz, 0), P.nz - 1);
+    const int l = lab[jz * sz + jy * sy + jx * sx];
+    const bool ok = l < lut.n;
+    c0e[i] = ok ? lut.c0[l] : 0.f;
+    rho0e[i] = ok ? lut.rho0[l] : 0.f;
+    alphae[i] = ok ? lut.alpha[l] : 0.f;
+  }
+}
+
 // Packaging of kwave_if.py:136-141 on the device: p_min -> -p_min (float32) and
 // intensity = 1e-4 * p_min^2 / (2 Z) with the float32 square and scale and the float64 divide of the numpy expression.
 __global__ void k_package(const float* __restrict__ pmin, const double* __restrict__ two_z, double two_z_s,

@@ -107,6 +107,7 @@ def load():
         "lifu_destroy": (C.c_int, [vp]),
         "lifu_set_medium": (C.c_int, [vp, vp, vp, vp, C.c_float, C.c_int, C.c_int]),
         "lifu_set_medium_f64": (C.c_int, [vp, vp, vp, vp, C.POINTER(i64), C.c_float, C.c_int]),
+        "lifu_set_medium_labels": (C.c_int, [vp, vp, C.POINTER(i64), i32, vp, vp, vp, C.c_float, C.c_int]),
         "lifu_set_elements": (C.c_int, [vp, i32, vp, vp, vp, f64, i32, C.POINTER(i64)]),
         "lifu_set_source_geometry": (C.c_int, [vp, vp, vp, vp, vp, i64, i64, i32]),
         "lifu_get_source_sizes": (C.c_int, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]),
@@ -146,7 +147,7 @@ def load():
 
 
 EXPORTED = ["lifu_abi_version", "lifu_last_error", "lifu_make_time", "lifu_pml_auto", "lifu_device_count", "lifu_create", "lifu_destroy",
-            "lifu_set_medium", "lifu_set_medium_f64", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
+            "lifu_set_medium", "lifu_set_medium_f64", "lifu_set_medium_labels", "lifu_set_elements", "lifu_set_source_geometry", "lifu_get_source_sizes",
             "lifu_get_source_geometry", "lifu_set_drive", "lifu_run", "lifu_set_two_z", "lifu_get_packaged", "lifu_get_field", "lifu_get_info",
             "lifu_profile_stages", "lifu_slab_unique_id", "lifu_create_slab", "lifu_slab_layout_of",
             "lifu_set_medium_planes", "lifu_analysis_create", "lifu_analysis_set_focus", "lifu_analysis_run_focus",
@@ -291,6 +292,25 @@ class LifuSim:
         else:
             _check(self._lib.lifu_set_medium_planes(self._h, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]), alpha_power,
                                                     mode, 0, int(plane0), int(shape[2])))
+
+    def set_medium_labels(self, labels, c0, rho0, alpha_db=None, alpha_power=0.9, alpha_mode="binary"):
+        """Medium from a label volume (integer array of shape (Nx, Ny, Nz), any dense layout, values < 32) and per-label
+        tables: the maps are expanded on the device (``lifu_set_medium_labels``)."""
+        mode = ALPHA_MODES[alpha_mode] if isinstance(alpha_mode, str) else int(alpha_mode)
+        lab = np.asarray(labels)
+        if lab.shape != self.n:
+            raise ValueError(f"labels must have shape {self.n}")
+        if lab.dtype != np.uint8:
+            if lab.size and (lab.min() < 0 or lab.max() > 255):
+                raise ValueError("labels must lie in [0, 255]")
+            lab = lab.astype(np.uint8)
+        if not (lab.flags.c_contiguous or lab.flags.f_contiguous):
+            lab = np.ascontiguousarray(lab)
+        t = [np.ascontiguousarray(v, dtype=np.float64).reshape(-1) for v in (c0, rho0)]
+        ta = None if alpha_db is None else np.ascontiguousarray(alpha_db, dtype=np.float64).reshape(-1)
+        st = (C.c_int64 * 3)(*[int(v) for v in lab.strides])
+        _check(self._lib.lifu_set_medium_labels(self._h, _ptr(lab), st, t[0].size, _ptr(t[0]), _ptr(t[1]), _ptr(ta),
+                                                alpha_power, mode))
 
     # ------------------------------------------------------------------ source geometry
     def set_elements(self, pos_m, size_m, angle_deg, bli_tolerance=0.05, upsampling_rate=5):

@@ -110,6 +110,15 @@ def _gather_foci(mine: Dict[int, Any], n_foci: int, world: int, coords) -> list:
     return out
 
 
+def candidate_transducer(transducer: Transducer, transform) -> Transducer:
+    """The transducer placed at one candidate pose the way the reference does it: a ``TransformedTransducer`` carrying
+    the 4x4 ``transform``, baked into element positions / orientations (``xdc/transducer.py:412-417``)."""
+    from dataclasses import fields as dc_fields
+    from ..xdc.transducer import TransformedTransducer
+    kw = {f.name: deepcopy(getattr(transducer, f.name)) for f in dc_fields(Transducer)}
+    return TransformedTransducer(transform=np.asarray(transform, dtype=np.float64), **kw).bake()
+
+
 @dataclass
 class Protocol:
     id: str = "protocol"
@@ -242,9 +251,15 @@ class Protocol:
     def _simulate_foci(self, transducer, params, beams, cycles, sim_options, voltage, use_gpu):
         """Run one simulation per focus.  Serial unless several GPUs are visible and the stock
         ``run_simulation`` is in place; then focus i runs on device i mod G."""
+        return self._simulate_jobs([(transducer, d, a) for d, a in beams], params, cycles, sim_options, voltage, use_gpu)
+
+    def _simulate_jobs(self, jobs, params, cycles, sim_options, voltage, use_gpu):
+        """One simulation per job = (transducer, delays, apodization): the independent units of a sweep (foci of a
+        pattern, candidate poses of a virtual fit).  Job i runs on rank i mod world of a torch.distributed job, or on
+        device i mod G of this process; no data-path collective."""
         def one(i):
-            delays, apod = beams[i]
-            ds, _ = run_simulation(arr=transducer, params=params, delays=delays, apod=apod, freq=self.pulse.frequency,
+            arr, delays, apod = jobs[i]
+            ds, _ = run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=self.pulse.frequency,
                                    cycles=cycles, dt=sim_options.dt, t_end=sim_options.t_end, cfl=sim_options.cfl,
                                    amplitude=self.pulse.amplitude * voltage, gpu=use_gpu)
             return ds
@@ -252,25 +267,69 @@ class Protocol:
         world, rank = _dist_world()
         if world > 1 and kwave_if.multi_gpu_mode()[0] == "slab":
             world = 1                   # the ranks share every simulation (slab decomposition): same loop on all of them
-        if world > 1 and len(beams) > 1:
-            # one process per GPU (torchrun): rank r simulates foci r, r + world, ...; the fields are
+        if world > 1 and len(jobs) > 1:
+            # one process per GPU (torchrun): rank r simulates jobs r, r + world, ...; the fields are
             # all-gathered so that every rank holds the full stack, as the reference's serial loop would
-            mine = {i: one(i) for i in range(rank, len(beams), world)}
-            return _gather_foci(mine, len(beams), world, params.coords)
-        n_dev = _visible_devices() if (use_gpu and run_simulation is kwave_if.run_simulation and len(beams) > 1) else 1
+            mine = {i: one(i) for i in range(rank, len(jobs), world)}
+            return _gather_foci(mine, len(jobs), world, params.coords)
+        n_dev = _visible_devices() if (use_gpu and run_simulation is kwave_if.run_simulation and len(jobs) > 1) else 1
         if n_dev <= 1:
-            return [one(i) for i in range(len(beams))]
-        results: list = [None] * len(beams)
+            return [one(i) for i in range(len(jobs))]
+        results: list = [None] * len(jobs)
 
         def worker(dev):
             with kwave_if.use_device(dev):
-                for i in range(dev, len(beams), n_dev):
-                    self.logger.info(f"Simulate focus {i} on GPU {dev}...")
+                for i in range(dev, len(jobs), n_dev):
+                    self.logger.info(f"Simulate job {i} on GPU {dev}...")
                     results[i] = one(i)
 
         with ThreadPoolExecutor(max_workers=n_dev) as pool:
             for f in [pool.submit(worker, d) for d in range(n_dev)]:
                 f.result()
+        return results
+
+    def simulate_candidates(self, target: Point, transducer: Transducer, transforms, volume=None,
+                            sim_options: sim.SimSetup | None = None,
+                            analysis_options: SolutionAnalysisOptions | None = None, use_gpu: bool | None = None,
+                            voltage: float = 1.0, analyze: bool = True):
+        """Simulate a batch of candidate transducer poses for ONE target.
+
+        The reference's virtual fit (``virtual_fit.py:230-467``) returns its best ``top_n_candidates`` poses as 4x4
+        transforms and stops there -- it never simulates them.  Here every candidate is placed with the reference's own
+        mechanism, ``TransformedTransducer(transform=M).bake()`` (``xdc/transducer.py:412-417``: elements mapped by
+        ``inv(M)``, ``transducer.py:297-301``), beamformed onto the target and simulated on the protocol's grid; the
+        candidates are independent simulations and are sharded exactly like the foci of a pattern (candidate i -> rank /
+        device i mod G).  The off-grid source weights are rebuilt on the GPU per pose (10 ms on the 256^3 grid); medium,
+        solver handle and FFT tables are shared by all candidates.
+
+        Returns a list with one ``(Solution, SolutionAnalysis | None)`` per transform, in input order; every Solution holds
+        its baked transducer, the delays / apodizations and a one-focus ``simulation_result``."""
+        if use_gpu is None:
+            use_gpu = gpu_available()
+            if not use_gpu:
+                raise RuntimeError("Protocol.simulate_candidates: no B200-class CUDA device was found and openlifu_b200 has "
+                                   "no CPU simulation path")
+        sim_options = self.sim_setup if sim_options is None else sim_options
+        analysis_options = self.analysis_options if analysis_options is None else analysis_options
+        self.check_target(target)
+        params = sim_options.setup_sim_scene(self.seg_method, volume=volume)
+        cycles = np.min([np.round(self.pulse.duration * self.pulse.frequency), 20])
+        arrays = [candidate_transducer(transducer, m) for m in transforms]
+        jobs = []
+        for arr in arrays:
+            delays, apod = self.beamform(arr=arr, target=target, params=params)
+            jobs.append((arr, delays, apod))
+        outputs = self._simulate_jobs(jobs, params, cycles, sim_options, voltage, use_gpu)
+        results = []
+        for i, (ds, (arr, delays, apod)) in enumerate(zip(outputs, jobs)):
+            stacked = xa.concat([ds.assign_coords(focal_point_index=0)], dim="focal_point_index")
+            stamp = datetime.now().strftime("%Y%m%d_%H%M%S_%f")
+            sol = Solution(id=f"candidate_{i}_{stamp}", name=f"Candidate {i}", protocol_id=self.id, transducer=arr,
+                           delays=np.stack([delays], axis=0), apodizations=np.stack([apod], axis=0), pulse=self.pulse,
+                           voltage=voltage, sequence=self.sequence, foci=[target], target=target, simulation_result=stacked,
+                           approved=False, description=f"Candidate pose {i} of {len(jobs)} for target {target.id}")
+            ana = sol.analyze(options=analysis_options, param_constraints=self.param_constraints) if analyze else None
+            results.append((sol, ana))
         return results
 
     def _on_device_ok(self, use_gpu, n_foci) -> bool:

@@ -99,6 +99,15 @@ class SegmentationMethod(ABC):
                                        attrs={"units": info["units"], "long_name": info["name"],
                                               "ref_value": ref.get_param(pid)})
         params.attrs["ref_material"] = ref
+        if not uniform and n_mat <= 32 and bool(valid.all()):
+            # provenance for the solver adapter: while the three acoustic maps still hold what was expanded here
+            # (content keys), run_simulation uploads the label volume + tables instead of the maps (lifu_set_medium_labels)
+            from ..util.content import content_key
+            solver_ids = ("sound_speed", "density", "attenuation")
+            params.attrs["lifu_label_medium"] = {
+                "labels": labels.astype(np.uint8),
+                "lut": {pid: np.array([getattr(m, pid) for m in materials.values()], dtype=np.float64) for pid in solver_ids},
+                "keys": tuple(content_key(params[pid].data) for pid in solver_ids)}
         return params
 
     def seg_params(self, volume, materials: dict | None = None):

@@ -24,6 +24,7 @@ from typing import List
 import numpy as np
 
 from .. import _lib, xa
+from ..util.content import content_key as _content_key
 from ..util.units import getunitconversion
 
 log = logging.getLogger(__name__)
@@ -74,27 +75,6 @@ def _device():
     if "LOCAL_RANK" in os.environ:
         return int(os.environ["LOCAL_RANK"])
     return 0
-
-
-def _content_key(a: np.ndarray):
-    """Identity of an array's CONTENT for the medium cache: every byte takes part (an in-place edit of a single voxel
-    between two calls changes the key; the reference rebuilds the medium on every call, kwave_if.py:113).  Dense
-    arrays are summed as 64-bit words with wrap-around on all host threads (~5 ms for a float64 216^3 map) next to an
-    Adler-32 of a strided sample, which is sensitive to position; anything else is hashed byte by byte."""
-    a = np.asarray(a)
-    flat = None
-    if a.flags.c_contiguous or a.flags.f_contiguous:
-        flat = a.reshape(-1, order="A")
-    if flat is not None and flat.nbytes % 8 == 0 and flat.nbytes > 0:
-        words = flat.view(np.int64)
-        try:
-            import torch
-            total = int(torch.from_numpy(words).sum().item())
-        except Exception:  # noqa: BLE001 - torch missing or a read-only buffer it refuses
-            total = int(words.sum(dtype=np.int64))
-        step = max(1, flat.size // 4096)
-        return (a.shape, a.dtype.str, total, zlib.adler32(np.ascontiguousarray(flat[::step]).tobytes()))
-    return (a.shape, a.dtype.str, zlib.adler32(np.ascontiguousarray(a).tobytes()))
 
 
 def multi_gpu_mode():
@@ -251,7 +231,14 @@ def _setup_run(arr, params, delays, apod, freq, cycles, amplitude, dt, t_end, cf
                 lo, nz = sim.layout["medium_z0"], sim.layout["medium_nz"]      # only the planes this rank reads
                 sim.set_medium(*[m[:, :, lo:lo + nz] for m in maps], alpha_power=0.9, alpha_mode=alpha_mode, plane0=lo)
             else:
-                sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode)
+                lm = params.attrs.get("lifu_label_medium") if hasattr(params, "attrs") else None
+                if (lm is not None and os.environ.get("LIFU_MEDIUM_LABELS", "1") != "0"
+                        and lm["keys"] == tuple(mkey[1:4]) and lm["labels"].shape == tuple(kg["N"])):
+                    # the maps are still the ones _map_params expanded from this label volume: upload the labels (one
+                    # byte per voxel) and the per-label tables, expand on the device (seg_method.py:84-97)
+                    sim.set_medium_labels(lm["labels"], *[lm["lut"][k] for k in names], alpha_power=0.9, alpha_mode=alpha_mode)
+                else:
+                    sim.set_medium(*maps, alpha_power=0.9, alpha_mode=alpha_mode)
     medium_changed = ses.medium_key != mkey
     ses.medium_key = mkey
     # source geometry (get_karray + get_array_binary_mask + BLI weights), cached per transducer

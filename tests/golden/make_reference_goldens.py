@@ -168,6 +168,31 @@ def main():
     out["sa_line_z"] = np.asarray(line.data)
     out["sa_line_z_offsets"] = np.asarray(line.coords["offset_dz"].data)
 
+    # ---- candidate poses: the reference's TransformedTransducer.bake (xdc/transducer.py:412-417)
+    from dataclasses import fields as dc_fields
+    from openlifu.xdc.transducer import TransformedTransducer
+    rng = np.random.default_rng(147)
+    poses = []
+    for _ in range(3):
+        ax, ay, az = rng.uniform(-0.25, 0.25, 3)
+        rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        m = np.eye(4)
+        m[:3, :3] = rz @ ry @ rx
+        m[:3, 3] = rng.uniform(-4, 4, 3)
+        poses.append(m)
+    out["bake_transforms"] = np.array(poses)
+    for tag, arr in (("c1", arr1), ("c2", arr2)):
+        pos, ang = [], []
+        for m in poses:
+            kw = {f.name: getattr(arr.copy(), f.name) for f in dc_fields(xdc.Transducer)}
+            baked = TransformedTransducer(transform=m, **kw).bake()
+            pos.append(baked.get_positions(units="mm"))
+            ang.append([el.get_angle(units="deg") for el in baked.elements])
+        out[f"bake_{tag}_positions_mm"] = np.array(pos)
+        out[f"bake_{tag}_angles_deg"] = np.array(ang)
+
     np.savez_compressed(HERE / "ref_beamform.npz", **out)
     print("wrote", HERE / "ref_beamform.npz", "with", len(out), "arrays")
 

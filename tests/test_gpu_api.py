@@ -239,3 +239,91 @@ def test_field_stack_errors_and_numpy_semantics(lifu_lib):
         assert np.array_equal(a_pm, np.max(np.stack([h[0] for h in host]), axis=0))
         assert np.array_equal(a_pn, np.max(np.stack([h[1] for h in host]), axis=0))
         assert np.array_equal(a_it, np.mean(np.stack([h[2] for h in host]), axis=0))
+
+
+def test_simulate_candidates_against_oracle(lifu_lib):
+    """three candidate poses of the same array for one target, each an independent simulation with
+    its own off-grid source weights; source masks bit-exact and fields within 1e-4 of the oracle run on the baked
+    geometry; the analysis ranks the candidates."""
+    pr, arr, target, opts, _ = _wheel_protocol()
+    rng = np.random.default_rng(11)
+    transforms = [np.eye(4)]
+    for _ in range(2):
+        ay, ax = rng.uniform(-0.15, 0.15, 2)
+        ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        m = np.eye(4)
+        m[:3, :3] = ry @ rx
+        m[:3, 3] = rng.uniform(-2.5, 2.5, 3) * np.array([1, 1, 0.3])
+        transforms.append(m)
+    results = pr.simulate_candidates(target, arr, transforms, analysis_options=opts, use_gpu=True)
+    assert len(results) == 3
+    params = pr.sim_setup.setup_sim_scene(pr.seg_method)
+    peaks = []
+    for i, (sol, ana) in enumerate(results):
+        res = sol.simulation_result
+        assert tuple(res["p_min"].dims) == ("focal_point_index", "x", "y", "z") and res["p_min"].data.shape[0] == 1
+        sc = _scene(sol.transducer, params, 1e5)
+        want = osc.run_simulation(sc, delays=sol.delays[0], apod=sol.apodizations[0], freq=400e3, cycles=3,
+                                  dt=pr.sim_setup.dt, t_end=pr.sim_setup.t_end)
+        for k in ("p_max", "p_min", "intensity"):
+            assert cases.rel_l2(res[k].data[0], want[k]) < TOL, (i, k)
+        assert len(ana.mainlobe_pnp_MPa) == 1 and ana.mainlobe_pnp_MPa[0] > 0
+        peaks.append(ana.mainlobe_pnp_MPa[0])
+    # the identity pose reproduces the plain single-focus plan
+    sol0, _, _ = pr.__class__(pulse=pr.pulse, sequence=pr.sequence, sim_setup=pr.sim_setup).calc_solution(
+        target, arr, simulate=True, scale=False, analysis_options=opts, use_gpu=True)
+    assert np.array_equal(results[0][0].simulation_result["p_min"].data, sol0.simulation_result["p_min"].data)
+    assert len(set(np.round(peaks, 9))) == 3                                # the poses really differ
+
+
+def test_label_medium_on_device_equals_the_expanded_maps(lifu_lib, monkeypatch):
+    """the param maps of SegmentationMethod._map_params (seg_method.py:84-97) expanded on the DEVICE from
+    the label volume and the per-material tables (lifu_set_medium_labels) give bit-identical fields to uploading the three
+    float64 maps; run_simulation takes that route only while the maps still hold what _map_params wrote."""
+    from openlifu_b200 import _lib, configs
+    from openlifu_b200.sim import SimSetup, kwave_if
+    from openlifu_b200.xdc import Transducer
+    setup = SimSetup(spacing=1.0, x_extent=(-15, 15), y_extent=(-15, 15), z_extent=(-3, 36), dt=1.5e-7, t_end=90 * 1.5e-7)
+    seg = configs.seg_methods.LabelVolume(materials=dict(configs.PHANTOM_MATERIALS), ref_material="water")
+    volume = configs.skull_phantom_labels(setup.get_coords(), centre_mm=(0.0, 0.0, 40.0), r_in=24.0, r_out=28.0)
+    params = setup.setup_sim_scene(seg, volume=volume)
+    lm = params.attrs["lifu_label_medium"]
+    assert lm["labels"].dtype == np.uint8 and set(np.unique(lm["labels"])) == {0, 1, 2}
+    arr = Transducer.gen_matrix_array(nx=3, ny=3, pitch=4, kerf=0.5, units="mm", sensitivity=1e5)
+    calls = {"labels": 0, "maps": 0}
+    orig_l, orig_m = _lib.LifuSim.set_medium_labels, _lib.LifuSim.set_medium
+
+    def spy_l(self, *a, **k):
+        calls["labels"] += 1
+        return orig_l(self, *a, **k)
+
+    def spy_m(self, *a, **k):
+        calls["maps"] += 1
+        return orig_m(self, *a, **k)
+
+    monkeypatch.setattr(_lib.LifuSim, "set_medium_labels", spy_l)
+    monkeypatch.setattr(_lib.LifuSim, "set_medium", spy_m)
+    kw = dict(arr=arr, params=params, freq=400e3, cycles=3, dt=setup.dt, t_end=setup.t_end, amplitude=1.0, gpu=True)
+    kwave_if.clear_sessions()
+    ds_l, out_l = kwave_if.run_simulation(**kw)
+    assert calls == {"labels": 1, "maps": 0} and out_l["stats"]["homogeneous"] == 0 and out_l["stats"]["absorbing"] == 1
+    monkeypatch.setenv("LIFU_MEDIUM_LABELS", "0")
+    kwave_if.clear_sessions()
+    ds_m, _ = kwave_if.run_simulation(**kw)
+    assert calls == {"labels": 1, "maps": 1}
+    monkeypatch.delenv("LIFU_MEDIUM_LABELS")
+    for k in ("p_max", "p_min", "intensity"):
+        assert np.array_equal(ds_l[k].data, ds_m[k].data), k
+    # an in-place edit of one voxel of a map: the label route must not be taken any more, and the edit must be simulated
+    params["sound_speed"].data[15, 15, 20] = 1700.0
+    ds_e, _ = kwave_if.run_simulation(**kw)
+    assert calls == {"labels": 1, "maps": 2}
+    assert not np.array_equal(ds_e["p_min"].data, ds_m["p_min"].data)
+    kwave_if.clear_sessions()
+    # bad tables / labels are refused
+    with _lib.LifuSim([8, 8, 8], [1e-3] * 3, 1e-7, 2) as sim:
+        with pytest.raises(ValueError):
+            sim.set_medium_labels(np.zeros((8, 8, 8), dtype=np.uint8), np.ones(40), np.ones(40))
+        with pytest.raises(ValueError, match="sound speed must be positive"):
+            sim.set_medium_labels(np.full((8, 8, 8), 3, dtype=np.uint8), [1500.0, 1600.0], [1000.0, 1100.0])

@@ -388,3 +388,70 @@ def test_solution_json_layout_equals_reference_written_file():
     back = Solution.from_json(ref_text)
     assert back.id == "g" and back.transducer.numelements() == 16 and back.delays.shape == (2, 16)
     assert json.loads(back.to_json(include_simulation_data=False, compact=False)) == ref
+
+
+@pytest.mark.skipif(not Path("/root/reference/src/openlifu").exists(), reason="needs the reference sources (build container only)")
+def test_reference_analyze_consumes_the_dataset_run_simulation_packages():
+    """the Dataset that `run_simulation`'s packaging step hands out (package_fields -> concat over foci,
+    exactly what Protocol.calc_solution stores) is consumed by the REFERENCE's own, unmodified Solution.analyze /
+    Solution.scale (reference Transducer / Pulse / Point objects around it) and gives the numbers our analysis gives."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, json
+sys.path[:0] = ["%(root)s/tests/golden", "%(root)s/openlifu-python_b200", "%(root)s"]
+import numpy as np
+import make_reference_plan_goldens as m
+m.install_reference()
+from openlifu.bf import Pulse, Sequence
+from openlifu.bf.focal_patterns import Wheel
+from openlifu.geo import Point
+from openlifu.plan.solution import Solution as RefSolution
+from openlifu.plan.solution_analysis import SolutionAnalysisOptions
+from openlifu.xdc import Transducer
+from openlifu_b200 import xa
+from openlifu_b200.plan import Solution as OurSolution
+from openlifu_b200.sim import SimSetup
+from openlifu_b200.sim.kwave_if import package_fields
+from openlifu_b200.seg import seg_methods
+# flat x-fastest float32 sensor vectors as lifu_run returns them (p_min is the raw negative extreme)
+setup = SimSetup(spacing=1.0, x_extent=(-15, 15), y_extent=(-12, 12), z_extent=(20, 70))
+params = setup.setup_sim_scene(seg_methods.UniformWater())
+c = params.coords
+X, Y, Z = np.meshgrid(*[c[d].data for d in ("x", "y", "z")], indexing="ij")
+foci_mm = [(2.0, -1.0, 45.0), (-3.0, 2.0, 50.0)]
+per_focus = []
+for (fx, fy, fz), amp in zip(foci_mm, (1.3e6, 0.9e6)):
+    f = amp * np.exp(-(((X - fx) / 2.0) ** 2 + ((Y - fy) / 1.8) ** 2 + ((Z - fz) / 8.0) ** 2))
+    f += 0.25 * amp * np.exp(-(((X - fx - 9) / 2.0) ** 2 + ((Y - fy) / 2.0) ** 2 + ((Z - fz + 4) / 4.0) ** 2))
+    flat = f.astype(np.float32).flatten(order="F")
+    per_focus.append(package_fields(params, 1.05 * flat, -flat))
+stacked = xa.concat([o.assign_coords(focal_point_index=i) for i, o in enumerate(per_focus)], dim="focal_point_index")
+assert stacked["intensity"].data.dtype == np.float64 and stacked["p_min"].data.dtype == np.float32
+arr = Transducer.gen_matrix_array(nx=4, ny=4, pitch=4, kerf=0.5, units="mm")
+foci = [Point(position=np.array(f), units="mm", id=f"f{i}") for i, f in enumerate(foci_mm)]
+delays = np.array([[np.linalg.norm(np.array(f) - el.get_position(units="mm")) * 1e-3 / 1500 for el in arr.elements] for f in foci_mm])
+delays = delays.max(axis=1, keepdims=True) - delays
+kw = dict(id="g", transducer=arr, delays=delays, apodizations=np.ones((2, 16)), pulse=Pulse(frequency=400e3, amplitude=1.0, duration=50e-6),
+          sequence=Sequence(pulse_interval=0.01, pulse_count=4, pulse_train_interval=0.1, pulse_train_count=3), voltage=12.0,
+          foci=foci, target=foci[0])
+opts = SolutionAnalysisOptions(mainlobe_radius=2.5, beamwidth_radius=5.0, sidelobe_radius=3.0, sidelobe_zmin=1.0, distance_units="mm")
+ref_sol = RefSolution(simulation_result=stacked.copy(deep=True), **kw)
+want = m.analysis_to_plain(ref_sol.analyze(options=opts))
+ours = m.analysis_to_plain(OurSolution.analyze(RefSolution(simulation_result=stacked.copy(deep=True), **kw), options=opts, engine="host"))
+pattern = Wheel(center=True, num_spokes=1, spoke_radius=5.0, distance_units="mm", target_pressure=0.8, units="MPa")
+ref_sol.scale(pattern, analysis_options=opts)                 # in-place `.data *=` on our stacked arrays
+scaled = m.analysis_to_plain(ref_sol.analyze(options=opts))
+print(json.dumps({"want": want, "got": ours, "scaled_pnp": scaled["mainlobe_pnp_MPa"]}))
+''' % {"root": str(Path(__file__).resolve().parents[1])}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads(r.stdout.strip().splitlines()[-1])
+    for k, w in res["want"].items():
+        g = res["got"][k]
+        if w is None:
+            assert g is None, k
+        else:
+            np.testing.assert_allclose(np.asarray(g, dtype=float), np.asarray(w, dtype=float), rtol=1e-9, atol=1e-12,
+                                       equal_nan=True, err_msg=k)
+    np.testing.assert_allclose(res["scaled_pnp"], [0.8, 0.8], rtol=1e-5)

@@ -121,3 +121,22 @@ def test_drive_signals(tag, cyc):
     assert np.array_equal(on_delay, n_delay)
     assert np.array_equal(np.array(omat.shape), G[f"drive_{tag}_shape"])
     assert np.allclose(omat[[0, 7, arr.numelements() - 1]], G[f"drive_{tag}_rows"], rtol=1e-13, atol=1e-9)
+
+
+def test_candidate_poses_equal_the_reference_bake():
+    """candidate_transducer places the array like the reference's TransformedTransducer.bake
+    (xdc/transducer.py:412-417, 297-301); golden positions / Euler angles come from the real reference classes."""
+    from openlifu_b200 import configs
+    from openlifu_b200.plan.protocol import candidate_transducer
+    from openlifu_b200.xdc import Transducer
+    g = G
+    arrays = {"c1": Transducer.gen_matrix_array(nx=8, ny=8, pitch=4, kerf=0.5, units="mm", sensitivity=1e5),
+              "c2": configs.openlifu_2x_array()}
+    for tag, arr in arrays.items():
+        before = arr.get_positions(units="mm").copy()
+        for i, m in enumerate(g["bake_transforms"]):
+            baked = candidate_transducer(arr, m)
+            np.testing.assert_allclose(baked.get_positions(units="mm"), g[f"bake_{tag}_positions_mm"][i], rtol=0, atol=1e-10)
+            ang = np.array([el.get_angle(units="deg") for el in baked.elements])
+            np.testing.assert_allclose(ang, g[f"bake_{tag}_angles_deg"][i], rtol=0, atol=1e-9)
+        assert np.array_equal(arr.get_positions(units="mm"), before)        # the input transducer is not touched

@@ -51,16 +51,23 @@ def main():
     protocol_mod.xa.concat = timed("concat", xa.concat)
     lines = {}
     results = {}
-    for engine in ("cuda", "host", "cuda"):
-        os.environ["LIFU_ANALYZE"] = engine
+    Protocol._simulate_foci_on_device = timed("simulate_foci", Protocol._simulate_foci_on_device)
+    fields = {}
+    for engine, on_device in (("cuda", False), ("host", False), ("cuda", False), ("plan_on_device", True), ("plan_on_device", True)):
+        os.environ["LIFU_ANALYZE"] = "cuda" if on_device else engine
         T.clear()
         t0 = time.perf_counter()
-        sol, agg, ana = prot.calc_solution(cfg["target"], cfg["arr"], simulate=True, scale=True, use_gpu=True)
+        sol, agg, ana = prot.calc_solution(cfg["target"], cfg["arr"], simulate=True, scale=True, use_gpu=True,
+                                           on_device=on_device)
         tot = time.perf_counter() - t0
         n = len(sol.foci)
         lines[engine] = {"foci": n, "total_s": round(tot, 3), "foci_per_s": round(n / tot, 3),
                          **{k: round(v, 3) for k, v in T.items()}}
         results[engine] = ana
+        if engine != "host":
+            fields[engine] = (sol.simulation_result, agg)
+    same = all(np.array_equal(fields["cuda"][j][k].data, fields["plan_on_device"][j][k].data)
+               for j in (0, 1) for k in ("p_max", "p_min", "intensity"))
     a, b = results["cuda"], results["host"]
     worst = 0.0
     for k, v in b.__dict__.items():
@@ -73,6 +80,7 @@ def main():
         d = d[~(np.isnan(g) & np.isnan(w))]
         worst = max(worst, float(d.max()) if d.size else 0.0)
     print(json.dumps({"workload": f"C4-class: C2 grid ({n_inner}^3 inner), Wheel with {spokes} spokes + centre, calc_solution(scale=True)",
+                      "plan_on_device": lines["plan_on_device"], "plan_on_device_bit_identical_to_host_route": bool(same),
                       "analysis_on_device": lines["cuda"], "analysis_on_host": lines["host"],
                       "max_rel_diff_between_engines": worst, "host_cores": os.cpu_count()}))
 
