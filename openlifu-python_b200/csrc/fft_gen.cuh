@@ -203,6 +203,7 @@ __device__ __forceinline__ void g3_load_h(const GParams& G, const float2* __rest
                                           int kx0, float2* __restrict__ dst, const float2* __restrict__ mul) {
   const int L = G.Ls, LP = L + 1;
   const int items = nlines << G.lsh_s;
+#pragma unroll 4
   for (int w = threadIdx.x; w < items; w += blockDim.x) {
     const int lane = w & (L - 1), n = w >> G.lsh_s;
     const int kx = kx0 + lane;
@@ -255,61 +256,55 @@ __global__ void __launch_bounds__(256) g3_y_fwd(StepParams P, GParams G) {
   }
 }
 
-// z pass of the pressure gradient: H4[0] -> H4[0] = IFFT_z[kappa FFT_z p^], H4[1] = IFFT_z[i kz e^{+i kz dz/2} kappa FFT_z p^].
-// The forward transform is done twice (the second read of the column tile hits L2) so that two tile buffers suffice.
+// z pass of the pressure gradient, out of place: H4[0] -> H4[2] = IFFT_z[kappa FFT_z p^] (blockIdx.z = 0) and
+// H4[1] = IFFT_z[i kz e^{+i kz dz/2} kappa FFT_z p^] (blockIdx.z = 1).  grid (tiles, Ny, 2): the two chains run in
+// different CTAs (the second read of the column tile hits L2), two tile buffers each.
 __global__ void __launch_bounds__(256) g3_z_grad(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls, LP = L + 1;
-  const int kx0 = blockIdx.x * L, ky = blockIdx.y;
+  const int kx0 = blockIdx.x * L, ky = blockIdx.y, pass = blockIdx.z;
   float2* b0 = gen_buf(smraw, G.Nz, L, 0);
   float2* b1 = gen_buf(smraw, G.Nz, L, 1);
   const long long zs = (long long)G.Ny * G.PH;
-  float2* col = G.H4 + (long long)ky * G.PH;
+  const float2* col = G.H4 + (long long)ky * G.PH;
   const int items = G.Nz << G.lsh_s;
-  float2 keep[1];
-  (void)keep;
-  for (int pass = 1; pass >= 0; --pass) {      // pass 1: d/dz -> H4[1]; pass 0: plain -> H4[0] (in place, so it goes last)
-    g3_load_h(G, col, zs, G.Nz, kx0, b1, nullptr);
-    __syncthreads();
-    float2* cur = gen_fft<false>(G.pz, L, G.lsh_s, b1, b0, b1);
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int lane = w & (L - 1), kz = w >> G.lsh_s;
-      const int kx = min(kx0 + lane, G.Nxh - 1);
-      const float kap = kappa_rt(P.poly_ok, P.ax2[kx] + P.ay2[ky] + P.az2[kz]) * G.norm;
-      float2 v = cscale(cur[kz * LP + lane], kap);
-      if (pass == 1) v = cmul2(v, P.dpz[kz]);
-      cur[kz * LP + lane] = v;
-    }
-    __syncthreads();
-    float2* other = cur == b0 ? b1 : b0;
-    const float2* res = gen_fft<true>(G.pz, L, G.lsh_s, cur, other, cur);
-    float2* out = col + (pass == 1 ? G.HS : 0);
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int lane = w & (L - 1), zz = w >> G.lsh_s;
-      const int kx = kx0 + lane;
-      if (kx < G.Nxh) out[(long long)zz * zs + kx] = res[zz * LP + lane];
-    }
-    __syncthreads();
+  g3_load_h(G, col, zs, G.Nz, kx0, b1, nullptr);
+  __syncthreads();
+  float2* cur = gen_fft<false>(G.pz, L, G.lsh_s, b1, b0, b1);
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    const int lane = w & (L - 1), kz = w >> G.lsh_s;
+    const int kx = min(kx0 + lane, G.Nxh - 1);
+    const float kap = kappa_rt(P.poly_ok, P.ax2[kx] + P.ay2[ky] + P.az2[kz]) * G.norm;
+    float2 v = cscale(cur[kz * LP + lane], kap);
+    if (pass == 1) v = cmul2(v, P.dpz[kz]);
+    cur[kz * LP + lane] = v;
+  }
+  __syncthreads();
+  float2* other = cur == b0 ? b1 : b0;
+  const float2* res = gen_fft<true>(G.pz, L, G.lsh_s, cur, other, cur);
+  float2* out = G.H4 + (pass == 1 ? G.HS : 2 * G.HS) + (long long)ky * G.PH;
+#pragma unroll 4
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    const int lane = w & (L - 1), zz = w >> G.lsh_s;
+    const int kx = kx0 + lane;
+    if (kx < G.Nxh) out[(long long)zz * zs + kx] = res[zz * LP + lane];
   }
 }
 
-// y inverse of the three gradient components + row-pair merge.  grid (tiles, Nz)
-//   Z4[0] <- i kx e^{+i kx dx/2} IFFT_y[H4[0]];  Z4[1] <- IFFT_y[i ky e^{+i ky dy/2} H4[0]];  Z4[2] <- IFFT_y[H4[1]]
+// y inverse of the three gradient components + row-pair merge.  grid (tiles, Nz, 3), component = blockIdx.z
+//   Z4[0] <- i kx e^{+i kx dx/2} IFFT_y[H4[2]];  Z4[1] <- IFFT_y[i ky e^{+i ky dy/2} H4[2]];  Z4[2] <- IFFT_y[H4[1]]
 __global__ void __launch_bounds__(256) g3_y_inv_grad(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls;
-  const int kx0 = blockIdx.x * L, z = blockIdx.y;
+  const int kx0 = blockIdx.x * L, z = blockIdx.y, c = blockIdx.z;
   float2* b0 = gen_buf(smraw, G.Ny, L, 0);
   float2* b1 = gen_buf(smraw, G.Ny, L, 1);
   const float2* hp = G.H4 + (long long)z * G.Ny * G.PH;
   float2* zp = G.Z4 + (long long)z * G.My * G.Nx;
-  for (int c = 0; c < 3; ++c) {
-    g3_load_h(G, hp + (c == 2 ? G.HS : 0), G.PH, G.Ny, kx0, b1, c == 1 ? P.dpy : nullptr);
-    __syncthreads();
-    const float2* cur = gen_fft<true>(G.py, L, G.lsh_s, b1, b0, b1);
-    g3_merge_store(G, cur, zp + c * G.ZS, kx0, c == 0, P.dpx);
-    __syncthreads();
-  }
+  g3_load_h(G, hp + (c == 2 ? G.HS : 2 * G.HS), G.PH, G.Ny, kx0, b1, c == 1 ? P.dpy : nullptr);
+  __syncthreads();
+  const float2* cur = gen_fft<true>(G.py, L, G.lsh_s, b1, b0, b1);
+  g3_merge_store(G, cur, zp + c * G.ZS, kx0, c == 0, P.dpx);
 }
 
 // y inverse + row-pair merge of H4[comp] -> Z4[comp].  grid (tiles, Nz, ncomp)
@@ -326,9 +321,9 @@ __global__ void __launch_bounds__(256) g3_y_inv(StepParams P, GParams G) {
 }
 
 // z pass, in place, of (OP 0) the velocity divergence comps 0..2 [+ comp 3 = source field read from its slab, cos filter]
-// and (OP 1) the two absorption operands (fractional Laplacians k^(y-2), k^(y-1)).  grid (tiles, Ny)
+// and (OP 1) the two absorption operands (fractional Laplacians k^(y-2), k^(y-1)).  grid (tiles, Ny, ncomp)
 template <int OP>
-__global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G, int ncomp) {
+__global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls, LP = L + 1;
   const int kx0 = blockIdx.x * L, ky = blockIdx.y;
@@ -336,7 +331,8 @@ __global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G, int nc
   float2* b1 = gen_buf(smraw, G.Nz, L, 1);
   const long long zs = (long long)G.Ny * G.PH;
   const int items = G.Nz << G.lsh_s;
-  for (int comp = 0; comp < ncomp; ++comp) {
+  const int comp = blockIdx.z;
+  {
     float2* col = G.H4 + comp * G.HS + (long long)ky * G.PH;
     if (OP == 0 && comp == 3) {
       const float2* sp = G.HSslab + (long long)ky * G.PH;
@@ -373,35 +369,40 @@ __global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G, int nc
     __syncthreads();
     float2* other = cur == b0 ? b1 : b0;
     const float2* res = gen_fft<true>(G.pz, L, G.lsh_s, cur, other, cur);
+#pragma unroll 4
     for (int w = threadIdx.x; w < items; w += blockDim.x) {
       const int lane = w & (L - 1), zz = w >> G.lsh_s;
       const int kx = kx0 + lane;
       if (kx < G.Nxh) col[(long long)zz * zs + kx] = res[zz * LP + lane];
     }
-    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// x passes: a CTA owns a batch of L consecutive row pairs q = z * My + m (rows 2m, 2m+1 of plane z).
+// x passes: a CTA owns a batch of L consecutive row pairs q = z * My + m (rows 2m, 2m+1 of plane z); L (a power of two)
+// is a launch parameter chosen per kernel so that two tile buffers of N * (L + 1) float2 leave room for >= 2 CTAs per SM.
 // Lines are moved between global memory (x contiguous) and the tile (lane fastest) by warps walking along x.
-struct XBatch {
-  int q0, nq;         // first pair, pairs in this batch (<= L)
-};
-__device__ __forceinline__ void g3_x_load(const GParams& G, const float2* __restrict__ zfield, int q0, int nq, float2* __restrict__ dst) {
-  const int LP = G.Lx + 1;
+// Everything that has to outlive a transform (the source field, the du components, the partial pressure sum) is parked in
+// global scratch rows owned by the same thread (P.Sf, P.r3, P.r1): they are re-read from L2 a few microseconds later,
+// which is cheaper than a third, fourth and fifth tile buffer in shared memory (one CTA per SM).
+__device__ __forceinline__ void g3_x_load(const GParams& G, int L, const float2* __restrict__ zfield, int q0, int nq,
+                                          float2* __restrict__ dst) {
+  const int LP = L + 1;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int lane = wid; lane < G.Lx; lane += nw) {
+  for (int lane = wid; lane < L; lane += nw) {
     const float2* zp = zfield + (long long)(q0 + lane) * G.Nx;
     const bool ok = lane < nq;
+#pragma unroll 4
     for (int x = ln; x < G.Nx; x += 32) dst[x * LP + lane] = ok ? zp[x] : make_float2(0.f, 0.f);
   }
 }
-__device__ __forceinline__ void g3_x_store(const GParams& G, float2* __restrict__ zfield, int q0, int nq, const float2* __restrict__ src) {
-  const int LP = G.Lx + 1;
+__device__ __forceinline__ void g3_x_store(const GParams& G, int L, float2* __restrict__ zfield, int q0, int nq,
+                                           const float2* __restrict__ src) {
+  const int LP = L + 1;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int lane = wid; lane < nq; lane += nw) {
     float2* zp = zfield + (long long)(q0 + lane) * G.Nx;
+#pragma unroll 4
     for (int x = ln; x < G.Nx; x += 32) zp[x] = src[x * LP + lane];
   }
 }
@@ -414,53 +415,54 @@ __device__ __forceinline__ void g3_pair(const GParams& G, int q, int& z, int& yl
   r0 = ((long long)z * G.Ny + ylo) * G.Nx;
 }
 
-// IFFT_x of the three gradient components, u = pml_sg (pml_sg u - dt/rho0_sg dp), FFT_x of the new u.  grid = pair batches
+// IFFT_x of one gradient component (blockIdx.y), u = pml_sg (pml_sg u - dt/rho0_sg dp), FFT_x of the new u.
+// grid (pair batches, 3)
 template <bool HOMOG>
-__global__ void __launch_bounds__(512) g3_x_u(StepParams P, GParams G) {
+__global__ void __launch_bounds__(512) g3_x_u(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int L = G.Lx, LP = L + 1, N = G.Nx;
+  const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
   float2* b1 = gen_buf(smraw, N, L, 1);
   const int q0 = blockIdx.x * L;
   const int nq = min(L, G.Nz * G.My - q0);
+  const int c = blockIdx.y;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int c = 0; c < 3; ++c) {
-    g3_x_load(G, G.Z4 + c * G.ZS, q0, nq, b1);
-    __syncthreads();
-    float2* cur = gen_fft<true>(G.px, L, G.lsh_x, b1, b0, b1);
-    for (int lane = wid; lane < nq; lane += nw) {
-      int z, ylo; bool hh; long long r0;
-      g3_pair(G, q0 + lane, z, ylo, hh, r0);
-      float* u = P.u + c * P.RS + r0;
-      const float* mrow = HOMOG ? nullptr : P.dt_rho0_sg + c * P.RS + r0;
-      float2 s = make_float2(1.f, 1.f);
-      if (c == 1) s = make_float2(P.sgy[ylo], hh ? P.sgy[ylo + 1] : 0.f);
-      else if (c == 2) s.x = s.y = P.sgz[z];
-      for (int x = ln; x < N; x += 32) {
-        if (c == 0) s.x = s.y = P.sgx[x];
-        float2 d;
-        if (HOMOG) d.x = d.y = -P.dt_rho0_sg_s;
-        else { d.x = -mrow[x]; d.y = hh ? -mrow[N + x] : 0.f; }
-        const float2 g = cur[x * LP + lane];
-        const float2 uo = make_float2(u[x], hh ? u[N + x] : 0.f);
-        float2 un = __fmul2_rn(s, __ffma2_rn(d, g, __fmul2_rn(s, uo)));
-        if (!hh) un.y = 0.f;
-        u[x] = un.x;
-        if (hh) u[N + x] = un.y;
-        cur[x * LP + lane] = un;
-      }
+  g3_x_load(G, L, G.Z4 + c * G.ZS, q0, nq, b1);
+  __syncthreads();
+  float2* cur = gen_fft<true>(G.px, L, lsh, b1, b0, b1);
+  for (int lane = wid; lane < nq; lane += nw) {
+    int z, ylo; bool hh; long long r0;
+    g3_pair(G, q0 + lane, z, ylo, hh, r0);
+    float* u = P.u + c * P.RS + r0;
+    const float* mrow = HOMOG ? nullptr : P.dt_rho0_sg + c * P.RS + r0;
+    float2 s = make_float2(1.f, 1.f);
+    if (c == 1) s = make_float2(P.sgy[ylo], hh ? P.sgy[ylo + 1] : 0.f);
+    else if (c == 2) s.x = s.y = P.sgz[z];
+#pragma unroll 2
+    for (int x = ln; x < N; x += 32) {
+      if (c == 0) s.x = s.y = P.sgx[x];
+      float2 d;
+      if (HOMOG) d.x = d.y = -P.dt_rho0_sg_s;
+      else { d.x = -mrow[x]; d.y = hh ? -mrow[N + x] : 0.f; }
+      const float2 g = cur[x * LP + lane];
+      const float2 uo = make_float2(u[x], hh ? u[N + x] : 0.f);
+      float2 un = __fmul2_rn(s, __ffma2_rn(d, g, __fmul2_rn(s, uo)));
+      if (!hh) un.y = 0.f;
+      u[x] = un.x;
+      if (hh) u[N + x] = un.y;
+      cur[x * LP + lane] = un;
     }
-    __syncthreads();
-    float2* other = cur == b0 ? b1 : b0;
-    const float2* res = gen_fft<false>(G.px, L, G.lsh_x, cur, other, cur);
-    g3_x_store(G, G.Z4 + c * G.ZS, q0, nq, res);
-    __syncthreads();
   }
+  __syncthreads();
+  float2* other = cur == b0 ? b1 : b0;
+  const float2* res = gen_fft<false>(G.px, L, lsh, cur, other, cur);
+  g3_x_store(G, L, G.Z4 + c * G.ZS, q0, nq, res);
 }
 
 // sensor rows of a pair batch: running max / min of p (kept as a pair in `acc`) on the rows inside the inner grid
-__device__ __forceinline__ void g3_sensor(const StepParams& P, const GParams& G, int q0, int nq, const float2* __restrict__ acc) {
-  const int LP = G.Lx + 1, N = G.Nx;
+__device__ __forceinline__ void g3_sensor(const StepParams& P, const GParams& G, int L, int q0, int nq,
+                                          const float2* __restrict__ acc) {
+  const int LP = L + 1, N = G.Nx;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int lane = wid; lane < nq; lane += nw) {
     int z, ylo; bool hh; long long r0;
@@ -479,30 +481,35 @@ __device__ __forceinline__ void g3_sensor(const StepParams& P, const GParams& G,
 }
 
 // SRC: 0 none, 1 filtered source spectrum in Z4[3], 2 unfiltered dense slab.  ABS: absorbing medium (see fft_v2.cuh).
-// Tile buffers: b0, b1 (transform ping-pong), SUM (sum rho, then p), [SRCB source pair field], [DSUM sum of du].
+// Two tile buffers; the source rows live in P.Sf, the du rows (ABS) in P.r3, the density rows are re-read for the sum.
 template <bool HOMOG, int SRC, bool ABS>
-__global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G) {
+__global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int L = G.Lx, LP = L + 1, N = G.Nx;
+  const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
   float2* b1 = gen_buf(smraw, N, L, 1);
-  float2* SUM = gen_buf(smraw, N, L, 2);
-  float2* SRCB = gen_buf(smraw, N, L, 3);
-  float2* DSUM = gen_buf(smraw, N, L, SRC == 1 ? 4 : 3);
   const int q0 = blockIdx.x * L;
   const int nq = min(L, G.Nz * G.My - q0);
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
   if (SRC == 1) {
-    g3_x_load(G, G.Z4 + 3 * G.ZS, q0, nq, b1);
+    g3_x_load(G, L, G.Z4 + 3 * G.ZS, q0, nq, b1);
     __syncthreads();
-    const float2* cur = gen_fft<true>(G.px, L, G.lsh_x, b1, b0, b1);
-    for (int w = threadIdx.x; w < N * LP; w += blockDim.x) SRCB[w] = cur[w];
+    const float2* cur = gen_fft<true>(G.px, L, lsh, b1, b0, b1);
+    for (int lane = wid; lane < nq; lane += nw) {
+      int z, ylo; bool hh; long long r0;
+      g3_pair(G, q0 + lane, z, ylo, hh, r0);
+      for (int x = ln; x < N; x += 32) {
+        const float2 v = cur[x * LP + lane];
+        P.Sf[r0 + x] = v.x;
+        if (hh) P.Sf[r0 + N + x] = v.y;
+      }
+    }
     __syncthreads();
   }
   for (int c = 0; c < 3; ++c) {
-    g3_x_load(G, G.Z4 + c * G.ZS, q0, nq, b1);
+    g3_x_load(G, L, G.Z4 + c * G.ZS, q0, nq, b1);
     __syncthreads();
-    const float2* cur = gen_fft<true>(G.px, L, G.lsh_x, b1, b0, b1);
+    const float2* cur = gen_fft<true>(G.px, L, lsh, b1, b0, b1);
     for (int lane = wid; lane < nq; lane += nw) {
       int z, ylo; bool hh; long long r0;
       g3_pair(G, q0 + lane, z, ylo, hh, r0);
@@ -514,6 +521,7 @@ __global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G) {
       const int zr = z - G.z0s;
       const bool sin_ = SRC == 2 && zr >= 0 && zr < G.nzs;
       const float* srow = SRC == 2 ? G.Sslab + ((long long)zr * G.Ny + ylo) * N : nullptr;
+#pragma unroll 2
       for (int x = ln; x < N; x += 32) {
         if (c == 0) a.x = a.y = P.pmlx[x];
         float2 d;
@@ -522,83 +530,77 @@ __global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G) {
         const float2 g = cur[x * LP + lane];
         const float2 ro = make_float2(rho[x], hh ? rho[N + x] : 0.f);
         float2 rn = __fmul2_rn(a, __ffma2_rn(d, g, __fmul2_rn(a, ro)));
-        if (SRC == 1) rn = cadd(rn, SRCB[x * LP + lane]);
+        if (SRC == 1) rn = cadd(rn, make_float2(P.Sf[r0 + x], hh ? P.Sf[r0 + N + x] : 0.f));
         if (SRC == 2 && sin_) rn = cadd(rn, make_float2(srow[x], hh ? srow[N + x] : 0.f));
         rho[x] = rn.x;
         if (hh) rho[N + x] = rn.y;
-        SUM[x * LP + lane] = c == 0 ? rn : cadd(SUM[x * LP + lane], rn);          // (rho_x + rho_y) + rho_z
-        if (ABS) DSUM[x * LP + lane] = c == 0 ? g : cadd(DSUM[x * LP + lane], g);  // (dux + duy) + duz
+        if (ABS) { P.r3[c * P.RS + r0 + x] = g.x; if (hh) P.r3[c * P.RS + r0 + N + x] = g.y; }
       }
     }
     __syncthreads();
   }
-  if (ABS) {
-    // operands of the two fractional Laplacians: rho0 * sum du -> Z4[0], sum rho -> Z4[1] (and r1 keeps sum rho)
-    for (int lane = wid; lane < nq; lane += nw) {
-      int z, ylo; bool hh; long long r0;
-      g3_pair(G, q0 + lane, z, ylo, hh, r0);
-      const float* mrow = HOMOG ? nullptr : P.dt_rho0 + r0;
-      for (int x = ln; x < N; x += 32) {
-        float2 r0v;
-        if (HOMOG) r0v.x = r0v.y = P.rho0_s;
-        else { r0v.x = mrow[x] * P.inv_dt; r0v.y = hh ? mrow[N + x] * P.inv_dt : 0.f; }
-        DSUM[x * LP + lane] = __fmul2_rn(r0v, DSUM[x * LP + lane]);
-        const float2 sm = SUM[x * LP + lane];
-        P.r1[r0 + x] = sm.x;
-        if (hh) P.r1[r0 + N + x] = sm.y;
-      }
-    }
-    // lanes beyond nq hold stale data: clear them so the transforms stay finite
-    for (int lane = nq + wid; lane < L; lane += nw)
-      for (int x = ln; x < N; x += 32) { DSUM[x * LP + lane] = make_float2(0.f, 0.f); SUM[x * LP + lane] = make_float2(0.f, 0.f); }
-    __syncthreads();
-    const float2* r = gen_fft<false>(G.px, L, G.lsh_x, DSUM, b0, b1);
-    g3_x_store(G, G.Z4, q0, nq, r);
-    __syncthreads();
-    r = gen_fft<false>(G.px, L, G.lsh_x, SUM, b0, b1);
-    g3_x_store(G, G.Z4 + G.ZS, q0, nq, r);
-  } else {
-    // equation of state, sensor, forward transform of the new pressure
+  // epilogue: every thread re-reads the rows it wrote itself
+  for (int pass = ABS ? 0 : 1; pass < 2; ++pass) {
+    // pass 0 (ABS only): rho0 * ((dux + duy) + duz) -> Z4[0];  pass 1: sum rho = (rho_x + rho_y) + rho_z -> p or Z4[1]
     for (int lane = wid; lane < L; lane += nw) {
-      if (lane >= nq) { for (int x = ln; x < N; x += 32) SUM[x * LP + lane] = make_float2(0.f, 0.f); continue; }
+      if (lane >= nq) { for (int x = ln; x < N; x += 32) b1[x * LP + lane] = make_float2(0.f, 0.f); continue; }
       int z, ylo; bool hh; long long r0;
       g3_pair(G, q0 + lane, z, ylo, hh, r0);
+      const float* f0 = (pass == 0 ? P.r3 : P.rho) + r0;
+      const float* mrow = HOMOG ? nullptr : P.dt_rho0 + r0;
+#pragma unroll 2
       for (int x = ln; x < N; x += 32) {
-        float2 c2;
-        if (HOMOG) c2.x = c2.y = P.c2_s;
-        else { c2.x = P.c2[r0 + x]; c2.y = hh ? P.c2[r0 + N + x] : 0.f; }
-        const float2 p = __fmul2_rn(c2, SUM[x * LP + lane]);
-        SUM[x * LP + lane] = p;
-        if (G.store_p) { P.p[r0 + x] = p.x; if (hh) P.p[r0 + N + x] = p.y; }
+        float2 sm = cadd(cadd(make_float2(f0[x], hh ? f0[N + x] : 0.f),
+                              make_float2(f0[P.RS + x], hh ? f0[P.RS + N + x] : 0.f)),
+                         make_float2(f0[2 * P.RS + x], hh ? f0[2 * P.RS + N + x] : 0.f));
+        if (pass == 0) {
+          float2 r0v;
+          if (HOMOG) r0v.x = r0v.y = P.rho0_s;
+          else { r0v.x = mrow[x] * P.inv_dt; r0v.y = hh ? mrow[N + x] * P.inv_dt : 0.f; }
+          sm = __fmul2_rn(r0v, sm);
+        } else if (ABS) {
+          P.r1[r0 + x] = sm.x;
+          if (hh) P.r1[r0 + N + x] = sm.y;
+        } else {
+          float2 c2;
+          if (HOMOG) c2.x = c2.y = P.c2_s;
+          else { c2.x = P.c2[r0 + x]; c2.y = hh ? P.c2[r0 + N + x] : 0.f; }
+          sm = __fmul2_rn(c2, sm);
+          if (G.store_p) { P.p[r0 + x] = sm.x; if (hh) P.p[r0 + N + x] = sm.y; }
+        }
+        b1[x * LP + lane] = sm;
       }
     }
     __syncthreads();
-    g3_sensor(P, G, q0, nq, SUM);
-    const float2* r = gen_fft<false>(G.px, L, G.lsh_x, SUM, b0, b1);
-    g3_x_store(G, G.ZP, q0, nq, r);
+    if (!ABS) g3_sensor(P, G, L, q0, nq, b1);
+    const float2* r = gen_fft<false>(G.px, L, lsh, b1, b0, b1);
+    g3_x_store(G, L, ABS ? G.Z4 + pass * G.ZS : G.ZP, q0, nq, r);
+    __syncthreads();
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *P.step = *P.step + 1;
 }
 
-// Absorbing medium, last pass: p = c0^2 (sum rho + tau L1 - eta L2), sensor, FFT_x of p -> ZP.  Buffers b0, b1, ACC.
+// Absorbing medium, last pass: p = c0^2 (sum rho + tau L1 - eta L2), sensor, FFT_x of p -> ZP.  Two tile buffers; the
+// partial sum (sum rho + tau L1) waits in P.r3[0] while the second operand is transformed.
 template <bool HOMOG>
-__global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int use_tau, int use_eta) {
+__global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int L, int lsh, int use_tau, int use_eta) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int L = G.Lx, LP = L + 1, N = G.Nx;
+  const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
   float2* b1 = gen_buf(smraw, N, L, 1);
-  float2* ACC = gen_buf(smraw, N, L, 2);
   const int q0 = blockIdx.x * L;
   const int nq = min(L, G.Nz * G.My - q0);
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float2* cur = nullptr;
   for (int c = 0; c < 2; ++c) {
-    g3_x_load(G, G.Z4 + c * G.ZS, q0, nq, b1);
+    g3_x_load(G, L, G.Z4 + c * G.ZS, q0, nq, b1);
     __syncthreads();
-    const float2* cur = gen_fft<true>(G.px, L, G.lsh_x, b1, b0, b1);
+    cur = gen_fft<true>(G.px, L, lsh, b1, b0, b1);
     for (int lane = wid; lane < L; lane += nw) {
-      if (lane >= nq) { if (c == 1) for (int x = ln; x < N; x += 32) ACC[x * LP + lane] = make_float2(0.f, 0.f); continue; }
+      if (lane >= nq) { if (c == 1) for (int x = ln; x < N; x += 32) cur[x * LP + lane] = make_float2(0.f, 0.f); continue; }
       int z, ylo; bool hh; long long r0;
       g3_pair(G, q0 + lane, z, ylo, hh, r0);
+#pragma unroll 2
       for (int x = ln; x < N; x += 32) {
         const float2 v = cur[x * LP + lane];
         if (c == 0) {
@@ -606,30 +608,33 @@ __global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int use_t
           if (HOMOG) ta.x = ta.y = P.tau_s;
           else { ta.x = P.tau[r0 + x]; ta.y = hh ? P.tau[r0 + N + x] : 0.f; }
           const float2 s0 = make_float2(P.r1[r0 + x], hh ? P.r1[r0 + N + x] : 0.f);
-          ACC[x * LP + lane] = use_tau ? __ffma2_rn(ta, v, s0) : s0;
+          const float2 acc = use_tau ? __ffma2_rn(ta, v, s0) : s0;
+          P.r3[r0 + x] = acc.x;
+          if (hh) P.r3[r0 + N + x] = acc.y;
         } else {
           float2 et, c2;
           if (HOMOG) { et.x = et.y = -P.eta_s; c2.x = c2.y = P.c2_s; }
           else { et.x = -P.eta[r0 + x]; et.y = hh ? -P.eta[r0 + N + x] : 0.f; c2.x = P.c2[r0 + x]; c2.y = hh ? P.c2[r0 + N + x] : 0.f; }
-          float2 acc = ACC[x * LP + lane];
+          float2 acc = make_float2(P.r3[r0 + x], hh ? P.r3[r0 + N + x] : 0.f);
           if (use_eta) acc = __ffma2_rn(et, v, acc);
           acc = __fmul2_rn(c2, acc);
-          ACC[x * LP + lane] = acc;
+          cur[x * LP + lane] = acc;
           if (G.store_p) { P.p[r0 + x] = acc.x; if (hh) P.p[r0 + N + x] = acc.y; }
         }
       }
     }
     __syncthreads();
   }
-  g3_sensor(P, G, q0, nq, ACC);
-  const float2* r = gen_fft<false>(G.px, L, G.lsh_x, ACC, b0, b1);
-  g3_x_store(G, G.ZP, q0, nq, r);
+  g3_sensor(P, G, L, q0, nq, cur);
+  float2* other = cur == b0 ? b1 : b0;
+  const float2* r = gen_fft<false>(G.px, L, lsh, cur, other, cur);
+  g3_x_store(G, L, G.ZP, q0, nq, r);
 }
 
 // x forward of the dense source slab (row pairs of the slab planes).  grid = pair batches of the slab
-__global__ void __launch_bounds__(512) g3_x_src(StepParams P, GParams G) {
+__global__ void __launch_bounds__(512) g3_x_src(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  const int L = G.Lx, LP = L + 1, N = G.Nx;
+  const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
   float2* b1 = gen_buf(smraw, N, L, 1);
   const int q0 = blockIdx.x * L;
@@ -644,8 +649,8 @@ __global__ void __launch_bounds__(512) g3_x_src(StepParams P, GParams G) {
       b1[x * LP + lane] = ok ? make_float2(row[x], hh ? row[N + x] : 0.f) : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  const float2* r = gen_fft<false>(G.px, L, G.lsh_x, b1, b0, b1);
-  g3_x_store(G, G.ZSslab, q0, nq, r);
+  const float2* r = gen_fft<false>(G.px, L, lsh, b1, b0, b1);
+  g3_x_store(G, L, G.ZSslab, q0, nq, r);
 }
 
 // Source scatter into the dense slab (same arithmetic as k_source_scatter of v1).

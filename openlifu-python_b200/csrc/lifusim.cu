@@ -1193,14 +1193,24 @@ static int v3_setup(lifu_sim* s) {
     LIFU_CHECK(dev_alloc(s, (void**)&G.H4, sizeof(float2) * 4 * G.HS));
     LIFU_CHECK(dev_alloc(s, (void**)&G.pm, sizeof(float2) * s->V));
     // tile widths: as wide as two CTAs per SM allow (strided passes: two buffers; x passes: up to five)
-    G.Ls = v3_lanes(std::max(Ny, Nz), 2, 108 * 1024, 16);
-    G.lsh_s = 0; while ((1 << G.lsh_s) < G.Ls) ++G.lsh_s;
     s->v3_ready = true;
   }
-  // the x passes need 3 buffers (+1 with a filtered source, +1 in an absorbing medium)
-  const int nbx = 3 + (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 0) + (s->absorbing ? 1 : 0);
-  G.Lx = v3_lanes(Nx, nbx, (size_t)nbx * Nx * 17 * sizeof(float2) <= 100 * 1024 ? 100 * 1024 : kV3SmemCap, 16);
+  auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return (e && e[0]) ? atoi(e) : dflt; };
+  G.Ls = v3_lanes(std::max(Ny, Nz), 2, 108 * 1024, 16);
+  {
+    const int o = env_int("LIFU_V3_LS", 0);                     // tuning override: lanes per strided tile (power of two)
+    if (o == 1 || o == 2 || o == 4 || o == 8 || o == 16) G.Ls = v3_lanes(std::max(Ny, Nz), 2, kV3SmemCap, o);
+  }
+  G.lsh_s = 0; while ((1 << G.lsh_s) < G.Ls) ++G.lsh_s;
+  // the x passes hold two tile buffers as well (what outlives a transform is parked in global scratch rows)
+  G.Lx = v3_lanes(Nx, 2, 108 * 1024, 16);
+  {
+    const int o = env_int("LIFU_V3_LX", 0);
+    if (o == 1 || o == 2 || o == 4 || o == 8 || o == 16) G.Lx = v3_lanes(Nx, 2, kV3SmemCap, o);
+  }
   G.lsh_x = 0; while ((1 << G.lsh_x) < G.Lx) ++G.lsh_x;
+  s->v3_ts = std::min(256, std::max(64, env_int("LIFU_V3_TS", 256) / 32 * 32));
+  s->v3_tx = std::min(512, std::max(64, env_int("LIFU_V3_TX", 256) / 32 * 32));
   int z0 = 0, nz = 1;
   if (s->n_src > 0) {
     long long first = 0, last = 0;
@@ -1234,16 +1244,15 @@ static int enqueue_step_v3(lifu_sim* s, bool src_active, int* n_kernels, const s
   const unsigned gx = (unsigned)(((long long)G.Nz * G.My + G.Lx - 1) / G.Lx);
   const int src = !src_active ? 0 : (s->source_mode == LIFU_SOURCE_ADDITIVE ? 1 : 2);
   const double srcf = (double)G.nzs / G.Nz;
-  const int TS = 256;                                                  // threads of the strided passes
-  const int TX = (size_t)5 * smx > 100 * 1024 ? 512 : 256;             // fat x tiles run one CTA per SM: more threads
+  const int TS = s->v3_ts, TX = s->v3_tx;                              // threads per CTA of the strided / x passes
   int nk = 0;
   // (1) pressure gradient
   v2_launch(g3_y_fwd<0>, dim3(tx, G.Nz, 1), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_p", 8);
-  v2_launch(g3_z_grad, dim3(tx, G.Ny), TS, smz, st, s->P, G); ++nk; mark("g3_z_grad", 12);
-  v2_launch(g3_y_inv_grad, dim3(tx, G.Nz), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv_grad", 20);
+  v2_launch(g3_z_grad, dim3(tx, G.Ny, 2), TS, smz, st, s->P, G); ++nk; mark("g3_z_grad", 12);
+  v2_launch(g3_y_inv_grad, dim3(tx, G.Nz, 3), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
-  if (s->homogeneous) v2_launch(g3_x_u<true>, dim3(gx), TX, 2 * smx, st, s->P, G);
-  else v2_launch(g3_x_u<false>, dim3(gx), TX, 2 * smx, st, s->P, G);
+  if (s->homogeneous) v2_launch(g3_x_u<true>, dim3(gx, 3), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x);
+  else v2_launch(g3_x_u<false>, dim3(gx, 3), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x);
   ++nk; mark("g3_x_u", s->homogeneous ? 48 : 60);
   v2_launch(g3_y_fwd<1>, dim3(tx, G.Nz, 3), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_u", 24);
   // (3) source field on its slab
@@ -1252,18 +1261,17 @@ static int enqueue_step_v3(lifu_sim* s, bool src_active, int* n_kernels, const s
     ++nk; mark("g3_source_scatter", 0);
     if (src == 1) {
       const unsigned gs = (unsigned)(((long long)G.nzs * G.My + G.Lx - 1) / G.Lx);
-      v2_launch(g3_x_src, dim3(gs), TX, 2 * smx, st, s->P, G); ++nk; mark("g3_x_src", 8 * srcf);
+      v2_launch(g3_x_src, dim3(gs), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x); ++nk; mark("g3_x_src", 8 * srcf);
       v2_launch(g3_y_fwd<2>, dim3(tx, G.nzs, 1), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_src", 8 * srcf);
     }
   }
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src == 1 ? 4 : 3;
-  v2_launch(g3_z_pass<0>, dim3(tx, G.Ny), TS, smz, st, s->P, G, ncomp); ++nk;
+  v2_launch(g3_z_pass<0>, dim3(tx, G.Ny, ncomp), TS, smz, st, s->P, G); ++nk;
   mark("g3_z_div", 24 + (src == 1 ? 4 + 4 * srcf : 0));
   v2_launch(g3_y_inv, dim3(tx, G.Nz, ncomp), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
-  const int nbx = 3 + (src == 1 ? 1 : 0) + (s->absorbing ? 1 : 0);
-#define V3_RHO(H, SRCV, A) v2_launch(g3_x_rho_p<H, SRCV, A>, dim3(gx), TX, nbx * smx, st, s->P, G)
+#define V3_RHO(H, SRCV, A) v2_launch(g3_x_rho_p<H, SRCV, A>, dim3(gx), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x)
 #define V3_RHO_SRC(H, A) do { if (src == 0) V3_RHO(H, 0, A); else if (src == 1) V3_RHO(H, 1, A); else V3_RHO(H, 2, A); } while (0)
   if (s->homogeneous) { if (s->absorbing) V3_RHO_SRC(true, true); else V3_RHO_SRC(true, false); }
   else { if (s->absorbing) V3_RHO_SRC(false, true); else V3_RHO_SRC(false, false); }
@@ -1276,11 +1284,11 @@ static int enqueue_step_v3(lifu_sim* s, bool src_active, int* n_kernels, const s
   } else {
     mark("g3_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src == 1 ? 4 : 0));
     v2_launch(g3_y_fwd<3>, dim3(tx, G.Nz, 2), TS, smy, st, s->P, G); ++nk; mark("g3_y_fwd_abs", 16);
-    v2_launch(g3_z_pass<1>, dim3(tx, G.Ny), TS, smz, st, s->P, G, 2); ++nk; mark("g3_z_absorb", 16);
+    v2_launch(g3_z_pass<1>, dim3(tx, G.Ny, 2), TS, smz, st, s->P, G); ++nk; mark("g3_z_absorb", 16);
     v2_launch(g3_y_inv, dim3(tx, G.Nz, 2), TS, smy, st, s->P, G); ++nk; mark("g3_y_inv_abs", 16);
     const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
-    if (s->homogeneous) v2_launch(g3_x_p<true>, dim3(gx), TX, 3 * smx, st, s->P, G, use_tau, use_eta);
-    else v2_launch(g3_x_p<false>, dim3(gx), TX, 3 * smx, st, s->P, G, use_tau, use_eta);
+    if (s->homogeneous) v2_launch(g3_x_p<true>, dim3(gx), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x, use_tau, use_eta);
+    else v2_launch(g3_x_p<false>, dim3(gx), TX, 2 * smx, st, s->P, G, G.Lx, G.lsh_x, use_tau, use_eta);
     ++nk; mark("g3_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
   }
   LIFU_CUDA(cudaGetLastError());

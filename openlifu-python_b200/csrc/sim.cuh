@@ -119,6 +119,7 @@ struct lifu_sim {
   lifu::GParams G{};
   float2* d_gtw[3] = {nullptr, nullptr, nullptr};
   long long v3_slab_planes = 0;
+  int v3_ts = 256, v3_tx = 256;   // threads per CTA of the strided / x passes (LIFU_V3_TS / LIFU_V3_TX)
 
   // per-stage profiling (lifu_profile_stages)
   bool prof_on = false;

@@ -514,17 +514,42 @@ class Solution:
         return Solution.from_dict(d)
 
     def to_files(self, json_filepath: Path, nc_filepath: Path | None = None) -> None:
+        """JSON + netCDF pair (reference ``to_files``, solution.py:499-516).  The reference writes netCDF-4 through
+        ``engine='h5netcdf'``; where that backend is not installed (h5py / h5netcdf are optional and absent from the
+        offline image) the fields are written as NetCDF-3 64-bit-offset (``engine='scipy'``) instead -- announced at
+        WARNING level; ``from_files`` recognises either container by its magic bytes, and xarray itself opens both."""
         json_filepath = Path(json_filepath)
         nc_filepath = _nc_path_for(json_filepath) if nc_filepath is None else Path(nc_filepath)
         json_filepath.parent.mkdir(parents=True, exist_ok=True)
         nc_filepath.parent.mkdir(parents=True, exist_ok=True)
         json_filepath.write_text(self.to_json(include_simulation_data=False, compact=False))
-        self.simulation_result.to_netcdf(nc_filepath, engine="h5netcdf")
+        if _netcdf4_available():
+            self.simulation_result.to_netcdf(nc_filepath, engine="h5netcdf")
+        else:
+            logging.getLogger(__name__).warning(
+                "Solution.to_files: no netCDF-4 backend (h5netcdf / h5py) is installed; writing %s as NetCDF-3 "
+                "(64-bit offset, engine='scipy')", nc_filepath)
+            self.simulation_result.to_netcdf(nc_filepath, engine="scipy")
 
     @staticmethod
     def from_files(json_filepath: Path, nc_filepath: Path | None = None) -> "Solution":
         json_filepath = Path(json_filepath)
         nc_filepath = _nc_path_for(json_filepath) if nc_filepath is None else Path(nc_filepath)
-        ds = xa.open_dataset(nc_filepath, engine="h5netcdf").load()
+        with open(nc_filepath, "rb") as f:
+            magic = f.read(4)
+        engine = "scipy" if magic[:3] == b"CDF" else "h5netcdf"        # NetCDF-3 classic / 64-bit offset vs HDF5
+        ds = xa.open_dataset(nc_filepath, engine=engine).load()
         ds.close()
         return Solution.from_json(json_filepath.read_text(), simulation_result=ds)
+
+
+def _netcdf4_available() -> bool:
+    """Is there a backend that writes netCDF-4 (HDF5) files?  Needs real xarray with h5netcdf + h5py."""
+    if not getattr(xa, "HAVE_XARRAY", False):
+        return False
+    try:
+        import h5netcdf  # noqa: F401
+        import h5py  # noqa: F401
+    except ImportError:
+        return False
+    return True
