@@ -501,6 +501,8 @@ def main():
     ap.add_argument("--n-inner", type=int, default=216)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--poses", type=int, default=0, help="candidate-pose sweep (SURVEY.md 8f row 3): every bench step "
+                    "simulates another of this many transducer poses (source weights rebuilt per step)")
     ap.add_argument("--no-slab-leg", action="store_true", help="N > 1: skip the appended slab-decomposition leg")
     ap.add_argument("--slab-n-inner", type=int, default=472, help="slab leg: inner grid size (472 -> 512^3 with PML)")
     ap.add_argument("--slab-time-steps", type=int, default=10)
@@ -565,9 +567,38 @@ def main():
     def focus_for(step):
         return (rank + step * world) % len(beams)
 
+    # candidate poses: small rigid motions of the array (what a virtual fit proposes), one per bench step
+    pose_arrays, pose_beams = [], []
+    if args.poses > 0:
+        from openlifu_b200.plan.protocol import candidate_transducer
+        rng = np.random.default_rng(147)
+        for _ in range(args.poses):
+            ay, ax = rng.uniform(-0.06, 0.06, 2)
+            ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+            rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+            m = np.eye(4)
+            m[:3, :3] = ry @ rx
+            m[:3, 3] = rng.uniform(-2.0, 2.0, 3) * np.array([1, 1, 0.25])
+            a = candidate_transducer(arr, m)
+            pose_arrays.append(a)
+            dm, am = cfg.get("delay_method"), cfg.get("apod_method")
+            from openlifu_b200.bf import apod_methods, delay_methods
+            dm = dm or delay_methods.Direct()
+            am = am or apod_methods.Uniform()
+            pose_beams.append((dm.calc_delays(a, cfg["target"], params), am.calc_apodization(a, cfg["target"], params)))
+
+    def pose_for(step):
+        return (rank + step * world) % args.poses
+
     def resident_step(step):
-        delays, apod = beams[focus_for(step)]
-        n_delay, gains, base_gain = arr.drive_plan(kg["dt"], delays, apod)
+        if args.poses > 0:
+            a = pose_arrays[pose_for(step)]
+            delays, apod = pose_beams[pose_for(step)]
+            sim.set_elements(*element_geometry(a, offset), 0.05, 5)      # off-grid source weights of this pose
+        else:
+            a = arr
+            delays, apod = beams[focus_for(step)]
+        n_delay, gains, base_gain = a.drive_plan(kg["dt"], delays, apod)
         sim.set_drive(base * base_gain, n_delay, gains)
         return sim.run(d_pmax.data_ptr(), d_pmin.data_ptr())[2]
 
@@ -634,11 +665,16 @@ def main():
 
         def api_step(step):
             nonlocal h2d, d2h
-            delays, apod = beams[focus_for(step)]
+            if args.poses > 0:
+                a_step = pose_arrays[pose_for(step)]
+                delays, apod = pose_beams[pose_for(step)]
+            else:
+                a_step = arr
+                delays, apod = beams[focus_for(step)]
             ses = next(iter(kwave_if._SESSIONS.values()), None)
             if ses is not None:
                 ses.medium_key = None          # the medium is an input of every call: upload it every step
-            ds, out = kwave_if.run_simulation(arr=arr, params=params, delays=delays, apod=apod, freq=freq, cycles=cycles,
+            ds, out = kwave_if.run_simulation(arr=a_step, params=params, delays=delays, apod=apod, freq=freq, cycles=cycles,
                                               dt=cfg["setup"].dt, t_end=cfg["setup"].t_end, cfl=cfg["setup"].cfl,
                                               amplitude=amp, gpu=True)
             dev_pkg = os.environ.get("LIFU_PACKAGING", "host") == "device"
@@ -699,7 +735,10 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": bench_config(args, V, Nt),
-                "detail": {"n_src": int(n_src), "foci": "C4 wheel: rank r, step s -> focus (r + s*N) mod 32", "l2": l2,
+                "detail": {"n_src": int(n_src),
+                           "foci": ("C4 wheel: rank r, step s -> focus (r + s*N) mod 32" if args.poses == 0 else
+                                    f"candidate poses: rank r, step s -> pose (r + s*N) mod {args.poses}, source weights rebuilt per step"),
+                           "l2": l2,
                            "fft": ("hand-written fused FFT passes" if st["fft_launches"] == 0 else "cuFFT 3-D R2C/C2R (v1 pipeline)"),
                            "time_loop_only_value": loop_value},
                 "e2e": e2e, "gpu_launches": int(launches), "fft_launches": int(st["fft_launches"] * args.steps),

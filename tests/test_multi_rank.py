@@ -146,3 +146,50 @@ def test_slab_fft_two_ranks_matches_fftn(shape):
     out = _spawn(_slab_fft, 2, shape, 147)
     for r in (0, 1):
         assert out[r][0] < 1e-10 and out[r][1] < 1e-12, out
+
+
+# ------------------------------------------------------------------------------------------------
+def _candidates(rank, world, n_poses):
+    """Protocol.simulate_candidates under torch.distributed: pose i runs on rank i mod world, every rank ends up with
+    every pose's fields."""
+    from openlifu_b200.bf import Pulse, Sequence
+    from openlifu_b200.geo import Point
+    from openlifu_b200.plan import Protocol, SolutionAnalysisOptions
+    from openlifu_b200.plan import protocol as pmod
+    from openlifu_b200.sim import SimSetup
+    from openlifu_b200.xdc import Transducer
+    calls = []
+
+    def counting(**kw):
+        calls.append(float(np.sum(np.abs(kw["delays"]))))
+        return _fake_run_simulation(**kw)
+
+    pmod.run_simulation = counting
+    pr = Protocol(pulse=Pulse(frequency=400e3, duration=25e-6), sequence=Sequence(pulse_interval=0.01, pulse_count=1, pulse_train_interval=0),
+                  sim_setup=SimSetup(spacing=2.0, x_extent=(-10, 10), y_extent=(-10, 10), z_extent=(0, 40)))
+    arr = Transducer.gen_matrix_array(nx=4, ny=4, pitch=4, kerf=0.5, units="mm", sensitivity=1e4)
+    target = Point(position=np.array([0, 0, 30.0]), units="mm", id="tgt")
+    transforms = []
+    for i in range(n_poses):
+        m = np.eye(4)
+        m[0, 3], m[2, 3] = 1.5 * i, -0.5 * i
+        transforms.append(m)
+    opts = SolutionAnalysisOptions(mainlobe_radius=4.0, beamwidth_radius=8.0, sidelobe_radius=6.0, sidelobe_zmin=1.0, distance_units="mm")
+    res = pr.simulate_candidates(target, arr, transforms, analysis_options=opts, use_gpu=True, analyze=True)
+    return {"calls": len(calls), "p_min": [np.asarray(s.simulation_result["p_min"].data) for s, _ in res],
+            "delays": [np.asarray(s.delays) for s, _ in res], "pnp": [a.mainlobe_pnp_MPa[0] for _, a in res],
+            "pos0": [s.transducer.get_positions(units="mm")[0].tolist() for s, _ in res]}
+
+
+def test_candidate_poses_sharded_over_two_ranks_matches_serial():
+    two = _spawn(_candidates, 2, 5)
+    one = _spawn(_candidates, 1, 5)[0]
+    assert one["calls"] == 5 and two[0]["calls"] == 3 and two[1]["calls"] == 2
+    assert len({tuple(p) for p in one["pos0"]}) == 5                       # five different poses
+    for r in (0, 1):
+        assert two[r]["pos0"] == one["pos0"]
+        for i in range(5):
+            assert two[r]["p_min"][i].shape[0] == 1
+            np.testing.assert_array_equal(two[r]["p_min"][i], one["p_min"][i])
+            np.testing.assert_array_equal(two[r]["delays"][i], one["delays"][i])
+        np.testing.assert_allclose(two[r]["pnp"], one["pnp"], rtol=0, atol=0)
