@@ -291,8 +291,9 @@ int lifu_stack_destroy(lifu_stack* stack);
 /* Package the result of the solver's last lifu_run into slot `focus` (needs lifu_set_two_z): no host round trip. */
 int lifu_stack_put(lifu_stack* stack, int32_t focus, lifu_sim* sim);
 /* Solution.scale on one focus: pressures *= s (product in float64, rounded to float32: numpy >= 2 semantics of
- * `float32_array *= np.float64(s)`), intensity *= s*s. */
-int lifu_stack_scale(lifu_stack* stack, int32_t focus, double s);
+ * `float32_array *= np.float64(s)`), intensity *= s2.  The caller passes s2 = `s ** 2` as ITS arithmetic forms it
+ * (numpy's scalar power is not always the correctly rounded s * s). */
+int lifu_stack_scale(lifu_stack* stack, int32_t focus, double s, double s2);
 /* Device pointers of one focus (for lifu_analysis_set_focus with strides (1, Nx, Nx*Ny)). */
 int lifu_stack_pointers(lifu_stack* stack, int32_t focus, float** p_max, float** pnp, double** intensity);
 /* Copy out one focus (focus >= 0) or the whole stack (focus = -1); host or device destinations, any may be NULL. */

@@ -25,6 +25,17 @@
 #pragma once
 #include "fft_v2.cuh"
 
+// Launch bounds of the v3 kernels.  Default: 256 threads (512 for the x passes), registers uncapped (128 in practice,
+// two CTAs per SM).  -DLIFU_G3_LB512 is the experiment build: 512-thread CTAs capped at 64 registers (radices <= 8 only,
+// LIFU_V3_RMAX=8), 32 warps per SM.
+#ifdef LIFU_G3_LB512
+#define G3_LB_S __launch_bounds__(512, 2)
+#define G3_LB_X __launch_bounds__(512, 2)
+#else
+#define G3_LB_S __launch_bounds__(256)
+#define G3_LB_X __launch_bounds__(512)
+#endif
+
 namespace lifu {
 
 // ------------------------------------------------------------------------------------------------
@@ -106,10 +117,24 @@ template <int R, bool INV> __device__ __forceinline__ void dft_any(float2 (&v)[R
 }
 
 // ------------------------------------------------------------------------------------------------
+// Optional global-memory ends of a line transform: the first stage can read its inputs straight from a strided global
+// column tile (R independent loads per work item instead of a staging pass through shared memory) and the last stage can
+// write its outputs straight back; element (n, lane) lives at g[n * stride + lane], lanes >= nvalid are masked, and an
+// optional per-line multiplier table rides on either end.
+struct GenIO {
+  const float2* gin = nullptr;
+  long long in_stride = 0;
+  const float2* in_mul = nullptr;
+  float2* gout = nullptr;
+  long long out_stride = 0;
+  const float2* out_mul = nullptr;
+  int nvalid = 0;
+};
+
 // One radix stage over a tile: src / dst are tile[n * LP + lane].
-template <int R, bool INV>
+template <int R, bool INV, bool GIN, bool GOUT>
 __device__ __forceinline__ void gen_stage(int N, int Ns, int L, int lsh, int LP, const float2* __restrict__ tw,
-                                          const float2* __restrict__ src, float2* __restrict__ dst) {
+                                          const float2* __restrict__ src, float2* __restrict__ dst, const GenIO& io) {
   const int nb = N / R;
   const int step = N / (Ns * R);
   const int items = nb << lsh;
@@ -117,9 +142,20 @@ __device__ __forceinline__ void gen_stage(int N, int Ns, int L, int lsh, int LP,
     const int lane = w & (L - 1), j = w >> lsh;
     const int k = Ns == 1 ? 0 : j % Ns;
     float2 v[R];
-    const float2* sp = src + j * LP + lane;
+    if (GIN) {
+      const bool ok = lane < io.nvalid;
+      const float2* gp = io.gin + (long long)j * io.in_stride + lane;
 #pragma unroll
-    for (int t = 0; t < R; ++t) v[t] = sp[t * nb * LP];
+      for (int t = 0; t < R; ++t) v[t] = ok ? gp[(long long)t * nb * io.in_stride] : make_float2(0.f, 0.f);
+      if (io.in_mul) {
+#pragma unroll
+        for (int t = 0; t < R; ++t) v[t] = cmul2(v[t], io.in_mul[j + t * nb]);
+      }
+    } else {
+      const float2* sp = src + j * LP + lane;
+#pragma unroll
+      for (int t = 0; t < R; ++t) v[t] = sp[t * nb * LP];
+    }
     if (Ns > 1) {
       const int ks = k * step;                 // t * ks < N for t < R: no wrap-around
 #pragma unroll
@@ -130,39 +166,70 @@ __device__ __forceinline__ void gen_stage(int N, int Ns, int L, int lsh, int LP,
       }
     }
     dft_any<R, INV>(v);
-    float2* dp = dst + ((j - k) * R + k) * LP + lane;
+    const int o0 = (j - k) * R + k;
+    if (GOUT) {
+      if (lane < io.nvalid) {
+        float2* gp = io.gout + (long long)o0 * io.out_stride + lane;
 #pragma unroll
-    for (int t = 0; t < R; ++t) dp[t * Ns * LP] = v[t];
+        for (int t = 0; t < R; ++t) {
+          float2 o = v[t];
+          if (io.out_mul) o = cmul2(o, io.out_mul[o0 + t * Ns]);
+          gp[(long long)t * Ns * io.out_stride] = o;
+        }
+      }
+    } else {
+      float2* dp = dst + o0 * LP + lane;
+#pragma unroll
+      for (int t = 0; t < R; ++t) dp[t * Ns * LP] = v[t];
+    }
   }
 }
 
-// The whole line transform of a tile.  First stage reads `src`, stages alternate between b0 and b1 starting with b0;
-// src may be b1 (it is overwritten from the second stage on) but not b0.  Returns the buffer holding the result.
-// Every thread of the CTA must call it; the caller synchronises before (src complete) -- a barrier follows every stage.
-template <bool INV>
-__device__ __noinline__ float2* gen_fft(const GenPlan& pl, int L, int lsh, const float2* src, float2* b0, float2* b1) {
+template <bool INV, bool GIN, bool GOUT>
+__device__ __forceinline__ void gen_stage_any(int r, int N, int Ns, int L, int lsh, int LP, const float2* tw, const float2* in,
+                                              float2* out, const GenIO& io) {
+  switch (r) {
+    case 16: gen_stage<16, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 9: gen_stage<9, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 8: gen_stage<8, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 7: gen_stage<7, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 5: gen_stage<5, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 4: gen_stage<4, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    case 3: gen_stage<3, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+    default: gen_stage<2, INV, GIN, GOUT>(N, Ns, L, lsh, LP, tw, in, out, io); break;
+  }
+}
+
+// The whole line transform of a tile.  First stage reads `src` (or io.gin when GIN), stages alternate between b0 and b1
+// starting with b0; src may be b1 (it is overwritten from the second stage on) but not b0.  Returns the buffer holding
+// the result (nullptr when GOUT: the last stage wrote to io.gout).  Every thread of the CTA must call it; the caller
+// synchronises before (src complete) -- a barrier follows every stage that wrote shared memory.
+template <bool INV, bool GIN, bool GOUT>
+__device__ __noinline__ float2* gen_fft_io(const GenPlan& pl, int L, int lsh, const float2* src, float2* b0, float2* b1,
+                                           const GenIO& io) {
   const int LP = L + 1;
   int Ns = 1;
   const float2* in = src;
   float2* out = b0;
   for (int s = 0; s < pl.ns; ++s) {
     const int r = pl.radix[s];
-    switch (r) {
-      case 16: gen_stage<16, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 9: gen_stage<9, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 8: gen_stage<8, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 7: gen_stage<7, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 5: gen_stage<5, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 4: gen_stage<4, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      case 3: gen_stage<3, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-      default: gen_stage<2, INV>(pl.N, Ns, L, lsh, LP, pl.tw, in, out); break;
-    }
-    __syncthreads();
+    const bool gi = GIN && s == 0, go = GOUT && s == pl.ns - 1;
+    bool done = false;
+    if constexpr (GIN && GOUT) { if (gi && go) { gen_stage_any<INV, true, true>(r, pl.N, Ns, L, lsh, LP, pl.tw, in, out, io); done = true; } }
+    if constexpr (GIN) { if (!done && gi) { gen_stage_any<INV, true, false>(r, pl.N, Ns, L, lsh, LP, pl.tw, in, out, io); done = true; } }
+    if constexpr (GOUT) { if (!done && go) { gen_stage_any<INV, false, true>(r, pl.N, Ns, L, lsh, LP, pl.tw, in, out, io); done = true; } }
+    if (!done) gen_stage_any<INV, false, false>(r, pl.N, Ns, L, lsh, LP, pl.tw, in, out, io);
+    if (!go) __syncthreads();
     Ns *= r;
     in = out;
     out = (out == b0) ? b1 : b0;
   }
-  return const_cast<float2*>(in);
+  return GOUT ? nullptr : const_cast<float2*>(in);
+}
+template <bool INV>
+__device__ __forceinline__ float2* gen_fft(const GenPlan& pl, int L, int lsh, const float2* src, float2* b0, float2* b1) {
+  GenIO io;
+  return gen_fft_io<INV, false, false>(pl, L, lsh, src, b0, b1, io);
 }
 
 __device__ __forceinline__ float kappa_rt(int poly, float a2) {
@@ -218,7 +285,7 @@ __device__ __forceinline__ void g3_load_h(const GParams& G, const float2* __rest
 // y forward: packed row pairs -> half spectrum.  grid (tiles, planes, ncomp)
 // MODE 0 pressure; 1 velocity (comp 0: x multiplier i kx e^{-i kx dx/2}, comp 1: y multiplier); 2 source slab; 3 absorption operands
 template <int MODE>
-__global__ void __launch_bounds__(256) g3_y_fwd(StepParams P, GParams G) {
+__global__ void G3_LB_S g3_y_fwd(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls, LP = L + 1;
   const int kx0 = blockIdx.x * L, z = blockIdx.y, comp = blockIdx.z;
@@ -243,23 +310,18 @@ __global__ void __launch_bounds__(256) g3_y_fwd(StepParams P, GParams G) {
     if (2 * m + 1 < G.Ny) b1[(2 * m + 1) * LP + lane] = b2;
   }
   __syncthreads();
-  const float2* cur = gen_fft<false>(G.py, L, G.lsh_s, b1, b0, b1);
-  float2* hp = Hout + (long long)z * G.Ny * G.PH;
-  const int items2 = G.Ny << G.lsh_s;
-  for (int w = threadIdx.x; w < items2; w += blockDim.x) {
-    const int lane = w & (L - 1), ky = w >> G.lsh_s;
-    const int kx = kx0 + lane;
-    if (kx >= G.Nxh) continue;
-    float2 o = cur[ky * LP + lane];
-    if (MODE == 1 && comp == 1) o = cmul2(o, P.dny[ky]);
-    hp[(long long)ky * G.PH + kx] = o;
-  }
+  GenIO io;
+  io.gout = Hout + (long long)z * G.Ny * G.PH + kx0;
+  io.out_stride = G.PH;
+  io.out_mul = (MODE == 1 && comp == 1) ? P.dny : nullptr;
+  io.nvalid = min(L, G.Nxh - kx0);
+  gen_fft_io<false, false, true>(G.py, L, G.lsh_s, b1, b0, b1, io);
 }
 
 // z pass of the pressure gradient, out of place: H4[0] -> H4[2] = IFFT_z[kappa FFT_z p^] (blockIdx.z = 0) and
 // H4[1] = IFFT_z[i kz e^{+i kz dz/2} kappa FFT_z p^] (blockIdx.z = 1).  grid (tiles, Ny, 2): the two chains run in
 // different CTAs (the second read of the column tile hits L2), two tile buffers each.
-__global__ void __launch_bounds__(256) g3_z_grad(StepParams P, GParams G) {
+__global__ void G3_LB_S g3_z_grad(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls, LP = L + 1;
   const int kx0 = blockIdx.x * L, ky = blockIdx.y, pass = blockIdx.z;
@@ -268,9 +330,13 @@ __global__ void __launch_bounds__(256) g3_z_grad(StepParams P, GParams G) {
   const long long zs = (long long)G.Ny * G.PH;
   const float2* col = G.H4 + (long long)ky * G.PH;
   const int items = G.Nz << G.lsh_s;
-  g3_load_h(G, col, zs, G.Nz, kx0, b1, nullptr);
-  __syncthreads();
-  float2* cur = gen_fft<false>(G.pz, L, G.lsh_s, b1, b0, b1);
+  GenIO io;
+  io.gin = col + kx0;
+  io.in_stride = zs;
+  io.gout = G.H4 + (pass == 1 ? G.HS : 2 * G.HS) + (long long)ky * G.PH + kx0;
+  io.out_stride = zs;
+  io.nvalid = min(L, G.Nxh - kx0);
+  float2* cur = gen_fft_io<false, true, false>(G.pz, L, G.lsh_s, b1, b0, b1, io);
   for (int w = threadIdx.x; w < items; w += blockDim.x) {
     const int lane = w & (L - 1), kz = w >> G.lsh_s;
     const int kx = min(kx0 + lane, G.Nxh - 1);
@@ -281,19 +347,12 @@ __global__ void __launch_bounds__(256) g3_z_grad(StepParams P, GParams G) {
   }
   __syncthreads();
   float2* other = cur == b0 ? b1 : b0;
-  const float2* res = gen_fft<true>(G.pz, L, G.lsh_s, cur, other, cur);
-  float2* out = G.H4 + (pass == 1 ? G.HS : 2 * G.HS) + (long long)ky * G.PH;
-#pragma unroll 4
-  for (int w = threadIdx.x; w < items; w += blockDim.x) {
-    const int lane = w & (L - 1), zz = w >> G.lsh_s;
-    const int kx = kx0 + lane;
-    if (kx < G.Nxh) out[(long long)zz * zs + kx] = res[zz * LP + lane];
-  }
+  gen_fft_io<true, false, true>(G.pz, L, G.lsh_s, cur, other, cur, io);
 }
 
 // y inverse of the three gradient components + row-pair merge.  grid (tiles, Nz, 3), component = blockIdx.z
 //   Z4[0] <- i kx e^{+i kx dx/2} IFFT_y[H4[2]];  Z4[1] <- IFFT_y[i ky e^{+i ky dy/2} H4[2]];  Z4[2] <- IFFT_y[H4[1]]
-__global__ void __launch_bounds__(256) g3_y_inv_grad(StepParams P, GParams G) {
+__global__ void G3_LB_S g3_y_inv_grad(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls;
   const int kx0 = blockIdx.x * L, z = blockIdx.y, c = blockIdx.z;
@@ -301,29 +360,34 @@ __global__ void __launch_bounds__(256) g3_y_inv_grad(StepParams P, GParams G) {
   float2* b1 = gen_buf(smraw, G.Ny, L, 1);
   const float2* hp = G.H4 + (long long)z * G.Ny * G.PH;
   float2* zp = G.Z4 + (long long)z * G.My * G.Nx;
-  g3_load_h(G, hp + (c == 2 ? G.HS : 2 * G.HS), G.PH, G.Ny, kx0, b1, c == 1 ? P.dpy : nullptr);
-  __syncthreads();
-  const float2* cur = gen_fft<true>(G.py, L, G.lsh_s, b1, b0, b1);
+  GenIO io;
+  io.gin = hp + (c == 2 ? G.HS : 2 * G.HS) + kx0;
+  io.in_stride = G.PH;
+  io.in_mul = c == 1 ? P.dpy : nullptr;
+  io.nvalid = min(L, G.Nxh - kx0);
+  const float2* cur = gen_fft_io<true, true, false>(G.py, L, G.lsh_s, b1, b0, b1, io);
   g3_merge_store(G, cur, zp + c * G.ZS, kx0, c == 0, P.dpx);
 }
 
 // y inverse + row-pair merge of H4[comp] -> Z4[comp].  grid (tiles, Nz, ncomp)
-__global__ void __launch_bounds__(256) g3_y_inv(StepParams P, GParams G) {
+__global__ void G3_LB_S g3_y_inv(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls;
   const int kx0 = blockIdx.x * L, z = blockIdx.y, comp = blockIdx.z;
   float2* b0 = gen_buf(smraw, G.Ny, L, 0);
   float2* b1 = gen_buf(smraw, G.Ny, L, 1);
-  g3_load_h(G, G.H4 + comp * G.HS + (long long)z * G.Ny * G.PH, G.PH, G.Ny, kx0, b1, nullptr);
-  __syncthreads();
-  const float2* cur = gen_fft<true>(G.py, L, G.lsh_s, b1, b0, b1);
+  GenIO io;
+  io.gin = G.H4 + comp * G.HS + (long long)z * G.Ny * G.PH + kx0;
+  io.in_stride = G.PH;
+  io.nvalid = min(L, G.Nxh - kx0);
+  const float2* cur = gen_fft_io<true, true, false>(G.py, L, G.lsh_s, b1, b0, b1, io);
   g3_merge_store(G, cur, G.Z4 + comp * G.ZS + (long long)z * G.My * G.Nx, kx0, false, nullptr);
 }
 
 // z pass, in place, of (OP 0) the velocity divergence comps 0..2 [+ comp 3 = source field read from its slab, cos filter]
 // and (OP 1) the two absorption operands (fractional Laplacians k^(y-2), k^(y-1)).  grid (tiles, Ny, ncomp)
 template <int OP>
-__global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G) {
+__global__ void G3_LB_S g3_z_pass(StepParams P, GParams G) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int L = G.Ls, LP = L + 1;
   const int kx0 = blockIdx.x * L, ky = blockIdx.y;
@@ -343,11 +407,20 @@ __global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G) {
         if (kx < G.Nxh && zr >= 0 && zr < G.nzs) v = sp[(long long)zr * zs + kx];
         b1[zz * LP + lane] = v;
       }
-    } else {
-      g3_load_h(G, col, zs, G.Nz, kx0, b1, nullptr);
     }
-    __syncthreads();
-    float2* cur = gen_fft<false>(G.pz, L, G.lsh_s, b1, b0, b1);
+    GenIO io;
+    io.gin = col + kx0;
+    io.in_stride = zs;
+    io.gout = col + kx0;
+    io.out_stride = zs;
+    io.nvalid = min(L, G.Nxh - kx0);
+    float2* cur;
+    if (OP == 0 && comp == 3) {
+      __syncthreads();
+      cur = gen_fft<false>(G.pz, L, G.lsh_s, b1, b0, b1);
+    } else {
+      cur = gen_fft_io<false, true, false>(G.pz, L, G.lsh_s, b1, b0, b1, io);
+    }
     for (int w = threadIdx.x; w < items; w += blockDim.x) {
       const int lane = w & (L - 1), kz = w >> G.lsh_s;
       const int kx = min(kx0 + lane, G.Nxh - 1);
@@ -368,13 +441,7 @@ __global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G) {
     }
     __syncthreads();
     float2* other = cur == b0 ? b1 : b0;
-    const float2* res = gen_fft<true>(G.pz, L, G.lsh_s, cur, other, cur);
-#pragma unroll 4
-    for (int w = threadIdx.x; w < items; w += blockDim.x) {
-      const int lane = w & (L - 1), zz = w >> G.lsh_s;
-      const int kx = kx0 + lane;
-      if (kx < G.Nxh) col[(long long)zz * zs + kx] = res[zz * LP + lane];
-    }
+    gen_fft_io<true, false, true>(G.pz, L, G.lsh_s, cur, other, cur, io);
   }
 }
 
@@ -385,16 +452,27 @@ __global__ void __launch_bounds__(256) g3_z_pass(StepParams P, GParams G) {
 // Everything that has to outlive a transform (the source field, the du components, the partial pressure sum) is parked in
 // global scratch rows owned by the same thread (P.Sf, P.r3, P.r1): they are re-read from L2 a few microseconds later,
 // which is cheaper than a third, fourth and fifth tile buffer in shared memory (one CTA per SM).
+__device__ __forceinline__ void cp_async8(void* sdst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+// Lines of a pair batch -> tile (transposing).  cp.async copies of 8 bytes: every thread has its whole share of the tile
+// in flight at once (no registers involved), which is what the memory system needs to stream -- the plain load / store
+// loop it replaces kept 4 loads per thread in flight.  The caller's __syncthreads() follows.
 __device__ __forceinline__ void g3_x_load(const GParams& G, int L, const float2* __restrict__ zfield, int q0, int nq,
                                           float2* __restrict__ dst) {
   const int LP = L + 1;
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int lane = wid; lane < L; lane += nw) {
     const float2* zp = zfield + (long long)(q0 + lane) * G.Nx;
-    const bool ok = lane < nq;
-#pragma unroll 4
-    for (int x = ln; x < G.Nx; x += 32) dst[x * LP + lane] = ok ? zp[x] : make_float2(0.f, 0.f);
+    if (lane < nq) {
+      for (int x = ln; x < G.Nx; x += 32) cp_async8(dst + x * LP + lane, zp + x);
+    } else {
+      for (int x = ln; x < G.Nx; x += 32) dst[x * LP + lane] = make_float2(0.f, 0.f);
+    }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
 }
 __device__ __forceinline__ void g3_x_store(const GParams& G, int L, float2* __restrict__ zfield, int q0, int nq,
                                            const float2* __restrict__ src) {
@@ -402,7 +480,7 @@ __device__ __forceinline__ void g3_x_store(const GParams& G, int L, float2* __re
   const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int lane = wid; lane < nq; lane += nw) {
     float2* zp = zfield + (long long)(q0 + lane) * G.Nx;
-#pragma unroll 4
+#pragma unroll 8
     for (int x = ln; x < G.Nx; x += 32) zp[x] = src[x * LP + lane];
   }
 }
@@ -418,7 +496,7 @@ __device__ __forceinline__ void g3_pair(const GParams& G, int q, int& z, int& yl
 // IFFT_x of one gradient component (blockIdx.y), u = pml_sg (pml_sg u - dt/rho0_sg dp), FFT_x of the new u.
 // grid (pair batches, 3)
 template <bool HOMOG>
-__global__ void __launch_bounds__(512) g3_x_u(StepParams P, GParams G, int L, int lsh) {
+__global__ void G3_LB_X g3_x_u(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
@@ -438,7 +516,7 @@ __global__ void __launch_bounds__(512) g3_x_u(StepParams P, GParams G, int L, in
     float2 s = make_float2(1.f, 1.f);
     if (c == 1) s = make_float2(P.sgy[ylo], hh ? P.sgy[ylo + 1] : 0.f);
     else if (c == 2) s.x = s.y = P.sgz[z];
-#pragma unroll 2
+#pragma unroll 4
     for (int x = ln; x < N; x += 32) {
       if (c == 0) s.x = s.y = P.sgx[x];
       float2 d;
@@ -483,7 +561,7 @@ __device__ __forceinline__ void g3_sensor(const StepParams& P, const GParams& G,
 // SRC: 0 none, 1 filtered source spectrum in Z4[3], 2 unfiltered dense slab.  ABS: absorbing medium (see fft_v2.cuh).
 // Two tile buffers; the source rows live in P.Sf, the du rows (ABS) in P.r3, the density rows are re-read for the sum.
 template <bool HOMOG, int SRC, bool ABS>
-__global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G, int L, int lsh) {
+__global__ void G3_LB_X g3_x_rho_p(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
@@ -521,7 +599,7 @@ __global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G, int L
       const int zr = z - G.z0s;
       const bool sin_ = SRC == 2 && zr >= 0 && zr < G.nzs;
       const float* srow = SRC == 2 ? G.Sslab + ((long long)zr * G.Ny + ylo) * N : nullptr;
-#pragma unroll 2
+#pragma unroll 4
       for (int x = ln; x < N; x += 32) {
         if (c == 0) a.x = a.y = P.pmlx[x];
         float2 d;
@@ -548,7 +626,7 @@ __global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G, int L
       g3_pair(G, q0 + lane, z, ylo, hh, r0);
       const float* f0 = (pass == 0 ? P.r3 : P.rho) + r0;
       const float* mrow = HOMOG ? nullptr : P.dt_rho0 + r0;
-#pragma unroll 2
+#pragma unroll 4
       for (int x = ln; x < N; x += 32) {
         float2 sm = cadd(cadd(make_float2(f0[x], hh ? f0[N + x] : 0.f),
                               make_float2(f0[P.RS + x], hh ? f0[P.RS + N + x] : 0.f)),
@@ -583,7 +661,7 @@ __global__ void __launch_bounds__(512) g3_x_rho_p(StepParams P, GParams G, int L
 // Absorbing medium, last pass: p = c0^2 (sum rho + tau L1 - eta L2), sensor, FFT_x of p -> ZP.  Two tile buffers; the
 // partial sum (sum rho + tau L1) waits in P.r3[0] while the second operand is transformed.
 template <bool HOMOG>
-__global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int L, int lsh, int use_tau, int use_eta) {
+__global__ void G3_LB_X g3_x_p(StepParams P, GParams G, int L, int lsh, int use_tau, int use_eta) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);
@@ -600,7 +678,7 @@ __global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int L, in
       if (lane >= nq) { if (c == 1) for (int x = ln; x < N; x += 32) cur[x * LP + lane] = make_float2(0.f, 0.f); continue; }
       int z, ylo; bool hh; long long r0;
       g3_pair(G, q0 + lane, z, ylo, hh, r0);
-#pragma unroll 2
+#pragma unroll 4
       for (int x = ln; x < N; x += 32) {
         const float2 v = cur[x * LP + lane];
         if (c == 0) {
@@ -632,7 +710,7 @@ __global__ void __launch_bounds__(512) g3_x_p(StepParams P, GParams G, int L, in
 }
 
 // x forward of the dense source slab (row pairs of the slab planes).  grid = pair batches of the slab
-__global__ void __launch_bounds__(512) g3_x_src(StepParams P, GParams G, int L, int lsh) {
+__global__ void G3_LB_X g3_x_src(StepParams P, GParams G, int L, int lsh) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int LP = L + 1, N = G.Nx;
   float2* b0 = gen_buf(smraw, N, L, 0);

@@ -1125,9 +1125,12 @@ static int enqueue_step_v2(lifu_sim* s, int kind, int* n_kernels, const std::fun
 // pipeline v3: the same fused passes for any 2/3/5/7-smooth axis length (fft_gen.cuh)
 static bool gen_factor(int n, int* radix, int* ns) {
   static const int cand[8] = {16, 9, 8, 7, 5, 4, 3, 2};
+  const char* rm = getenv("LIFU_V3_RMAX");                  // tuning: largest radix allowed (e.g. 8)
+  const int rmax = (rm && rm[0]) ? atoi(rm) : 16;
   int k = 0;
   for (int c = 0; c < 8 && n > 1; ++c) {
     const int r = cand[c];
+    if (r > rmax) continue;
     while (n % r == 0 && n > 1) {
       if (r == 16 && n / 16 == 2) break;          // 32 -> 8 x 4 rather than 16 x 2
       if (k >= 8) return false;
@@ -1209,7 +1212,7 @@ static int v3_setup(lifu_sim* s) {
     if (o == 1 || o == 2 || o == 4 || o == 8 || o == 16) G.Lx = v3_lanes(Nx, 2, kV3SmemCap, o);
   }
   G.lsh_x = 0; while ((1 << G.lsh_x) < G.Lx) ++G.lsh_x;
-  s->v3_ts = std::min(256, std::max(64, env_int("LIFU_V3_TS", 256) / 32 * 32));
+  s->v3_ts = std::min(512, std::max(64, env_int("LIFU_V3_TS", 256) / 32 * 32));
   s->v3_tx = std::min(512, std::max(64, env_int("LIFU_V3_TX", 256) / 32 * 32));
   int z0 = 0, nz = 1;
   if (s->n_src > 0) {

@@ -160,12 +160,11 @@ int lifu_stack_put(lifu_stack* k, int32_t focus, lifu_sim* s) {
   return LIFU_OK;
 }
 
-int lifu_stack_scale(lifu_stack* k, int32_t focus, double s) {
+int lifu_stack_scale(lifu_stack* k, int32_t focus, double s, double s2) {
   if (!k || focus < 0 || focus >= k->n_foci) { set_error("lifu_stack_scale: bad argument"); return LIFU_ERR_INVALID; }
   if (!k->filled[focus]) { set_error("lifu_stack_scale: focus %d has no fields yet", focus); return LIFU_ERR_STATE; }
   LIFU_CUDA(cudaSetDevice(k->device));
   const size_t off = (size_t)focus * (size_t)k->V;
-  const volatile double s2 = s * s;                     // `s ** 2` of the host expression, rounded once
   k_stack_scale<<<k->blocks, 256, 0, k->stream>>>(k->d_pmax + off, k->d_pnp + off, k->d_int + off, k->V, s, s2);
   LIFU_CUDA(cudaGetLastError());
   LIFU_CUDA(cudaStreamSynchronize(k->stream));

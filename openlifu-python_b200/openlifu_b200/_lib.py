@@ -131,7 +131,7 @@ def load():
         "lifu_stack_create": (C.c_int, [C.c_int, vp, C.POINTER(i32), i32, C.POINTER(vp)]),
         "lifu_stack_destroy": (C.c_int, [vp]),
         "lifu_stack_put": (C.c_int, [vp, i32, vp]),
-        "lifu_stack_scale": (C.c_int, [vp, i32, f64]),
+        "lifu_stack_scale": (C.c_int, [vp, i32, f64, f64]),
         "lifu_stack_pointers": (C.c_int, [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
         "lifu_stack_get": (C.c_int, [vp, i32, vp, vp, vp]),
         "lifu_stack_aggregate": (C.c_int, [vp, vp, vp, vp]),
@@ -559,8 +559,10 @@ class FieldStack:
         """Package the last run of ``sim`` (which needs ``set_two_z``) into slot ``focus``."""
         _check(self._lib.lifu_stack_put(self._h, int(focus), sim._h))
 
-    def scale(self, focus, s):
-        _check(self._lib.lifu_stack_scale(self._h, int(focus), float(s)))
+    def scale(self, focus, s, s2=None):
+        """pressures *= s, intensity *= s2 (default ``s ** 2`` evaluated on ``s`` as given, e.g. a numpy float64)."""
+        s2 = s ** 2 if s2 is None else s2
+        _check(self._lib.lifu_stack_scale(self._h, int(focus), float(s), float(s2)))
 
     def pointers(self, focus):
         """(p_max, pnp, intensity) device pointers of one focus, and the element strides of (x, y, z)."""

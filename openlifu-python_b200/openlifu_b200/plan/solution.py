@@ -427,7 +427,7 @@ class Solution:
         for i in range(self.num_foci()):
             s = v1 / v0 * apod_factors[i]
             if stack is not None:
-                stack.scale(i, s)            # same IEEE operations on the device-resident fields (csrc/stack.cu)
+                stack.scale(i, s, s ** 2)    # same IEEE operations on the device-resident fields (csrc/stack.cu)
             else:
                 self.simulation_result["p_min"][i].data *= s
                 self.simulation_result["p_max"][i].data *= s

@@ -217,7 +217,7 @@ def test_field_stack_errors_and_numpy_semantics(lifu_lib):
             st.put(f, sim)
             pm = p_max.reshape(N, order="F")
             pn = (-1 * p_min).reshape(N, order="F")
-            it = ((np.float32(1e-4) * p_min ** 2) / (2 * 1000.0 * 1500.0)).reshape(N, order="F")
+            it = ((np.float32(1e-4) * p_min ** 2) / np.float64(2 * 1000.0 * 1500.0)).reshape(N, order="F")
             host.append([pm.copy(), pn.copy(), it.copy()])
             if f < 2:
                 with pytest.raises(_lib.LifuError, match="no fields yet"):

@@ -65,9 +65,22 @@ def main():
                          **{k: round(v, 3) for k, v in T.items()}}
         results[engine] = ana
         if engine != "host":
-            fields[engine] = (sol.simulation_result, agg)
-    same = all(np.array_equal(fields["cuda"][j][k].data, fields["plan_on_device"][j][k].data)
-               for j in (0, 1) for k in ("p_max", "p_min", "intensity"))
+            fields.setdefault(engine, []).append((sol.simulation_result, agg, sol.voltage, sol.apodizations.copy()))
+    def diff(a, b):
+        out = {}
+        for j, tag in ((0, "stack"), (1, "aggregated")):
+            for k in ("p_max", "p_min", "intensity"):
+                x, y = np.asarray(a[j][k].data), np.asarray(b[j][k].data)
+                ne = x != y
+                if ne.any():
+                    out[f"{tag}.{k}"] = {"differing": int(ne.sum()), "max_rel": float(np.max(np.abs(x[ne] - y[ne]) / np.abs(y[ne]).clip(1e-300)))}
+        if a[2] != b[2] or not np.array_equal(a[3], b[3]):
+            out["voltage/apod"] = [float(a[2]), float(b[2])]
+        return out
+    d_route = diff(fields["plan_on_device"][-1], fields["cuda"][-1])
+    d_repeat_host = diff(fields["cuda"][0], fields["cuda"][-1])
+    d_repeat_dev = diff(fields["plan_on_device"][0], fields["plan_on_device"][-1])
+    same = not d_route
     a, b = results["cuda"], results["host"]
     worst = 0.0
     for k, v in b.__dict__.items():
@@ -81,6 +94,8 @@ def main():
         worst = max(worst, float(d.max()) if d.size else 0.0)
     print(json.dumps({"workload": f"C4-class: C2 grid ({n_inner}^3 inner), Wheel with {spokes} spokes + centre, calc_solution(scale=True)",
                       "plan_on_device": lines["plan_on_device"], "plan_on_device_bit_identical_to_host_route": bool(same),
+                      "differences": {"device_vs_host_route": d_route, "host_route_run_to_run": d_repeat_host,
+                                      "device_route_run_to_run": d_repeat_dev},
                       "analysis_on_device": lines["cuda"], "analysis_on_host": lines["host"],
                       "max_rel_diff_between_engines": worst, "host_cores": os.cpu_count()}))
 
