@@ -639,7 +639,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         prof = sim.profile_stages(reps=8, with_source=True)
-        own = [(n, ms, b) for n, ms, b in prof if n.startswith(("k_", "k2_")) and b > 0]
+        own = [(n, ms, b) for n, ms, b in prof if n.startswith(("k_", "k2_", "g3_")) and b > 0]
         tot = sum(ms for _, ms, _ in prof)
         name, ms, bpv = max(own, key=lambda r: r[1])
         ach = bpv * V / (ms * 1e-3) / 1e9

@@ -20,8 +20,11 @@
 //   Z layout    Z[z][m][kx], m < My = ceil(Ny / 2), kx < Nx : x-spectrum of the ROW PAIR row(2m) + i row(2m+1) (a missing
 //               second row of an odd Ny is zero)
 //   H layout    H[z][ky][kx], kx <= Nx/2, row pitch PH        half spectrum
-// Strided (y, z) passes work on tiles of L consecutive kx (global accesses of L * 8 contiguous bytes); x passes on batches
-// of L row pairs, transposed into the same tile layout on the way in and out (row pitch L + 1 keeps that conflict free).
+// Strided (y, z) passes work on tiles of L consecutive kx (global accesses of L * 8 contiguous bytes); their first radix
+// stage reads the column tile straight from global memory (R independent loads per work item) and their last stage writes
+// straight back (GenIO), so only the stages in between and the point-wise spectral operators touch shared memory.  x
+// passes work on batches of L row pairs, moved into the same tile layout with 8-byte cp.async copies (row pitch L + 1 keeps
+// the transposition conflict free); what has to outlive a transform there is parked in global scratch rows (re-read from L2).
 #pragma once
 #include "fft_v2.cuh"
 

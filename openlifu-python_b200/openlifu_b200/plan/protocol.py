@@ -336,6 +336,8 @@ class Protocol:
         """Can the whole plan stay on one GPU?  (stock ``run_simulation``, one process, one worker device)"""
         if not use_gpu or run_simulation is not kwave_if.run_simulation:
             return False
+        if os.environ.get("LIFU_ANALYZE", "cuda") == "host" or kwave_if.multi_gpu_mode()[0] == "slab":
+            return False                    # the device route analyses on the device and needs one whole grid per GPU
         if _dist_world()[0] > 1:
             return False
         return n_foci <= 1 or _visible_devices() <= 1 or os.environ.get("LIFU_FOCI_GPUS", "") == "1"
@@ -366,10 +368,11 @@ class Protocol:
         """Delays/apodizations per focus, simulated fields, scaling to the target pressure and
         the beam analysis (reference semantics, protocol.py:242-398).
 
-        ``on_device`` (not in the reference; ``None`` -> ``$LIFU_PLAN_ON_DEVICE`` == "1"): keep the fields of every
-        focus in HBM from the solver through stacking, ``Solution.scale``, the aggregation over foci and both beam
+        ``on_device`` (not in the reference; ``None`` -> on unless ``$LIFU_PLAN_ON_DEVICE`` == "0"): keep the fields of
+        every focus in HBM from the solver through stacking, ``Solution.scale``, the aggregation over foci and both beam
         analyses (``_lib.FieldStack``, csrc/stack.cu), and copy the finished stack to the host once.  Same numbers, bit
-        for bit, as the host route (tests/test_gpu_api.py); used when one GPU runs the whole plan."""
+        for bit, as the host route (tests/test_gpu_api.py); applies when one GPU runs the whole plan (one process, one
+        worker device, stock ``run_simulation``), otherwise the host route is taken."""
         if use_gpu is None:
             use_gpu = gpu_available()
             if not use_gpu and simulate:
@@ -393,7 +396,7 @@ class Protocol:
             self.logger.info(f"Beamform for focus {focus}...")
             beams.append(self.beamform(arr=transducer, target=focus, params=params))
         if on_device is None:
-            on_device = os.environ.get("LIFU_PLAN_ON_DEVICE", "0") == "1"
+            on_device = os.environ.get("LIFU_PLAN_ON_DEVICE", "1") != "0"
         stacked = xa.Dataset()
         stack = None
         if simulate and on_device and self._on_device_ok(use_gpu, len(foci)):
