@@ -324,6 +324,37 @@ __global__ void __launch_bounds__(16 * R, R == 16 ? 2 : 4) k2_y_inv_grad(StepPar
   merge_store<R>(zp + 2 * Q.ZS, a, kx, Q.Nx, true);
 }
 
+// The same three gradient components with one component per CTA (grid (nxt+1, Nz, 3)): 80 registers, three CTAs per SM,
+// no serial chain of three transforms inside a CTA; components 0 and 1 both read H4[0] (the second read hits L2).
+// LIFU_V2_YGRAD=split selects it (profiles/r2_ygrad_split.md).
+template <int R>
+__global__ void __launch_bounds__(16 * R, R == 16 ? 3 : 6) k2_y_inv_grad_split(StepParams P, V2Params Q) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using S = Strided<R>;
+  const int l = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int comp = blockIdx.z;
+  int kx, z;
+  if (!lane_map(Q, Q.Nz, l, kx, z)) return;
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  const float2* hp = Q.H4 + (comp == 2 ? Q.HS : 0) + ((long long)z * Q.Ny + t) * Q.PH + kx;      // ky = t + R*k1
+  const int kstep = R * Q.PH;
+  float2 a[R];
+#pragma unroll
+  for (int k1 = 0; k1 < R; ++k1) a[k1] = hp[k1 * kstep];
+  const float4* tw = S::load_tw(smraw, 1, Q.tw4y);
+  if (comp == 1) {
+#pragma unroll
+    for (int k1 = 0; k1 < R; ++k1) a[k1] = cmul4(a[k1], Q.dpy4[t + R * k1]);
+  }
+  strided_fft<R, true>(a, tw, xa, l, t);
+  if (comp == 0) {
+    const float4 mx = with_i(P.dpx[kx]);
+#pragma unroll
+    for (int j = 0; j < R; ++j) a[j] = cmul4(a[j], mx);
+  }
+  merge_store<R>(Q.Z4 + comp * Q.ZS + ((long long)z * (Q.Ny / 2) + t) * Q.Nx, a, kx, Q.Nx, true);
+}
+
 // z pass of the velocity divergence (comp 0..2, in place) and of the source field (comp 3).
 // grid (nxt+1, Ny); the CTA walks the components with the loads of component c+1 in flight while component
 // c is transformed (register double buffer), so HBM stays busy through the FFT phases; kappa is evaluated

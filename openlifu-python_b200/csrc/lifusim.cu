@@ -881,6 +881,8 @@ static int v2_setup(lifu_sim* s) {
     Q.xrev = o & 1; Q.zmajor = (o >> 1) & 1;
     const char* pa = getenv("LIFU_PM_ALWAYS");
     Q.pm_always = (pa && pa[0] == '1') ? 1 : 0;
+    const char* yg = getenv("LIFU_V2_YGRAD");
+    s->v2_ygrad_split = yg && !strcmp(yg, "split");
   }
   // TMA descriptors of the z passes.  Opt-in (LIFU_Z_TMA=1): on C2 the persistent TMA-fed kernels measure 3 % slower
   // than the per-thread-load kernels (profiles/r1_z_tma.md) -- the z passes are bound by their two 256-point
@@ -1066,7 +1068,8 @@ static int enqueue_step_v2(lifu_sim* s, int kind, int* n_kernels, const std::fun
   else if (poly == 1) V2_R(Rz, (v2_launch(k2_z_grad<RR, 1>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
   else V2_R(Rz, (v2_launch(k2_z_grad<RR, 0>, dim3(zx, Q.Ny), 16 * RR, Strided<RR>::smem(2), st, s->P, Qn)));
   ++nk; mark("k2_z_grad", 12);
-  V2_R(Ry, (v2_launch(k2_y_inv_grad<RR>, dim3(tx, Q.Nz), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
+  if (s->v2_ygrad_split) V2_R(Ry, (v2_launch(k2_y_inv_grad_split<RR>, dim3(tx, Q.Nz, 3), 16 * RR, Strided<RR>::smem(1), st, s->P, Q)));
+  else V2_R(Ry, (v2_launch(k2_y_inv_grad<RR>, dim3(tx, Q.Nz), 16 * RR, Strided<RR>::smem(2), st, s->P, Q)));
   ++nk; mark("k2_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
   V2_R(Rx, (v2_launch_x_u<RR>(s, gx)));

@@ -108,6 +108,7 @@ struct lifu_sim {
   unsigned char tmH[128] __attribute__((aligned(64))) = {};   // CUtensorMap of H4[comp][z][ky][kx]
   unsigned char tmS[128] __attribute__((aligned(64))) = {};   // CUtensorMap of the source slab spectrum
   bool last_used_v2 = false;
+  bool v2_ygrad_split = false; // gradient y-inverse with one component per CTA (LIFU_V2_YGRAD=split)
   float* d_fk = nullptr;       // steady-state source: [2][RS] filtered basis fields
   float* d_qsrc = nullptr;     // [2][nws] time coefficients
   float* d_qcur = nullptr;     // coefficients of the current step
