@@ -58,9 +58,11 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_bytes(stage):
+def ncu_traffic_bytes(stage, workload=None, weights=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `stage`, from the committed
-    `ncu --set full` capture (profiles/ncu_traffic.json); None when that kernel has not been captured."""
+    `ncu --set full` captures (profiles/ncu_traffic.json); None when that kernel has not been captured.  Captures are
+    labelled by workload; a kernel with several instantiations in one capture (k2_x_rho_p<R, HOMOG, SRC, ABS>: one per
+    source kind) is averaged with `weights` = {SRC value: launches}, otherwise the largest one is reported."""
     f = ROOT / "profiles" / "ncu_traffic.json"
     if not f.exists():
         return None
@@ -68,11 +70,25 @@ def ncu_traffic_bytes(stage):
         ks = json.loads(f.read_text())["kernels"]
     except Exception:  # noqa: BLE001
         return None
-    hits = [v for k, v in ks.items() if k.split("<")[0] == stage]
+    hits = [(k, v) for k, v in ks.items() if k.split("<")[0].split(" [")[0] == stage
+            and (workload is None or str(v.get("capture", "")).startswith(workload))]
+    hits = [(k, v) for k, v in hits if v.get("dram_read_MB") is not None and v.get("dram_write_MB") is not None]
     if not hits:
         return None
-    v = max(hits, key=lambda h: h["dram_read_MB"] + h["dram_write_MB"])
-    return (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6
+    total = lambda v: (v["dram_read_MB"] + v["dram_write_MB"]) * 1e6  # noqa: E731
+    if weights and stage == "k2_x_rho_p":
+        num = den = 0.0
+        for k, v in hits:
+            try:
+                src = int(k.split("<")[1].split(">")[0].split(",")[2])
+            except (IndexError, ValueError):
+                continue
+            w = float(weights.get(src, 0))
+            num += w * total(v)
+            den += w
+        if den > 0:
+            return num / den
+    return max(total(v) for _, v in hits)
 
 
 class ClockSampler:
@@ -667,9 +683,12 @@ def main():
         bpv = acc[name][1] / acc[name][2]                      # mean algorithmic bytes per voxel of a launch
         ach = bpv * V / (ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic_bytes(name), "algorithmic_bytes": bpv * V,
-                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full capture of this kernel, bytes per launch, "
-                                      "largest instantiation)",
+                    "traffic": ncu_traffic_bytes(name, args.workload,
+                                                 {(1 if st.get("fft_launches", 0) == 0 else 1): st["source_steps"] - n_steady,
+                                                  3: n_steady, 0: Nt - st["source_steps"]}),
+                    "algorithmic_bytes": bpv * V,
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full captures of this workload's kernels, DRAM "
+                                      "bytes per launch, averaged over the launches of a simulation)",
                     "peak_source": peak_src, "algorithmic_bytes_per_voxel": bpv,
                     "kernel_ms": ms, "launches_per_simulation": acc[name][2], "share_of_step": acc[name][0] / tot,
                     "step": {"algorithmic_bytes_per_voxel_step": st["bytes_per_voxel_step"],

@@ -237,31 +237,53 @@ int bli_build(lifu_sim* s, int n_el, const double* pos, const double* size, cons
   if (s->Vin >= (1LL << 31)) { set_error("inner grid too large for the source mask scan"); return LIFU_ERR_INVALID; }
 
   cudaStream_t st = s->stream;
-  BliElem* d_el = nullptr; BliPoint* d_bp = nullptr; double* d_pts = nullptr; double* d_tab = nullptr;
-  float* d_wbox = nullptr; unsigned char* d_tbox = nullptr; unsigned char* d_mask = nullptr;
-  long long* d_nsel = nullptr; int* d_cnt = nullptr; void* d_tmp = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(d_el); cudaFree(d_bp); cudaFree(d_pts); cudaFree(d_tab); cudaFree(d_wbox);
-    cudaFree(d_tbox); cudaFree(d_mask); cudaFree(d_nsel); cudaFree(d_cnt); cudaFree(d_tmp);
-  };
+  // Memory.  Rebuilding the geometry is a per-candidate-pose operation (Protocol.simulate_candidates): every cudaMalloc /
+  // cudaFree on a device that holds gigabytes of solver state costs milliseconds to tens of milliseconds and synchronises,
+  // so the temporaries come out of ONE workspace kept on the handle (grown when needed) and the result buffers are
+  // reused while their capacity suffices.
 #define BLI_CUDA(call)                                                                        \
   do {                                                                                        \
     cudaError_t e__ = (call);                                                                 \
     if (e__ != cudaSuccess) {                                                                 \
       set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
-      cleanup();                                                                              \
       return LIFU_ERR_CUDA;                                                                   \
     }                                                                                         \
   } while (0)
   const int TW = 2 * h + 1;
-  BLI_CUDA(cudaMalloc(&d_el, sizeof(BliElem) * n_el));
-  BLI_CUDA(cudaMalloc(&d_bp, sizeof(BliPoint) * n_pts));
-  BLI_CUDA(cudaMalloc(&d_pts, sizeof(double) * 3 * n_pts));
-  BLI_CUDA(cudaMalloc(&d_tab, sizeof(double) * 3 * TW * n_pts));
-  BLI_CUDA(cudaMalloc(&d_wbox, sizeof(float) * std::max<long long>(box_total, 1)));
-  BLI_CUDA(cudaMalloc(&d_tbox, std::max<long long>(box_total, 1)));
-  BLI_CUDA(cudaMalloc(&d_mask, s->Vin));
-  BLI_CUDA(cudaMalloc(&d_nsel, sizeof(long long)));
+  const long long cap = std::max<long long>(std::min<long long>(box_total, s->Vin), 1);   // upper bound on selected points
+  size_t sel_bytes = 0, scan_bytes = 0;
+  cub::CountingInputIterator<long long> counting(0);
+  BLI_CUDA(cub::DeviceSelect::Flagged(nullptr, sel_bytes, counting, (unsigned char*)nullptr, (long long*)nullptr, (long long*)nullptr,
+                                      (int)s->Vin, st));
+  BLI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (int)(cap + 1), st));
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t o_el = 0;
+  const size_t o_bp = o_el + up(sizeof(BliElem) * n_el);
+  const size_t o_pts = o_bp + up(sizeof(BliPoint) * n_pts);
+  const size_t o_tab = o_pts + up(sizeof(double) * 3 * n_pts);
+  const size_t o_wbox = o_tab + up(sizeof(double) * 3 * TW * n_pts);
+  const size_t o_tbox = o_wbox + up(sizeof(float) * std::max<long long>(box_total, 1));
+  const size_t o_mask = o_tbox + up(std::max<long long>(box_total, 1));
+  const size_t o_nsel = o_mask + up(s->Vin);
+  const size_t o_cnt = o_nsel + up(sizeof(long long));
+  const size_t o_tmp = o_cnt + up(sizeof(int) * (cap + 1));
+  const size_t ws_bytes = o_tmp + up(std::max(sel_bytes, scan_bytes));
+  if (ws_bytes > s->bli_ws_cap) {
+    if (s->d_bli_ws) { cudaFree(s->d_bli_ws); s->d_bli_ws = nullptr; s->bli_ws_cap = 0; }
+    BLI_CUDA(cudaMalloc(&s->d_bli_ws, ws_bytes));
+    s->bli_ws_cap = ws_bytes;
+  }
+  char* ws = reinterpret_cast<char*>(s->d_bli_ws);
+  BliElem* d_el = reinterpret_cast<BliElem*>(ws + o_el);
+  BliPoint* d_bp = reinterpret_cast<BliPoint*>(ws + o_bp);
+  double* d_pts = reinterpret_cast<double*>(ws + o_pts);
+  double* d_tab = reinterpret_cast<double*>(ws + o_tab);
+  float* d_wbox = reinterpret_cast<float*>(ws + o_wbox);
+  unsigned char* d_tbox = reinterpret_cast<unsigned char*>(ws + o_tbox);
+  unsigned char* d_mask = reinterpret_cast<unsigned char*>(ws + o_mask);
+  long long* d_nsel = reinterpret_cast<long long*>(ws + o_nsel);
+  int* d_cnt = reinterpret_cast<int*>(ws + o_cnt);
+  void* d_tmp = ws + o_tmp;
   BLI_CUDA(cudaMemcpyAsync(d_el, elems.data(), sizeof(BliElem) * n_el, cudaMemcpyHostToDevice, st));
   BLI_CUDA(cudaMemcpyAsync(d_bp, bps.data(), sizeof(BliPoint) * n_pts, cudaMemcpyHostToDevice, st));
   BLI_CUDA(cudaMemcpyAsync(d_pts, pts.data(), sizeof(double) * 3 * n_pts, cudaMemcpyHostToDevice, st));
@@ -277,54 +299,49 @@ int bli_build(lifu_sim* s, int n_el, const double* pos, const double* size, cons
   BLI_CUDA(cudaGetLastError());
 
   // compact the mask into sorted linear indices (x fastest == matlab_find order)
-  long long* d_idx_tmp = nullptr;
-  size_t tmp_bytes = 0;
-  cub::CountingInputIterator<long long> counting(0);
-  BLI_CUDA(cub::DeviceSelect::Flagged(nullptr, tmp_bytes, counting, d_mask, d_idx_tmp, d_nsel, (int)s->Vin, st));
-  BLI_CUDA(cudaMalloc(&d_tmp, tmp_bytes));
-  // upper bound on selected points: total box voxels
-  long long cap = std::min<long long>(box_total, s->Vin);
-  BLI_CUDA(cudaMalloc(&d_idx_tmp, sizeof(long long) * std::max<long long>(cap, 1)));
-  cudaError_t ce = cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, counting, d_mask, d_idx_tmp, d_nsel, (int)s->Vin, st);
-  long long n_src = 0;
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&n_src, d_nsel, sizeof(long long), cudaMemcpyDeviceToHost, st);
-  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess) { cudaFree(d_idx_tmp); BLI_CUDA(ce); }
-
-  // drop any previous geometry
   s->geometry_set = false;
-  cudaFree(s->d_idx); cudaFree(s->d_row_ptr); cudaFree(s->d_col); cudaFree(s->d_w);
-  cudaFree(s->d_lin_exp); cudaFree(s->d_scale);
-  s->d_idx = nullptr; s->d_row_ptr = nullptr; s->d_col = nullptr; s->d_w = nullptr;
-  s->d_lin_exp = nullptr; s->d_scale = nullptr;
-  s->d_idx = d_idx_tmp;   // over-allocated to `cap`, first n_src valid
+  if (cap > s->idx_cap || !s->d_idx) {
+    if (s->d_idx) { cudaFree(s->d_idx); s->d_idx = nullptr; }
+    if (s->d_row_ptr) { cudaFree(s->d_row_ptr); s->d_row_ptr = nullptr; }
+    s->idx_cap = 0;
+    BLI_CUDA(cudaMalloc(&s->d_idx, sizeof(long long) * cap));
+    BLI_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(int) * (cap + 1)));
+    s->idx_cap = cap;
+  }
+  size_t tmp_bytes = sel_bytes;
+  BLI_CUDA(cub::DeviceSelect::Flagged(d_tmp, tmp_bytes, counting, d_mask, s->d_idx, d_nsel, (int)s->Vin, st));
+  long long n_src = 0;
+  BLI_CUDA(cudaMemcpyAsync(&n_src, d_nsel, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  BLI_CUDA(cudaStreamSynchronize(st));
   s->n_src = n_src;
   s->n_el = n_el;
 
-  BLI_CUDA(cudaMalloc(&d_cnt, sizeof(int) * (n_src + 1)));
-  BLI_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(int) * (n_src + 1)));
   BLI_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * (n_src + 1), st));
   if (n_src > 0) {
     k_bli_rows<false><<<grid_blocks(s, n_src, 128), 128, 0, st>>>(s->d_idx, n_src, d_el, n_el, d_wbox, d_tbox,
                                                                   n[0], n[1], d_cnt, nullptr, nullptr, nullptr);
   }
-  size_t tmp2 = 0;
-  BLI_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, d_cnt, s->d_row_ptr, (int)(n_src + 1), st));
-  if (tmp2 > tmp_bytes) { cudaFree(d_tmp); d_tmp = nullptr; BLI_CUDA(cudaMalloc(&d_tmp, tmp2)); }
+  size_t tmp2 = scan_bytes;
   BLI_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, tmp2, d_cnt, s->d_row_ptr, (int)(n_src + 1), st));
   int nnz = 0;
   BLI_CUDA(cudaMemcpyAsync(&nnz, s->d_row_ptr + n_src, sizeof(int), cudaMemcpyDeviceToHost, st));
   BLI_CUDA(cudaStreamSynchronize(st));
   s->nnz = nnz;
-  BLI_CUDA(cudaMalloc(&s->d_col, sizeof(int) * std::max(nnz, 1)));
-  BLI_CUDA(cudaMalloc(&s->d_w, sizeof(float) * std::max(nnz, 1)));
+  if ((long long)nnz > s->nnz_cap || !s->d_col) {
+    if (s->d_col) { cudaFree(s->d_col); s->d_col = nullptr; }
+    if (s->d_w) { cudaFree(s->d_w); s->d_w = nullptr; }
+    s->nnz_cap = 0;
+    const long long want = std::max<long long>((long long)nnz + nnz / 8, 1);      // some slack: poses differ by a few points
+    BLI_CUDA(cudaMalloc(&s->d_col, sizeof(int) * want));
+    BLI_CUDA(cudaMalloc(&s->d_w, sizeof(float) * want));
+    s->nnz_cap = want;
+  }
   if (n_src > 0) {
     k_bli_rows<true><<<grid_blocks(s, n_src, 128), 128, 0, st>>>(s->d_idx, n_src, d_el, n_el, d_wbox, d_tbox,
                                                                  n[0], n[1], nullptr, s->d_row_ptr, s->d_col, s->d_w);
   }
   BLI_CUDA(cudaGetLastError());
   BLI_CUDA(cudaStreamSynchronize(st));
-  cleanup();
 #undef BLI_CUDA
   s->geometry_set = true;
   return upload_source_points(s);

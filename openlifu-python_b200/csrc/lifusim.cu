@@ -445,6 +445,7 @@ int lifu_destroy(lifu_sim* s) {
   cufftHandle hs[6] = {s->r2c1, s->r2c3, s->c2r1, s->c2r3, s->r2c2, s->c2r2};
   if (s->plans_ready || s->r2c1) for (cufftHandle h : hs) if (h) cufftDestroy(h);
   for (void* p : s->allocs) cudaFree(p);
+  cudaFree(s->d_bli_ws);
   cudaFree(s->d_idx); cudaFree(s->d_lin_exp); cudaFree(s->d_row_ptr); cudaFree(s->d_col);
   cudaFree(s->d_w); cudaFree(s->d_scale); cudaFree(s->d_base); cudaFree(s->d_delay); cudaFree(s->d_gain);
   for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
@@ -654,10 +655,12 @@ int lifu_set_source_geometry(lifu_sim* s, const int64_t* idx, const int32_t* row
   s->geometry_set = false;
   cudaFree(s->d_idx); cudaFree(s->d_row_ptr); cudaFree(s->d_col); cudaFree(s->d_w);
   s->d_idx = nullptr; s->d_row_ptr = nullptr; s->d_col = nullptr; s->d_w = nullptr;
+  s->idx_cap = 0; s->nnz_cap = 0;
   LIFU_CUDA(cudaMalloc(&s->d_idx, sizeof(long long) * std::max<int64_t>(n_src, 1)));
   LIFU_CUDA(cudaMalloc(&s->d_row_ptr, sizeof(int) * (n_src + 1)));
   LIFU_CUDA(cudaMalloc(&s->d_col, sizeof(int) * std::max<int64_t>(nnz, 1)));
   LIFU_CUDA(cudaMalloc(&s->d_w, sizeof(float) * std::max<int64_t>(nnz, 1)));
+  s->idx_cap = std::max<int64_t>(n_src, 1); s->nnz_cap = std::max<int64_t>(nnz, 1);
   if (n_src > 0) {
     LIFU_CUDA(cudaMemcpyAsync(s->d_idx, idx, sizeof(long long) * n_src, cudaMemcpyDefault, st));
     LIFU_CUDA(cudaMemcpyAsync(s->d_row_ptr, row_ptr, sizeof(int) * (n_src + 1), cudaMemcpyDefault, st));

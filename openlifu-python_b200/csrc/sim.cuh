@@ -75,6 +75,9 @@ struct lifu_sim {
   float* d_w = nullptr;
   float* d_scale = nullptr;
   bool geometry_set = false;
+  long long idx_cap = 0, nnz_cap = 0;  // capacities of d_idx / d_row_ptr (points) and d_col / d_w (non-zeros)
+  void* d_bli_ws = nullptr;            // workspace of the GPU source-geometry build (bli.cu), kept across rebuilds
+  size_t bli_ws_cap = 0;
 
   // drive
   float* d_base = nullptr;
