@@ -431,6 +431,7 @@ int lifu_analysis_run_focus(lifu_analysis* a, int32_t focus, const lifu_focus_qu
   for (int i = 0; i < 3; ++i)
     if (!(q->aspect[i] != 0.0)) { set_error("lifu_analysis_run_focus: zero aspect ratio"); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(a->device));
+  NvtxRange nvtx_r("lifu_analysis_run_focus");
   cudaStream_t st = a->stream;
 
   // per-axis products w[i][a] * axis_a (plain float64 multiplies, as numpy forms them)

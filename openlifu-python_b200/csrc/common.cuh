@@ -11,9 +11,20 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler injects itself
+
 #include "lifusim.h"
 
 namespace lifu {
+
+// NVTX range for the lifetime of a scope (tracing row): nsys / ncu --nvtx show the phases of the C ABI
+// calls (create, medium, source geometry, set-up / graph capture / time loop / read-back of lifu_run, plan stack, analysis).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 void set_error(const char* fmt, ...);
 

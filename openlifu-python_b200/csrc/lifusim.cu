@@ -308,6 +308,7 @@ int lifu_pml_auto(const int32_t n[3], int32_t pml_out[3]) {
 }
 
 static int create_impl(const lifu_grid* g, int device, void* cuda_stream, const lifu_slab_desc* slab, lifu_sim** out) {
+  NvtxRange nvtx_r("lifu_create");
   if (!g || !out) { set_error("lifu_create: null argument"); return LIFU_ERR_INVALID; }
   *out = nullptr;
   for (int a = 0; a < 3; ++a) {
@@ -462,6 +463,7 @@ static int set_medium_impl(lifu_sim* s, const float* c0, const float* rho0, cons
                            const MediumLut* lut = nullptr) {
   if (!s || (!labels && (!c0 || !rho0))) { set_error("lifu_set_medium: null argument"); return LIFU_ERR_INVALID; }
   if (alpha_mode < 0 || alpha_mode > 2) { set_error("lifu_set_medium: alpha_mode %d unknown", alpha_mode); return LIFU_ERR_INVALID; }
+  NvtxRange nvtx_r("lifu_set_medium");
   LIFU_CUDA(cudaSetDevice(s->device));
   cudaStream_t st = s->stream;
   StepParams& P = s->P;
@@ -639,6 +641,7 @@ int lifu_set_elements(lifu_sim* s, int32_t n_el, const double* pos_m, const doub
                       const double* angle_deg, double bli_tolerance, int32_t upsampling_rate, int64_t* n_src) {
   if (!s || !pos_m || !size_m || !angle_deg) { set_error("lifu_set_elements: null argument"); return LIFU_ERR_INVALID; }
   LIFU_CUDA(cudaSetDevice(s->device));
+  NvtxRange nvtx_r("lifu_set_elements (BLI source geometry)");
   LIFU_CHECK(bli_build(s, n_el, pos_m, size_m, angle_deg, bli_tolerance, upsampling_rate));
   if (n_src) *n_src = s->n_src;
   return LIFU_OK;
@@ -1565,6 +1568,9 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     return LIFU_ERR_STATE;
   }
   if (!s->tables_ready) { set_error("lifu_run: internal error, tables not built"); return LIFU_ERR_STATE; }
+  NvtxRange nvtx_run("lifu_run");
+  nvtxRangePushA("lifu_run: set-up");
+  struct PopOnExit { int n = 1; ~PopOnExit() { for (int i = 0; i < n; ++i) nvtxRangePop(); } } nvtx_phase;
   LIFU_CUDA(cudaSetDevice(s->device));
   cudaStream_t user_stream = s->stream;
   cudaStream_t own = nullptr;
@@ -1637,6 +1643,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
 
   const int nt = s->grid.nt;
   const int L = s->n_src > 0 ? std::min(nt, s->max_delay + s->n_base) : 0;
+  nvtxRangePop(); nvtxRangePushA("lifu_run: steady-source basis + graph capture");
   // steady window of the source (v2 pipeline): steps [w0, w1) run the rank-2 source path
   int w0 = 0, w1 = 0;
   if (s->last_used_v2 && L > 0) {
@@ -1668,6 +1675,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     }
   }
   LIFU_CUDA(cudaEventRecord(s->ev[1], st));
+  nvtxRangePop(); nvtxRangePushA("lifu_run: time loop");
   int rc = LIFU_OK;
   for (int t = 0; t < nt && rc == LIFU_OK; ++t) {
     const int v = kind_of(t);
@@ -1684,6 +1692,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     }
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
+  nvtxRangePop(); nvtxRangePushA("lifu_run: crop + read-back + wait");
   if (rc == LIFU_OK && s->last_used_v2) k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
   if (rc == LIFU_OK && s->last_used_v3) g3_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->G.pm);
   if (rc == LIFU_OK && p_max && s->Vsens) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;

@@ -148,6 +148,7 @@ int lifu_stack_put(lifu_stack* k, int32_t focus, lifu_sim* s) {
   if (s->last.steps <= 0) { set_error("lifu_stack_put: call lifu_run first"); return LIFU_ERR_STATE; }
   if (s->two_z_mode == 0) { set_error("lifu_stack_put: call lifu_set_two_z first"); return LIFU_ERR_STATE; }
   LIFU_CUDA(cudaSetDevice(k->device));
+  NvtxRange nvtx_r("lifu_stack_put");
   // the solver's stream orders this after the time loop; the stack's stream is joined through an event
   cudaStream_t st = s->stream;
   const size_t off = (size_t)focus * (size_t)k->V;
@@ -199,6 +200,7 @@ int lifu_stack_aggregate(lifu_stack* k, float* p_max_max, float* pnp_max, double
   for (int f = 0; f < k->n_foci; ++f)
     if (!k->filled[f]) { set_error("lifu_stack_aggregate: focus %d has no fields yet", f); return LIFU_ERR_STATE; }
   LIFU_CUDA(cudaSetDevice(k->device));
+  NvtxRange nvtx_r("lifu_stack_aggregate");
   k_stack_aggregate<<<k->blocks, 256, 0, k->stream>>>(k->d_pmax, k->d_pnp, k->d_int, k->V, k->n_foci, k->d_agg_f,
                                                       k->d_agg_f + k->V, k->d_agg_d);
   LIFU_CUDA(cudaGetLastError());
