@@ -229,12 +229,14 @@ class LifuSim:
             self.layout = {k: getattr(lay, k) for k, _ in lay._fields_}
         self._keep = []
         self._stage = None             # page-locked result staging buffers (run()), allocated on first use
+        self._stage3 = None            # ... and of run_packaged()
 
     def close(self):
         if self._h:
             self._lib.lifu_destroy(self._h)
             self._h = C.c_void_p()
         self._stage = None
+        self._stage3 = None
 
     def __del__(self):
         try:
@@ -400,15 +402,38 @@ class LifuSim:
 
     def run_packaged(self):
         """Time loop + the packaging of kwave_if.py:136-141 on the device: (p_max, -p_min, intensity, stats) as flat
-        x-fastest host arrays (float32, float32, float64)."""
+        x-fastest host arrays (float32, float32, float64).  Large results come through page-locked staging buffers kept
+        on the handle and a threaded copy into the fresh arrays that are handed out (as in ``run``)."""
         st = lifu_stats()
         _check(self._lib.lifu_run(self._h, None, None, C.byref(st)))
         nvox = int(np.prod(self.n))
         p_max = np.empty(nvox, dtype=np.float32)
         pnp = np.empty(nvox, dtype=np.float32)
         inten = np.empty(nvox, dtype=np.float64)
-        _check(self._lib.lifu_get_packaged(self._h, _ptr(p_max), _ptr(pnp), _ptr(inten)))
+        stage = self._pinned_stage3(nvox) if nvox >= (1 << 20) else None
+        if stage is not None:
+            import torch
+            _check(self._lib.lifu_get_packaged(self._h, C.c_void_p(stage[0].data_ptr()), C.c_void_p(stage[1].data_ptr()),
+                                               C.c_void_p(stage[2].data_ptr())))
+            torch.from_numpy(p_max).copy_(stage[0])
+            torch.from_numpy(pnp).copy_(stage[1])
+            torch.from_numpy(inten).copy_(stage[2])
+        else:
+            _check(self._lib.lifu_get_packaged(self._h, _ptr(p_max), _ptr(pnp), _ptr(inten)))
         return p_max, pnp, inten, st.as_dict()
+
+    def _pinned_stage3(self, nvox):
+        cur = getattr(self, "_stage3", None)
+        if cur is not None and cur[0].numel() == nvox:
+            return cur
+        try:
+            import torch
+            self._stage3 = (torch.empty(nvox, dtype=torch.float32, pin_memory=True),
+                            torch.empty(nvox, dtype=torch.float32, pin_memory=True),
+                            torch.empty(nvox, dtype=torch.float64, pin_memory=True))
+        except Exception:  # noqa: BLE001
+            self._stage3 = None
+        return self._stage3
 
     def get_field(self, which):
         st = lifu_stats()
