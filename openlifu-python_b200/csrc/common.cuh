@@ -118,7 +118,8 @@ struct V2Params {
   int nxt;                          // regular 16-lane kx tiles of the strided passes (Nx/32); tile nxt = Nyquist column
   int Ry;                           // radix of the y axis: rows y and y+Ry form a packed row pair
   int ry_sh, hy_sh;                 // log2(Ry), log2(Ny/2)
-  long long HS;                     // stride between batched H fields  (Nz*Ny*PH)
+  long long HS;                     // stride between batched H fields  (Nz*zsH)
+  long long zsH;                    // plane stride of the H layout: Ny*PH (v2) or Ny*PH + pad (wide: keeps the z stride off 2^15)
   long long ZS;                     // stride between batched Z fields  (Nz*(Ny/2)*Nx)
   const float4 *tw4x, *tw4y, *tw4z; // (w, i w), w = exp(-2 pi i m / N), m = 0..N (entry N = entry 0), per axis
   const float4 *dpy4, *dny4, *dpz4, *dnz4;   // derivative multipliers i k e^{+-i k d/2} as (m, i m)

@@ -1000,7 +1000,7 @@ __global__ void __launch_bounds__(256) k2_x_src(StepParams P, V2Params Q) {
 }
 
 // Source scatter into the dense slab (same arithmetic as k_source_scatter of v1).
-__global__ void __launch_bounds__(128) k2_source_scatter(StepParams P, V2Params Q, SourceParams S) {
+static __global__ void __launch_bounds__(128) k2_source_scatter(StepParams P, V2Params Q, SourceParams S) {
   const int t = *P.step;
   const long long slab0 = (long long)Q.z0s * P.Ny * P.Nx;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.n_src;
@@ -1016,7 +1016,7 @@ __global__ void __launch_bounds__(128) k2_source_scatter(StepParams P, V2Params 
 }
 
 // Steady-state source, set-up: dense slab of one spatial basis field, sum_e W[i,e] coef_e (coef_e = gain_e * c_{k,e}).
-__global__ void __launch_bounds__(128) k2_source_basis(StepParams P, V2Params Q, SourceParams S, const float* __restrict__ coef) {
+static __global__ void __launch_bounds__(128) k2_source_basis(StepParams P, V2Params Q, SourceParams S, const float* __restrict__ coef) {
   const long long slab0 = (long long)Q.z0s * P.Ny * P.Nx;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.n_src;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1049,11 +1049,11 @@ __global__ void __launch_bounds__(256) k2_x_inv_real(StepParams P, V2Params Q, c
 }
 
 // sensor field helpers: pm = interleaved (p_max, p_min) on the expanded grid
-__global__ void k2_pm_init(float2* pm, long long n) {
+static __global__ void k2_pm_init(float2* pm, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     pm[i] = make_float2(-INFINITY, INFINITY);
 }
-__global__ void k2_pm_crop(StepParams P, V2Params Q) {
+static __global__ void k2_pm_crop(StepParams P, V2Params Q) {
   const long long n = (long long)P.nx * P.ny * P.nz;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % P.nx);

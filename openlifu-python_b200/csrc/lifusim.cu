@@ -763,10 +763,25 @@ static void launch_rho_p(lifu_sim* s, int gb) {
 // pipeline v2: fused hand-written FFT passes (fft_v2.cuh)
 static int radix_of(int n) { return n == 64 ? 8 : (n == 256 ? 16 : 0); }
 
-static bool v2_eligible(const lifu_sim* s) {
-  if (s->pipeline == 1 || s->pipeline == 3) return false;
+static bool v2_square(const lifu_sim* s) {
   for (int a = 0; a < 3; ++a) if (radix_of(s->N[a]) == 0) return false;
   return true;
+}
+// pipeline "wide" (fft_wide.cuh, wide.cu): the same fused passes for 64 / 128 / 256 / 512 / 768 / 1024-point axes.  Taken for
+// non-square factorisations when asked for (LIFU_PIPELINE=v2) or when LIFU_WIDE_AUTO is not "0".
+static bool wide_ok(const lifu_sim* s) {
+  for (int a = 0; a < 3; ++a) if (!wide_ab(s->N[a], nullptr, nullptr)) return false;
+  if (s->drive_set && s->source_mode != LIFU_SOURCE_ADDITIVE) return false;
+  return true;
+}
+static bool wide_auto() {
+  const char* e = getenv("LIFU_WIDE_AUTO");
+  return !(e && e[0] == '0');
+}
+static bool v2_eligible(const lifu_sim* s) {
+  if (s->pipeline == 1 || s->pipeline == 3) return false;
+  if (v2_square(s)) return true;
+  return wide_ok(s) && (s->pipeline == 2 || wide_auto());
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (liblifusim does not link libcuda)
@@ -809,11 +824,20 @@ static int v2_setup(lifu_sim* s) {
     Q.Nx = s->N[0]; Q.Ny = s->N[1]; Q.Nz = s->N[2]; Q.Nxh = s->Nxh;
     Q.PH = (int)round_up(s->Nxh, 16);
     Q.nxt = s->N[0] / 32;
-    Q.HS = (long long)Q.Nz * Q.Ny * Q.PH;
+    {
+      // wide: pad every H plane so that the z stride is not a multiple of 32 KB (LIFU_WIDE_HPAD, in complex elements)
+      const char* hp = getenv("LIFU_WIDE_HPAD");
+      const int pad = (hp && hp[0]) ? atoi(hp) : 0;        // measured: no effect on 256^3 / 512^3 (profiles/r2_wide_summary.md)
+      Q.zsH = (long long)Q.Ny * Q.PH + ((!v2_square(s) || (getenv("LIFU_WIDE_SQUARE") && getenv("LIFU_WIDE_SQUARE")[0] == '1')) ? pad : 0);
+    }
+    Q.HS = (long long)Q.Nz * Q.zsH;
     Q.ZS = (long long)Q.Nz * (Q.Ny / 2) * Q.Nx;
     Q.norm = (float)(1.0 / (2.0 * (double)s->V));
+    const char* wsq = getenv("LIFU_WIDE_SQUARE");           // measurement switch: square grids through the wide kernels too
+    s->v2_wide = !v2_square(s) || (wsq && wsq[0] == '1' && wide_ok(s));
     for (int a = 0; a < 3; ++a) {
       s->R[a] = radix_of(s->N[a]);
+      if (s->v2_wide) wide_ab(s->N[a], nullptr, &s->R[a]);     // threads per line (B of N = A x B)
       const int n = s->N[a];
       std::vector<float4> tw(n + 1);
       for (int m = 0; m <= n; ++m) {
@@ -826,7 +850,7 @@ static int v2_setup(lifu_sim* s) {
       LIFU_CUDA(cudaStreamSynchronize(s->stream));
     }
     Q.Ry = s->R[1];
-    Q.ry_sh = Q.Ry == 8 ? 3 : 4;
+    Q.ry_sh = Q.Ry == 8 ? 3 : (Q.Ry == 16 ? 4 : 5);
     Q.hy_sh = 0;
     while ((1 << Q.hy_sh) < Q.Ny / 2) ++Q.hy_sh;
     Q.tw4x = s->d_tw[0]; Q.tw4y = s->d_tw[1]; Q.tw4z = s->d_tw[2];
@@ -871,7 +895,7 @@ static int v2_setup(lifu_sim* s) {
     // (re)allocate the slab buffers; old ones stay in the handle's allocation list until destroy
     LIFU_CHECK(dev_alloc(s, (void**)&Q.Sslab, sizeof(float) * (size_t)nz * s->N[1] * s->N[0]));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.ZSslab, sizeof(float2) * (size_t)nz * (s->N[1] / 2) * s->N[0]));
-    LIFU_CHECK(dev_alloc(s, (void**)&Q.HSslab, sizeof(float2) * (size_t)nz * s->N[1] * Q.PH));
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.HSslab, sizeof(float2) * (size_t)nz * Q.zsH));
     s->slab_planes_alloc = nz;
   }
   Q.z0s = z0; Q.nzs = nz;
@@ -894,7 +918,7 @@ static int v2_setup(lifu_sim* s) {
   // than the per-thread-load kernels (profiles/r1_z_tma.md) -- the z passes are bound by their two 256-point
   // transforms per element, not by load latency.
   const char* zt = getenv("LIFU_Z_TMA");
-  s->z_tma = (zt && zt[0] == '1') && encode_z_tile_map(s->tmH, Q.H4, Q.PH, Q.Ny, Q.Nz, 4) &&
+  s->z_tma = !s->v2_wide && (zt && zt[0] == '1') && encode_z_tile_map(s->tmH, Q.H4, Q.PH, Q.Ny, Q.Nz, 4) &&
              encode_z_tile_map(s->tmS, Q.HSslab, Q.PH, Q.Ny, Q.nzs, 0);
   return LIFU_OK;
 }
@@ -1465,7 +1489,7 @@ static int enqueue_step(lifu_sim* s, int kind, int* n_kernels, int* n_ffts) {
   mark("begin", 0);
   if (s->sl.on) return enqueue_step_slab(s, src_active, n_kernels, n_ffts, mark);
   if (s->last_used_v2) {
-    int rc2 = enqueue_step_v2(s, kind, n_kernels, mark);
+    int rc2 = s->v2_wide ? wide_enqueue_step(s, kind, n_kernels, mark) : enqueue_step_v2(s, kind, n_kernels, mark);
     if (n_ffts) *n_ffts = 0;
     return rc2;
   }
@@ -1592,7 +1616,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   } restore{s, user_stream, own};
   cudaStream_t st = s->stream;
   if (s->pipeline == 2 && !v2_eligible(s)) {
-    set_error("lifu_run: LIFU_PIPELINE=v2 needs a lossless medium and 64- or 256-point axes (grid is %dx%dx%d)",
+    set_error("lifu_run: LIFU_PIPELINE=v2 needs 64 / 128 / 256 / 512 / 768 / 1024-point axes (grid is %dx%dx%d)",
               s->N[0], s->N[1], s->N[2]);
     return LIFU_ERR_STATE;
   }
@@ -1646,7 +1670,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   nvtxRangePop(); nvtxRangePushA("lifu_run: steady-source basis + graph capture");
   // steady window of the source (v2 pipeline): steps [w0, w1) run the rank-2 source path
   int w0 = 0, w1 = 0;
-  if (s->last_used_v2 && L > 0) {
+  if (s->last_used_v2 && !s->v2_wide && L > 0) {
     LIFU_CHECK(v2_build_steady(s, nt));
     if (s->Q.nws > 0) { w0 = s->Q.t0s; w1 = s->Q.t0s + s->Q.nws; }
   }

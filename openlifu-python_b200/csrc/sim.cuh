@@ -1,5 +1,7 @@
 // sim.cuh -- the opaque handle behind lifu_sim.
 #pragma once
+#include <functional>
+
 #include "common.cuh"
 
 namespace lifu {
@@ -111,6 +113,7 @@ struct lifu_sim {
   unsigned char tmH[128] __attribute__((aligned(64))) = {};   // CUtensorMap of H4[comp][z][ky][kx]
   unsigned char tmS[128] __attribute__((aligned(64))) = {};   // CUtensorMap of the source slab spectrum
   bool last_used_v2 = false;
+  bool v2_wide = false;        // the grid has a non-square axis (128, 512, 768, 1024): passes of fft_wide.cuh / wide.cu
   bool v2_ygrad_split = false; // gradient y-inverse with one component per CTA (LIFU_V2_YGRAD=split)
   float* d_fk = nullptr;       // steady-state source: [2][RS] filtered basis fields
   float* d_qsrc = nullptr;     // [2][nws] time coefficients
@@ -144,6 +147,9 @@ int dev_alloc(lifu_sim* s, void** p, size_t bytes);
 int bli_build(lifu_sim* s, int n_el, const double* pos, const double* size, const double* ang,
               double tol, int ups);
 int upload_source_points(lifu_sim* s);
+// pipeline "wide" (wide.cu): axis lengths N = A x B it covers, one time step on the handle's stream
+bool wide_ab(int n, int* A, int* B);
+int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark);
 inline int grid_blocks(const lifu_sim* s, long long n, int threads, int per_sm = 8) {
   long long need = (n + threads - 1) / threads;
   long long cap = (long long)s->n_sm * per_sm;

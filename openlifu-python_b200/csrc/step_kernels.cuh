@@ -102,7 +102,7 @@ template <int POLY> __device__ __forceinline__ float cosk_sel(float a2) {
 }
 
 // ------------------------------------------------------------------ K1
-__global__ void __launch_bounds__(256) k_grad_spectral(StepParams P) {
+static __global__ void __launch_bounds__(256) k_grad_spectral(StepParams P) {
   const long long n = P.Vh;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_grad_spectral(StepParams P) {
 }
 
 // ------------------------------------------------------------------ K3
-__global__ void __launch_bounds__(256) k_div_spectral(StepParams P) {
+static __global__ void __launch_bounds__(256) k_div_spectral(StepParams P) {
   const long long n = P.Vh;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) k_update_u(StepParams P) {
 }
 
 // ------------------------------------------------------------------ source
-__global__ void __launch_bounds__(128) k_source_scatter(StepParams P, SourceParams S) {
+static __global__ void __launch_bounds__(128) k_source_scatter(StepParams P, SourceParams S) {
   const int t = *P.step;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.n_src;
        i += (long long)gridDim.x * blockDim.x) {
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(128) k_source_scatter(StepParams P, SourcePara
   }
 }
 
-__global__ void __launch_bounds__(256) k_source_filter(StepParams P) {
+static __global__ void __launch_bounds__(256) k_source_filter(StepParams P) {
   const long long n = P.Vh;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_update_rho_p(StepParams P) {
 }
 
 // ------------------------------------------------------------------ K5
-__global__ void __launch_bounds__(256) k_absorb_spectral(StepParams P) {
+static __global__ void __launch_bounds__(256) k_absorb_spectral(StepParams P) {
   const long long n = P.Vh;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) k_pressure_absorb(StepParams P, int use_t
 }
 
 // ------------------------------------------------------------------ setup kernels
-__global__ void k_fill(float* a, long long n, float v) {
+static __global__ void k_fill(float* a, long long n, float v) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     a[i] = v;
@@ -351,7 +351,7 @@ __global__ void k_expand_edge(const T* __restrict__ in, float* __restrict__ out,
 // on the device: one byte per voxel crosses PCIe instead of three float64 maps).  Labels outside the table give 0,
 // the reference's initial value.
 struct MediumLut { int n; float c0[32], rho0[32], alpha[32]; };
-__global__ void k_expand_edge_lut(const unsigned char* __restrict__ lab, float* __restrict__ c0e, float* __restrict__ rho0e,
+static __global__ void k_expand_edge_lut(const unsigned char* __restrict__ lab, float* __restrict__ c0e, float* __restrict__ rho0e,
                                   float* __restrict__ alphae, StepParams P, int n_planes, long long sx, long long sy,
                                   long long sz, MediumLut lut) {
   const long long n = (long long)P.Nx * P.Ny * n_planes;
@@ -374,7 +374,7 @@ __global__ void k_expand_edge_lut(const unsigned char* __restrict__ lab, float* 
 
 // Packaging of kwave_if.py:136-141 on the device: p_min -> -p_min (float32) and
 // intensity = 1e-4 * p_min^2 / (2 Z) with the float32 square and scale and the float64 divide of the numpy expression.
-__global__ void k_package(const float* __restrict__ pmin, const double* __restrict__ two_z, double two_z_s,
+static __global__ void k_package(const float* __restrict__ pmin, const double* __restrict__ two_z, double two_z_s,
                           float* __restrict__ pnp, double* __restrict__ inten, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float p = pmin[i];
@@ -386,7 +386,7 @@ __global__ void k_package(const float* __restrict__ pmin, const double* __restri
 
 // Derived medium maps on the expanded grid.  c0e/rho0e/alphae are the expanded maps;
 // alpha_np_coef = 100*(1e-6/2pi)^y/(20 log10 e) converts dB/(MHz^y cm) to Np/((rad/s)^y m).
-__global__ void k_derive_medium(const float* __restrict__ c0e, const float* __restrict__ rho0e,
+static __global__ void k_derive_medium(const float* __restrict__ c0e, const float* __restrict__ rho0e,
                                 const float* __restrict__ alphae, StepParams P, float dt, float y,
                                 double alpha_np_coef, double tan_term, float* dt_rho0_sg,
                                 float* dt_rho0, float* c2, float* tau, float* eta) {
@@ -415,7 +415,7 @@ __global__ void k_derive_medium(const float* __restrict__ c0e, const float* __re
   }
 }
 
-__global__ void k_source_points(const long long* __restrict__ idx_inner, long long n_src, StepParams P,
+static __global__ void k_source_points(const long long* __restrict__ idx_inner, long long n_src, StepParams P,
                                 const float* __restrict__ c0e, float c0_s, double dt, double dx,
                                 long long* lin_exp, float* scale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_src;

@@ -1,0 +1,124 @@
+// wide.cu -- host side and strided (y, z) passes of pipeline "wide" (fft_wide.cuh): the fused FFT passes for axis
+// lengths 64 / 128 / 256 / 512 / 768 / 1024.  The x passes live in wide_x.cu, one translation unit per factorisation.
+// Shares its state (V2Params, tables, buffers) with pipeline v2: lifusim.cu::v2_setup allocates, enqueue_step dispatches.
+#include <algorithm>
+#include <functional>
+
+#include "fft_wide.cuh"
+#include "sim.cuh"
+
+namespace lifu {
+
+#define WIDE_X_DECL(a, b) void wide_x_launch_##a##_##b(lifu_sim* s, int op, int src);
+WIDE_X_DECL(8, 8) WIDE_X_DECL(8, 16) WIDE_X_DECL(16, 16) WIDE_X_DECL(16, 32) WIDE_X_DECL(24, 32) WIDE_X_DECL(32, 32)
+
+bool wide_ab(int n, int* A, int* B) {
+  int a = 0, b = 0;
+  switch (n) {
+    case 64: a = 8; b = 8; break;
+    case 128: a = 8; b = 16; break;
+    case 256: a = 16; b = 16; break;
+    case 512: a = 16; b = 32; break;
+    case 768: a = 24; b = 32; break;
+    case 1024: a = 32; b = 32; break;
+    default: return false;
+  }
+  if (A) *A = a;
+  if (B) *B = b;
+  return true;
+}
+
+static void wide_x(lifu_sim* s, int op, int src) {
+  switch (s->N[0]) {
+    case 64: wide_x_launch_8_8(s, op, src); break;
+    case 128: wide_x_launch_8_16(s, op, src); break;
+    case 256: wide_x_launch_16_16(s, op, src); break;
+    case 512: wide_x_launch_16_32(s, op, src); break;
+    case 768: wide_x_launch_24_32(s, op, src); break;
+    default: wide_x_launch_32_32(s, op, src); break;
+  }
+}
+
+template <typename K, typename... Args>
+static void wlaunch(K kernel, dim3 grid, int threads, size_t sm, cudaStream_t st, Args... args) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  kernel<<<grid, threads, sm, st>>>(args...);
+}
+
+// EXPR sees constexpr int WA, WB = the factorisation of axis length NAX
+#define WIDE_AB(NAX, EXPR)                                                  \
+  do {                                                                      \
+    switch (NAX) {                                                          \
+      case 64: { constexpr int WA = 8, WB = 8; EXPR; } break;               \
+      case 128: { constexpr int WA = 8, WB = 16; EXPR; } break;             \
+      case 256: { constexpr int WA = 16, WB = 16; EXPR; } break;            \
+      case 512: { constexpr int WA = 16, WB = 32; EXPR; } break;            \
+      case 768: { constexpr int WA = 24, WB = 32; EXPR; } break;            \
+      default: { constexpr int WA = 32, WB = 32; EXPR; } break;             \
+    }                                                                       \
+  } while (0)
+
+template <int A, int B> static dim3 wgrid(const V2Params& Q, int n_other, int nz) {
+  return dim3((unsigned)(Q.Nx / (2 * Wide<A, B>::LANES) + 1), (unsigned)n_other, (unsigned)nz);
+}
+
+// kind: 0 no source, 1 source active (filtered additive source)
+int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark) {
+  V2Params Q = s->Q;
+  cudaStream_t st = s->stream;
+  const int Ny = s->N[1], Nz = s->N[2];
+  const int src = kind != 0 ? 1 : 0;
+  const double srcf = (double)Q.nzs / Q.Nz;
+  int nk = 0;
+  // (1) pressure gradient
+  WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 0>, wgrid<WA, WB>(Q, Q.Nz, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_y_fwd_p", 8);
+  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 0>, wgrid<WA, WB>(Q, Q.Ny, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_z_grad", 12);
+  WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, true>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_y_inv_grad", 20);
+  // (2) velocity update + forward x transform of the new velocity
+  wide_x(s, 0, 0);
+  ++nk; mark("kw_x_u", s->homogeneous ? 48 : 60);
+  WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 1>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_y_fwd_u", 24);
+  // (3) source field on its slab
+  if (src) {
+    k2_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, Q, s->S);
+    ++nk; mark("k2_source_scatter", 0);
+    wide_x(s, 3, 0);
+    ++nk; mark("kw_x_src", 8 * srcf);
+    WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 2>, wgrid<WA, WB>(Q, Q.nzs, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    ++nk; mark("kw_y_fwd_src", 8 * srcf);
+  }
+  // (4) divergence (+ filtered source) through z and back through y
+  const int ncomp = src ? 4 : 3;
+  Q.comp0 = 0;
+  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 1>, wgrid<WA, WB>(Q, Q.Ny, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
+  WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  ++nk; mark("kw_y_inv", 8 * ncomp);
+  // (5) density update, source, equation of state, sensor, forward x transform of p
+  wide_x(s, 1, src);
+  ++nk;
+  const double sens = (double)s->n[1] * s->n[2] / ((double)s->N[1] * s->N[2]);
+  if (!s->absorbing) {
+    mark("kw_x_rho_p", 12 + 24 + 16 * sens + 4 + (s->homogeneous ? 0 : 8) + (src ? 4 : 0));
+  } else {
+    // (6) absorbing medium: the two fractional Laplacians, then the equation of state
+    mark("kw_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src ? 4 : 0));
+    WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 3>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    ++nk; mark("kw_y_fwd_abs", 16);
+    WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 2>, wgrid<WA, WB>(Q, Q.Ny, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    ++nk; mark("kw_z_absorb", 16);
+    WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    ++nk; mark("kw_y_inv_abs", 16);
+    wide_x(s, 2, 0);
+    ++nk; mark("kw_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
+  }
+  LIFU_CUDA(cudaGetLastError());
+  if (n_kernels) *n_kernels = nk;
+  return LIFU_OK;
+}
+
+}  // namespace lifu
