@@ -146,6 +146,15 @@ struct V2Params {
   float* qcur;                      // [2] coefficients of the current step (written by the first kernel of the step)
   int t0s, nws;                     // first step and length of the steady window (nws = 0: off)
   int comp0;                        // component offset of k2_y_inv, first component of k2_z_div
+  // z-slab decomposition of pipeline wide (wide.cu): Nz above is the LOCAL plane count, H4 the local half spectra
+  // [4][Nzl][Ny][PH]; T4 holds this rank's ky rows of ALL planes, [4][NzG][Nyl][PH].  The y-forward kernels store straight
+  // into the owners' T4 and the z kernels straight into the owners' H4 through `peer` (every rank's exchange buffer,
+  // mapped with CUDA IPC; H4 at +0, T4 at +peerT).  G = 0: one GPU, no routing.
+  int G, Nzl, NzG, Nyl, z0g, ky0;
+  float2* T4;
+  float2* const* peer;
+  long long peerT;
+  int gz0s, gnzs;                   // planes of the source mask on the whole grid (z0s / nzs above: this rank's part)
 };
 
 // Pipeline v3 (fft_gen.cuh): generic-radix fused passes.

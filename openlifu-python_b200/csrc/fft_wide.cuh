@@ -221,13 +221,30 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_fwd(StepParams P,
   }
   wfft_strided<A, B, false>(v, tw, xa, l, t);
   if (live && (A == B || t < A)) {
-    float2* hp = Hout + (long long)z * Q.zsH + (long long)t * Q.PH + kx;   // ky = t + A kb
-    const long long kstep = (long long)A * Q.PH;
+    if (Q.G == 0) {
+      float2* hp = Hout + (long long)z * Q.zsH + (long long)t * Q.PH + kx;   // ky = t + A kb
+      const long long kstep = (long long)A * Q.PH;
 #pragma unroll
-    for (int kb = 0; kb < B; ++kb) {
-      float2 o = v[kb];
-      if (MODE == 1 && comp == 1) o = cmul4(o, Q.dny4[t + A * kb]);
-      hp[kb * kstep] = o;
+      for (int kb = 0; kb < B; ++kb) {
+        float2 o = v[kb];
+        if (MODE == 1 && comp == 1) o = cmul4(o, Q.dny4[t + A * kb]);
+        hp[kb * kstep] = o;
+      }
+    } else {
+      // slab decomposition: row ky of plane z0g + z belongs to rank ky / Nyl; store it into that rank's T4 over NVLink
+      // (G divides B: ky = t + A kb with t < A lies in block kb / (B / G), no division needed)
+      const int fld = MODE == 2 ? 3 : comp;
+      const long long zrow = (long long)(Q.z0g + z + (MODE == 2 ? Q.z0s : 0)) * Q.Nyl;
+      const int bg = B / Q.G;
+      int q = 0, rem = 0;
+      float2* dst = Q.peer[0] + Q.peerT + fld * Q.HS + (zrow + t) * Q.PH + kx;
+#pragma unroll
+      for (int kb = 0; kb < B; ++kb) {
+        float2 o = v[kb];
+        if (MODE == 1 && comp == 1) o = cmul4(o, Q.dny4[t + A * kb]);
+        dst[(long long)rem * A * Q.PH] = o;
+        if (++rem == bg) { rem = 0; ++q; if (q < Q.G) dst = Q.peer[q] + Q.peerT + fld * Q.HS + (zrow + t) * Q.PH + kx; }
+      }
     }
   }
 }
@@ -282,21 +299,33 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   const int chain = (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0);
   int kx, ky;
-  if (!wlane_map<L>(Q, Q.Ny, l, kx, ky, (int)blockIdx.y)) return;
-  const bool live = ky < Q.Ny;
-  const int kyc = live ? ky : Q.Ny - 1;
+  const int nky = Q.G ? Q.Nyl : Q.Ny;                 // ky rows held here (all of them without a slab decomposition)
+  if (!wlane_map<L>(Q, nky, l, kx, ky, (int)blockIdx.y)) return;
+  const bool live = ky < nky;
+  const int kyc = live ? ky : nky - 1;
+  const int kyg = kyc + (Q.G ? Q.ky0 : 0);           // global ky: index of the 1-D tables
   float2* xa = reinterpret_cast<float2*>(smraw);
-  const long long zs = Q.zsH;
+  const long long zs = Q.G ? (long long)Q.Nyl * Q.PH : Q.zsH;
   const long long col = (long long)kyc * Q.PH + kx;
-  const float2* in = OP == 0 ? Q.H4 + col : Q.H4 + chain * Q.HS + col;
-  float2* out = OP == 0 ? Q.H4 + (chain == 0 ? 2 : 1) * Q.HS + col : Q.H4 + chain * Q.HS + col;
+  const float2* base = Q.G ? Q.T4 : Q.H4;
+  const float2* in = OP == 0 ? base + col : base + chain * Q.HS + col;
+  const int fout = OP == 0 ? (chain == 0 ? 2 : 1) : chain;
   float2 v[B];
   if (OP == 1 && chain == 3) {
-    const float2* sp = Q.HSslab + col;
+    if (Q.G) {
+      // the owners of the source planes stored their rows into T4[3]; the other planes of that field are not defined
 #pragma unroll
-    for (int i = 0; i < A; ++i) {
-      const int zr = t + B * i - Q.z0s;
-      v[i] = (zr >= 0 && zr < Q.nzs) ? sp[(long long)zr * zs] : make_float2(0.f, 0.f);
+      for (int i = 0; i < A; ++i) {
+        const int zr = t + B * i - Q.gz0s;
+        v[i] = (zr >= 0 && zr < Q.gnzs) ? in[(long long)(t + B * i) * zs] : make_float2(0.f, 0.f);
+      }
+    } else {
+      const float2* sp = Q.HSslab + col;
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        const int zr = t + B * i - Q.z0s;
+        v[i] = (zr >= 0 && zr < Q.nzs) ? sp[(long long)zr * zs] : make_float2(0.f, 0.f);
+      }
     }
   } else {
 #pragma unroll
@@ -306,7 +335,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
   wfft_strided<A, B, false>(v, tw, xa, l, t);
   if (A == B || t < A) {
     if (OP == 2) {
-      const float kxy = P.kx2[kx] + P.ky2[kyc];
+      const float kxy = P.kx2[kx] + P.ky2[kyg];
       const float e = chain == 0 ? P.y_minus2_half : P.y_minus1_half;
 #pragma unroll
       for (int kb = 0; kb < B; ++kb) {
@@ -314,7 +343,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
         v[kb] = cscale(v[kb], k2 > 0.f ? __powf(k2, e) * Q.norm : 0.f);
       }
     } else {
-      const float axy = P.ax2[kx] + P.ay2[kyc];
+      const float axy = P.ax2[kx] + P.ay2[kyg];
 #pragma unroll
       for (int kb = 0; kb < B; ++kb) {
         const int kz = t + A * kb;
@@ -331,8 +360,23 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
   __syncthreads();                               // the exchange buffer is read out before the inverse reuses it
   wfft_strided<A, B, true>(v, tw, xa, l, t);
   if (live) {
+    if (Q.G == 0) {
+      float2* out = Q.H4 + fout * Q.HS + col;
 #pragma unroll
-    for (int i = 0; i < A; ++i) out[(long long)(t + B * i) * zs] = v[i];
+      for (int i = 0; i < A; ++i) out[(long long)(t + B * i) * zs] = v[i];
+    } else {
+      // slab decomposition: plane z belongs to rank z / Nzl; store the row into that rank's H4 over NVLink
+      // (G divides A: z = t + B i with t < B lies in block i / (A / G))
+      const long long rowg = (long long)kyg * Q.PH + kx;
+      const int ag = A / Q.G;
+      int q = 0, rem = 0;
+      float2* dst = Q.peer[0] + fout * Q.HS + (long long)t * Q.zsH + rowg;
+#pragma unroll
+      for (int i = 0; i < A; ++i) {
+        dst[(long long)rem * B * Q.zsH] = v[i];
+        if (++rem == ag) { rem = 0; ++q; if (q < Q.G) dst = Q.peer[q] + fout * Q.HS + (long long)t * Q.zsH + rowg; }
+      }
+    }
   }
 }
 
@@ -531,7 +575,7 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
           }
         }
       } else {
-        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
         if (zin && (unsigned)(ylo - P.py) < (unsigned)P.ny)
           XS::copy(st, reinterpret_cast<const char*>(Q.pm + r0), 8 * N, t);
         if (zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny)
@@ -634,7 +678,7 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
           }
         }
       } else {
-        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
         const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
         const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
         float2* pmg = Q.pm + r0;
@@ -710,7 +754,7 @@ __global__ void __launch_bounds__(TPB) kw_x_p(StepParams P, V2Params Q, int use_
           XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.c2 + r0 + hi), 4 * N, t);
         }
       } else {
-        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
         if (zin && (unsigned)(ylo - P.py) < (unsigned)P.ny)
           XS::copy(st, reinterpret_cast<const char*>(Q.pm + r0), 8 * N, t);
         if (zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny)
@@ -762,7 +806,7 @@ __global__ void __launch_bounds__(TPB) kw_x_p(StepParams P, V2Params Q, int use_
           }
         }
       } else {
-        const bool zin = (unsigned)(z - P.pz) < (unsigned)P.nz;
+        const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
         const bool in0 = zin && (unsigned)(ylo - P.py) < (unsigned)P.ny;
         const bool in1 = zin && (unsigned)(ylo + Q.Ry - P.py) < (unsigned)P.ny;
         float2* pmg = Q.pm + r0;
@@ -821,6 +865,19 @@ __global__ void __launch_bounds__(256) kw_x_src(StepParams P, V2Params Q) {
   if (ok && (A == B || t < A)) {
 #pragma unroll
     for (int kb = 0; kb < B; ++kb) Q.ZSslab[pair * N + t + A * kb] = v[kb];
+  }
+}
+
+// (p_max, p_min) pairs of the expanded (local) planes -> the two sensor arrays on the inner grid (this rank's planes)
+static __global__ void kw_pm_crop(StepParams P, const float2* __restrict__ pm, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % P.nx);
+    const long long r = i / P.nx;
+    const int y = (int)(r % P.ny), jl = (int)(r / P.ny);
+    const int z = jl + P.jz0 + P.pz - P.z0;                 // local expanded plane of inner plane jz0 + jl
+    const float2 v = pm[((long long)z * P.Ny + (y + P.py)) * P.Nx + (x + P.px)];
+    P.pmax[i] = v.x;
+    P.pmin[i] = v.y;
   }
 }
 

@@ -778,6 +778,19 @@ static bool wide_auto() {
   const char* e = getenv("LIFU_WIDE_AUTO");
   return !(e && e[0] == '0');
 }
+// Slab decomposition on the fused passes (wide.cu): peer-store exchange only; the block arithmetic of the routed stores
+// needs G | B of the y factorisation (Nyl = A B / G rows per rank) and G | A of the z factorisation (Nzl planes per rank).
+static bool slab_wide_ok(const lifu_sim* s) {
+  if (!s->sl.on || s->sl.exchange != 2 || !wide_ok(s)) return false;
+  const char* e = getenv("LIFU_SLAB_WIDE");
+  if (e && e[0] == '0') return false;
+  int A = 0, B = 0;
+  wide_ab(s->N[1], &A, &B);
+  if (B % s->sl.G) return false;
+  wide_ab(s->N[2], &A, &B);
+  if (A % s->sl.G) return false;
+  return true;
+}
 static bool v2_eligible(const lifu_sim* s) {
   if (s->pipeline == 1 || s->pipeline == 3) return false;
   if (v2_square(s)) return true;
@@ -820,21 +833,23 @@ static bool encode_z_tile_map(void* out, void* base, int PH, int Ny, int nz, int
 
 static int v2_setup(lifu_sim* s) {
   V2Params& Q = s->Q;
+  const bool sl = s->sl.on;                  // one slab of a decomposed grid: local planes, exchange buffers of slab_init
   if (!s->v2_ready) {
-    Q.Nx = s->N[0]; Q.Ny = s->N[1]; Q.Nz = s->N[2]; Q.Nxh = s->Nxh;
+    Q.Nx = s->N[0]; Q.Ny = s->N[1]; Q.Nz = sl ? s->sl.Nzl : s->N[2]; Q.Nxh = s->Nxh;
     Q.PH = (int)round_up(s->Nxh, 16);
     Q.nxt = s->N[0] / 32;
     {
       // wide: pad every H plane so that the z stride is not a multiple of 32 KB (LIFU_WIDE_HPAD, in complex elements)
       const char* hp = getenv("LIFU_WIDE_HPAD");
       const int pad = (hp && hp[0]) ? atoi(hp) : 0;        // measured: no effect on 256^3 / 512^3 (profiles/r2_wide_summary.md)
-      Q.zsH = (long long)Q.Ny * Q.PH + ((!v2_square(s) || (getenv("LIFU_WIDE_SQUARE") && getenv("LIFU_WIDE_SQUARE")[0] == '1')) ? pad : 0);
+      Q.zsH = (long long)Q.Ny * Q.PH + ((!sl && (!v2_square(s) || (getenv("LIFU_WIDE_SQUARE") && getenv("LIFU_WIDE_SQUARE")[0] == '1'))) ? pad : 0);
     }
-    Q.HS = (long long)Q.Nz * Q.zsH;
+    Q.HS = sl ? s->sl.Hl : (long long)Q.Nz * Q.zsH;
+    if (sl && s->sl.Hl != (long long)Q.Nz * Q.zsH) { set_error("slab exchange buffers do not match the padded half-spectrum layout"); return LIFU_ERR_STATE; }
     Q.ZS = (long long)Q.Nz * (Q.Ny / 2) * Q.Nx;
     Q.norm = (float)(1.0 / (2.0 * (double)s->V));
     const char* wsq = getenv("LIFU_WIDE_SQUARE");           // measurement switch: square grids through the wide kernels too
-    s->v2_wide = !v2_square(s) || (wsq && wsq[0] == '1' && wide_ok(s));
+    s->v2_wide = sl || !v2_square(s) || (wsq && wsq[0] == '1' && wide_ok(s));
     for (int a = 0; a < 3; ++a) {
       s->R[a] = radix_of(s->N[a]);
       if (s->v2_wide) wide_ab(s->N[a], nullptr, &s->R[a]);     // threads per line (B of N = A x B)
@@ -876,27 +891,49 @@ static int v2_setup(lifu_sim* s) {
     }
     LIFU_CHECK(dev_alloc(s, (void**)&Q.ZP, sizeof(float2) * Q.ZS));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.Z4, sizeof(float2) * 4 * Q.ZS));
-    LIFU_CHECK(dev_alloc(s, (void**)&Q.H4, sizeof(float2) * 4 * Q.HS));
-    LIFU_CHECK(dev_alloc(s, (void**)&Q.pm, sizeof(float2) * s->V));
+    if (sl) {
+      Q.H4 = s->sl.xbuf; Q.T4 = s->sl.xbuf + 4 * s->sl.Hl;
+      Q.G = s->sl.G; Q.Nzl = s->sl.Nzl; Q.NzG = s->N[2]; Q.Nyl = s->sl.Nyl; Q.z0g = s->sl.z0; Q.ky0 = s->sl.ky0;
+      Q.peer = s->sl.d_peer; Q.peerT = 4 * s->sl.Hl;
+    } else {
+      LIFU_CHECK(dev_alloc(s, (void**)&Q.H4, sizeof(float2) * 4 * Q.HS));
+      Q.G = 0; Q.T4 = nullptr; Q.peer = nullptr;
+    }
+    LIFU_CHECK(dev_alloc(s, (void**)&Q.pm, sizeof(float2) * s->Vloc));
     s->v2_ready = true;
   }
   // source slab: z range of the mask (indices are sorted, x fastest, so first/last give min/max z)
   int z0 = 0, nz = 1;
-  if (s->n_src > 0) {
+  const long long n_pts = sl ? s->sl.src_i1 - s->sl.src_i0 : s->n_src;        // a slab handle holds its own planes' points
+  if (n_pts > 0) {
     long long first = 0, last = 0;
     LIFU_CUDA(cudaMemcpyAsync(&first, s->d_lin_exp, sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
-    LIFU_CUDA(cudaMemcpyAsync(&last, s->d_lin_exp + (s->n_src - 1), sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
+    LIFU_CUDA(cudaMemcpyAsync(&last, s->d_lin_exp + (n_pts - 1), sizeof(long long), cudaMemcpyDeviceToHost, s->stream));
     LIFU_CUDA(cudaStreamSynchronize(s->stream));
     const long long plane = (long long)s->N[0] * s->N[1];
     z0 = (int)(first / plane);
     nz = (int)(last / plane) - z0 + 1;
   }
-  if (nz > s->slab_planes_alloc) {
+  if (sl) {
+    // planes of the mask on the WHOLE grid (every rank filters the same source field), then this rank's share of them:
+    // the owners store all their planes of the range, zero where they hold no points
+    float v[2] = {n_pts > 0 ? -(float)(s->sl.z0 + z0) : -1e9f, n_pts > 0 ? (float)(s->sl.z0 + z0 + nz - 1) : -1e9f};
+    LIFU_CHECK(slab_allreduce_max(s, v, 2));
+    if (v[1] < 0.f) { Q.gz0s = 0; Q.gnzs = 0; }
+    else { Q.gz0s = (int)(-v[0]); Q.gnzs = (int)v[1] - Q.gz0s + 1; }
+    const int lo = std::max(Q.gz0s, s->sl.z0), hi = std::min(Q.gz0s + Q.gnzs, s->sl.z0 + s->sl.Nzl);
+    z0 = hi > lo ? lo - s->sl.z0 : 0;
+    nz = hi > lo ? hi - lo : 0;
+  }
+  if (std::max(nz, 1) > s->slab_planes_alloc) {
+    const int nzs_keep = nz;
+    nz = std::max(nz, 1);
     // (re)allocate the slab buffers; old ones stay in the handle's allocation list until destroy
     LIFU_CHECK(dev_alloc(s, (void**)&Q.Sslab, sizeof(float) * (size_t)nz * s->N[1] * s->N[0]));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.ZSslab, sizeof(float2) * (size_t)nz * (s->N[1] / 2) * s->N[0]));
     LIFU_CHECK(dev_alloc(s, (void**)&Q.HSslab, sizeof(float2) * (size_t)nz * Q.zsH));
     s->slab_planes_alloc = nz;
+    nz = nzs_keep;
   }
   Q.z0s = z0; Q.nzs = nz;
   Q.store_p = 0;
@@ -1487,9 +1524,11 @@ static int enqueue_step(lifu_sim* s, int kind, int* n_kernels, int* n_ffts) {
     ++s->prof_used;
   };
   mark("begin", 0);
-  if (s->sl.on) return enqueue_step_slab(s, src_active, n_kernels, n_ffts, mark);
+  if (s->sl.on && !s->last_used_v2) return enqueue_step_slab(s, src_active, n_kernels, n_ffts, mark);
   if (s->last_used_v2) {
-    int rc2 = s->v2_wide ? wide_enqueue_step(s, kind, n_kernels, mark) : enqueue_step_v2(s, kind, n_kernels, mark);
+    std::function<int()> bar;
+    if (s->sl.on) bar = [s]() { return slab_barrier(s, s->stream); };
+    int rc2 = s->v2_wide ? wide_enqueue_step(s, kind, n_kernels, mark, bar) : enqueue_step_v2(s, kind, n_kernels, mark);
     if (n_ffts) *n_ffts = 0;
     return rc2;
   }
@@ -1624,11 +1663,11 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
     set_error("lifu_run: LIFU_PIPELINE=v3 needs 2/3/5/7-smooth axes (grid is %dx%dx%d)", s->N[0], s->N[1], s->N[2]);
     return LIFU_ERR_STATE;
   }
-  s->last_used_v2 = !s->sl.on && v2_eligible(s);
+  s->last_used_v2 = s->sl.on ? slab_wide_ok(s) : v2_eligible(s);
   // v3 (generic radices) is taken when asked for (LIFU_PIPELINE=v3) or, automatically, on the grids where it has been
   // measured faster than the library-FFT pipeline (profiles/r2_v3_summary.md): LIFU_V3_AUTO=0 / 1 overrides
   s->last_used_v3 = !s->sl.on && !s->last_used_v2 && v3_eligible(s) && (s->pipeline == 3 || v3_auto(s));
-  if (s->sl.on) {
+  if (s->sl.on && !s->last_used_v2) {
     LIFU_CHECK(slab_plans(s));
   } else if (s->last_used_v2) {
     LIFU_CHECK(v2_setup(s));
@@ -1654,7 +1693,7 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   if (s->last_used_v2) {
     LIFU_CUDA(cudaMemsetAsync(s->Q.ZP, 0, sizeof(float2) * s->Q.ZS, st));
     LIFU_CUDA(cudaMemsetAsync(s->Q.Sslab, 0, sizeof(float) * (size_t)s->Q.nzs * s->N[1] * s->N[0], st));
-    k2_pm_init<<<grid_blocks(s, s->V, 256), 256, 0, st>>>(s->Q.pm, s->V);
+    k2_pm_init<<<grid_blocks(s, s->Vloc, 256), 256, 0, st>>>(s->Q.pm, s->Vloc);
   }
   if (s->last_used_v3) {
     LIFU_CUDA(cudaMemsetAsync(s->G.ZP, 0, sizeof(float2) * s->G.ZS, st));
@@ -1717,7 +1756,10 @@ int lifu_run(lifu_sim* s, float* p_max, float* p_min, lifu_stats* stats) {
   }
   if (rc == LIFU_OK && cudaEventRecord(s->ev[2], st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   nvtxRangePop(); nvtxRangePushA("lifu_run: crop + read-back + wait");
-  if (rc == LIFU_OK && s->last_used_v2) k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
+  if (rc == LIFU_OK && s->last_used_v2) {
+    if (s->v2_wide) { if (s->Vsens > 0) wide_pm_crop(s); }
+    else k2_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->Q);
+  }
   if (rc == LIFU_OK && s->last_used_v3) g3_pm_crop<<<grid_blocks(s, s->Vin, 256), 256, 0, st>>>(s->P, s->G.pm);
   if (rc == LIFU_OK && p_max && s->Vsens) if (cudaMemcpyAsync(p_max, P.pmax, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;
   if (rc == LIFU_OK && p_min && s->Vsens) if (cudaMemcpyAsync(p_min, P.pmin, sizeof(float) * s->Vsens, cudaMemcpyDefault, st) != cudaSuccess) rc = LIFU_ERR_CUDA;

@@ -149,7 +149,9 @@ int bli_build(lifu_sim* s, int n_el, const double* pos, const double* size, cons
 int upload_source_points(lifu_sim* s);
 // pipeline "wide" (wide.cu): axis lengths N = A x B it covers, one time step on the handle's stream
 bool wide_ab(int n, int* A, int* B);
-int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark);
+int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark,
+                      const std::function<int()>& barrier);
+void wide_pm_crop(lifu_sim* s);
 inline int grid_blocks(const lifu_sim* s, long long n, int threads, int per_sm = 8) {
   long long need = (n + threads - 1) / threads;
   long long cap = (long long)s->n_sm * per_sm;

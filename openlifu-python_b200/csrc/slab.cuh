@@ -283,6 +283,10 @@ inline int slab_init(lifu_sim* s, const lifu_slab_desc* d) {
   L.med_lo = mlo; L.med_n = mhi - mlo + 1;
   L.Vl = (long long)s->N[0] * s->N[1] * L.Nzl;
   L.Hl = (long long)s->Nxh * s->N[1] * L.Nzl;
+  // grids the fused passes cover (wide.cu) keep their half spectra with a row pitch of round_up(Nxh, 16): size the exchange
+  // buffers for that layout (the library-FFT path uses Hl only as the stride between fields)
+  if (wide_ab(s->N[0], nullptr, nullptr) && wide_ab(s->N[1], nullptr, nullptr) && wide_ab(s->N[2], nullptr, nullptr))
+    L.Hl = round_up(s->Nxh, 16) * s->N[1] * L.Nzl;
   ncclUniqueId id;
   static_assert(sizeof(id.internal) == LIFU_NCCL_ID_BYTES, "ncclUniqueId size");
   memcpy(id.internal, d->nccl_id, LIFU_NCCL_ID_BYTES);

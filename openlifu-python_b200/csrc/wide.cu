@@ -62,40 +62,55 @@ template <int A, int B> static dim3 wgrid(const V2Params& Q, int n_other, int nz
   return dim3((unsigned)(Q.Nx / (2 * Wide<A, B>::LANES) + 1), (unsigned)n_other, (unsigned)nz);
 }
 
-// kind: 0 no source, 1 source active (filtered additive source)
-int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark) {
+// kind: 0 no source, 1 source active (filtered additive source).
+// Slab decomposition (Q.G > 0, `barrier` given): the y-forward kernels store straight into the owners' transposed buffers
+// and the z kernels straight back into the owners' plane buffers over NVLink, so an exchange is the store phase of a
+// transform kernel plus ONE barrier -- 4 barriers per time step (6 for absorbing media), no pack / unpack pass, no
+// library transform.  A phase touches {local Z / H, remote T} or {local T, remote H}: one barrier per phase is enough.
+int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function<void(const char*, double)>& mark,
+                      const std::function<int()>& barrier) {
   V2Params Q = s->Q;
   cudaStream_t st = s->stream;
   const int Ny = s->N[1], Nz = s->N[2];
   const int src = kind != 0 ? 1 : 0;
-  const double srcf = (double)Q.nzs / Q.Nz;
+  const bool slab = Q.G > 0;
+  const int nky = slab ? Q.Nyl : Q.Ny;                          // ky rows of the z passes
+  const double srcf = (double)(slab ? Q.gnzs : Q.nzs) / Nz;
   int nk = 0;
+  auto sync_ranks = [&]() -> int { if (slab && barrier) { ++nk; return barrier(); } return LIFU_OK; };
   // (1) pressure gradient
   WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 0>, wgrid<WA, WB>(Q, Q.Nz, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-  ++nk; mark("kw_y_fwd_p", 8);
-  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 0>, wgrid<WA, WB>(Q, Q.Ny, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-  ++nk; mark("kw_z_grad", 12);
+  LIFU_CHECK(sync_ranks());
+  ++nk; mark(slab ? "kw_y_fwd_p+xchg" : "kw_y_fwd_p", 8);
+  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 0>, wgrid<WA, WB>(Q, nky, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  LIFU_CHECK(sync_ranks());
+  ++nk; mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
   WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, true>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
   wide_x(s, 0, 0);
   ++nk; mark("kw_x_u", s->homogeneous ? 48 : 60);
   WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 1>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-  ++nk; mark("kw_y_fwd_u", 24);
-  // (3) source field on its slab
+  ++nk; if (!slab) mark("kw_y_fwd_u", 24);
+  // (3) source field on its slab (slab decomposition: on this rank's planes of it, if any)
   if (src) {
-    k2_source_scatter<<<grid_blocks(s, s->n_src, 128), 128, 0, st>>>(s->P, Q, s->S);
-    ++nk; mark("k2_source_scatter", 0);
-    wide_x(s, 3, 0);
-    ++nk; mark("kw_x_src", 8 * srcf);
-    WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 2>, wgrid<WA, WB>(Q, Q.nzs, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-    ++nk; mark("kw_y_fwd_src", 8 * srcf);
+    if (Q.nzs > 0) {
+      if (s->S.n_src > 0) { k2_source_scatter<<<grid_blocks(s, s->S.n_src, 128), 128, 0, st>>>(s->P, Q, s->S); ++nk; }
+      if (!slab) mark("k2_source_scatter", 0);
+      wide_x(s, 3, 0);
+      ++nk; if (!slab) mark("kw_x_src", 8 * srcf);
+      WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 2>, wgrid<WA, WB>(Q, Q.nzs, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+      ++nk; if (!slab) mark("kw_y_fwd_src", 8 * srcf);
+    }
   }
+  LIFU_CHECK(sync_ranks());
+  if (slab) mark("kw_y_fwd_u+src+xchg", 24 + (src ? 16 * srcf : 0));
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 1>, wgrid<WA, WB>(Q, Q.Ny, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-  ++nk; mark("kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
+  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 1>, wgrid<WA, WB>(Q, nky, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  LIFU_CHECK(sync_ranks());
+  ++nk; mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
   WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
@@ -108,9 +123,11 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
     // (6) absorbing medium: the two fractional Laplacians, then the equation of state
     mark("kw_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src ? 4 : 0));
     WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 3>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-    ++nk; mark("kw_y_fwd_abs", 16);
-    WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 2>, wgrid<WA, WB>(Q, Q.Ny, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
-    ++nk; mark("kw_z_absorb", 16);
+    LIFU_CHECK(sync_ranks());
+    ++nk; mark(slab ? "kw_y_fwd_abs+xchg" : "kw_y_fwd_abs", 16);
+    WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 2>, wgrid<WA, WB>(Q, nky, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    LIFU_CHECK(sync_ranks());
+    ++nk; mark(slab ? "kw_z_absorb+xchg" : "kw_z_absorb", 16);
     WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
     ++nk; mark("kw_y_inv_abs", 16);
     wide_x(s, 2, 0);
@@ -119,6 +136,10 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   LIFU_CUDA(cudaGetLastError());
   if (n_kernels) *n_kernels = nk;
   return LIFU_OK;
+}
+
+void wide_pm_crop(lifu_sim* s) {
+  kw_pm_crop<<<grid_blocks(s, s->Vsens, 256), 256, 0, s->stream>>>(s->P, s->Q.pm, s->Vsens);
 }
 
 }  // namespace lifu

@@ -33,9 +33,41 @@ def test_single_rank_slab_matches_single_gpu_and_oracle(lifu_lib, exchange):
     one = cases.run_cuda_case(case, pipeline="v1")
     want = cases.run_oracle_case(case)
     assert got["layout"]["exchange"] == {"nccl": 1, "peer": 2}[exchange]
-    assert got["layout"]["sensor_nz"] == case["N"][2] and got["stats"]["fft_launches"] > 0
+    assert got["layout"]["sensor_nz"] == case["N"][2]
+    # peer stores on a 64^3 grid: the fused passes with the exchange in their store phase (no library transform);
+    # NCCL transport: cuFFT 2-D / 1-D transforms around pack / send / unpack
+    assert (got["stats"]["fft_launches"] == 0) == (exchange == "peer")
     for k in ("p_max", "p_min"):
         assert cases.rel_l2(got[k], one[k]) < 1e-5, k
+        assert cases.rel_l2(got[k], want[k]) < TOL, k
+
+
+def test_single_rank_slab_peer_library_transforms(lifu_lib, monkeypatch):
+    """LIFU_SLAB_WIDE=0 keeps the cuFFT-based slab path under the peer-store exchange."""
+    monkeypatch.setenv("LIFU_SLAB_WIDE", "0")
+    case = cases.v2_small_case(steps=40)
+    got = _one_rank(case, "peer")
+    one = cases.run_cuda_case(case, pipeline="v1")
+    assert got["stats"]["fft_launches"] > 0
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(got[k], one[k]) < 1e-5, k
+
+
+@pytest.mark.parametrize("medium", ["water", "phantom"])
+def test_single_rank_slab_fused_passes_on_a_wide_grid(lifu_lib, medium):
+    """128 x 64 x 128 expanded grid (8 x 16 factorisations on x and z) through the slab code path of the fused passes:
+    routed stores into the (own) transposed buffer, source planes through T4[3], sensor crop of the local planes."""
+    from tests.test_gpu_wide import wide_case
+    case = wide_case((128, 64, 128), steps=60)
+    if medium == "phantom":
+        case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))
+        case["dt"], case["t_end"] = 1.5e-7, 60 * 1.5e-7
+    got = _one_rank(case, "peer")
+    assert got["stats"]["fft_launches"] == 0
+    one = cases.run_cuda_case(case, pipeline="v1")
+    want = cases.run_oracle_case(case)
+    for k in ("p_max", "p_min"):
+        assert cases.rel_l2(got[k], one[k]) < 2e-5, k
         assert cases.rel_l2(got[k], want[k]) < TOL, k
 
 
