@@ -92,7 +92,8 @@ inline NcclApi* nccl_api() {
 struct SlabParams {
   int Nx, Ny, Nxh, Nzl, NzG, Nyl, G;
   int z0, ky0;
-  long long Hl;                 // elements per field in either layout
+  long long Hl;                 // stride between fields in either layout (>= Hn: sized for the padded rows of wide.cu)
+  long long Hn;                 // elements per field = Nzl*Ny*Nxh = NzG*Nyl*Nxh
   float2* H;                    // local [4][Hl]
   float2* T;                    // local [4][Hl]
   float2* const* peer;          // [G] xbuf of every rank (H at +0, T at +4*Hl), or pack staging in NCCL mode
@@ -176,7 +177,7 @@ __device__ __forceinline__ void t_index(const SlabParams& S, long long i, int& k
 
 // pressure gradient: T0 <- kappa p^ / N ; T1 <- i kz e^{+i kz dz/2} kappa p^ / N
 __global__ void __launch_bounds__(256) k_slab_grad_z(StepParams P, SlabParams S) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hn; i += (long long)gridDim.x * blockDim.x) {
     int kx, ky, kz;
     t_index(S, i, kx, ky, kz);
     const float kap = kappa_of(P.ax2[kx] + P.ay2[ky] + P.az2[kz]) * P.invN;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(256) k_slab_grad_z(StepParams P, SlabParams S)
 template <int KIND>
 __global__ void __launch_bounds__(256) k_slab_div_z(StepParams P, SlabParams S, int f) {
   float2* T = S.T + f * S.Hl;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hn; i += (long long)gridDim.x * blockDim.x) {
     int kx, ky, kz;
     t_index(S, i, kx, ky, kz);
     const float a2 = P.ax2[kx] + P.ay2[ky] + P.az2[kz];
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(256) k_slab_div_z(StepParams P, SlabParams S, 
 // absorption operators, one field in place: T[f] *= k^(2e)/N with e = (y-2)/2 (tau operand) or (y-1)/2 (eta operand)
 __global__ void __launch_bounds__(256) k_slab_absorb_z(StepParams P, SlabParams S, int f, float e) {
   float2* T = S.T + f * S.Hl;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hn; i += (long long)gridDim.x * blockDim.x) {
     int kx, ky, kz;
     t_index(S, i, kx, ky, kz);
     const float k2 = P.kx2[kx] + P.ky2[ky] + P.kz2[kz];
@@ -226,7 +227,7 @@ __global__ void __launch_bounds__(256) k_slab_absorb_z(StepParams P, SlabParams 
 
 // after the return trip of the gradient: H3 = IFFT_z[kappa p^]  ->  H0 = i kx e^{+..} H3, H1 = i ky e^{+..} H3
 __global__ void __launch_bounds__(256) k_slab_grad_xy(StepParams P, SlabParams S) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hl; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < S.Hn; i += (long long)gridDim.x * blockDim.x) {
     const int kx = (int)(i % S.Nxh);
     const int ky = (int)((i / S.Nxh) % S.Ny);
     const float2 a = S.H[3 * S.Hl + i];
@@ -242,7 +243,7 @@ struct SlabHost {
     const SlabCtx& L = s->sl;
     SlabParams S{};
     S.Nx = s->N[0]; S.Ny = s->N[1]; S.Nxh = s->Nxh; S.Nzl = L.Nzl; S.NzG = s->N[2]; S.Nyl = L.Nyl; S.G = L.G;
-    S.z0 = L.z0; S.ky0 = L.ky0; S.Hl = L.Hl;
+    S.z0 = L.z0; S.ky0 = L.ky0; S.Hl = L.Hl; S.Hn = (long long)s->Nxh * s->N[1] * L.Nzl;
     S.H = L.xbuf; S.T = L.xbuf + 4 * L.Hl;
     S.peer = L.d_peer;
     S.peer_T_off = staging ? 0 : 4 * L.Hl;
@@ -336,7 +337,7 @@ inline int slab_init(lifu_sim* s, const lifu_slab_desc* d) {
   if (want == 1) {
     LIFU_CHECK(dev_alloc(s, (void**)&L.pack, sizeof(float2) * 4 * L.Hl));
     // staging "peers": block q of the pack buffer; a block is [Nzl][Nyl][Nxh] = Hl / G elements per field
-    for (int q = 0; q < L.G; ++q) peers[q] = L.pack + (long long)q * (L.Hl / L.G);
+    for (int q = 0; q < L.G; ++q) peers[q] = L.pack + (long long)q * ((long long)L.Nzl * L.Nyl * s->Nxh);
   }
   LIFU_CUDA(cudaMemcpyAsync(L.d_peer, peers.data(), sizeof(float2*) * L.G, cudaMemcpyHostToDevice, s->stream));
   LIFU_CUDA(cudaStreamSynchronize(s->stream));
@@ -414,7 +415,7 @@ inline int slab_exchange_fwd(lifu_sim* s, cudaStream_t st, int f, int kind, bool
   LIFU_CUDA(cudaGetLastError());
   if (!staging) return barrier ? slab_barrier(s, st) : LIFU_OK;
   NcclApi* N = nccl_api();
-  const long long blk = L.Hl / L.G;                          // complex elements per (field, destination)
+  const long long blk = (long long)L.Nzl * L.Nyl * s->Nxh;   // complex elements per (field, destination); Hl >= G * blk
   LIFU_NCCL(N->GroupStart());
   for (int q = 0; q < L.G; ++q) {
     LIFU_NCCL(N->Send(L.pack + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));
@@ -436,7 +437,7 @@ inline int slab_exchange_back(lifu_sim* s, cudaStream_t st, int f, int fd, bool 
     return barrier ? slab_barrier(s, st) : LIFU_OK;
   }
   NcclApi* N = nccl_api();
-  const long long blk = L.Hl / L.G;
+  const long long blk = (long long)L.Nzl * L.Nyl * s->Nxh;
   LIFU_NCCL(N->GroupStart());
   for (int q = 0; q < L.G; ++q) {
     LIFU_NCCL(N->Send(S.T + f * L.Hl + q * blk, 2 * blk, ncclFloat, q, (ncclComm_t)L.comm, st));

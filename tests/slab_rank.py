@@ -24,6 +24,14 @@ for p in (str(ROOT / "openlifu-python_b200"), str(ROOT)):
 
 def build_case(name, steps):
     from tests import cases
+    if name.startswith("wide"):
+        # 128 x 64 x 128 expanded (8 x 16 factorisations on x and z): the fused passes with routed stores on > 1 rank
+        from tests.test_gpu_wide import wide_case
+        case = wide_case((128, 64, 128), steps=steps)
+        if name == "wide_phantom":
+            case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))
+            case["dt"], case["t_end"] = 1.5e-7, steps * 1.5e-7
+        return case
     case = cases.v2_small_case(steps=steps)                       # inner 40x44x36 -> 64^3 with PML
     if name == "phantom":
         case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))

@@ -105,13 +105,15 @@ def _run_ranks(tmp_path, world, case, exchange):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(out.read_text())
     assert res["finite"] and res["world"] == world
+    tol_single = 2e-5 if case.startswith("wide") else 1e-5        # fused passes vs the library-FFT pipeline on one GPU
     for k in ("p_max", "p_min"):
-        assert res["vs_single"][k] < 1e-5, res
+        assert res["vs_single"][k] < tol_single, res
         assert res["vs_oracle"][k] < TOL, res
     return res
 
 
-@pytest.mark.parametrize("case,exchange", [("water", "peer"), ("water", "nccl"), ("phantom", "auto")])
+@pytest.mark.parametrize("case,exchange", [("water", "peer"), ("water", "nccl"), ("phantom", "auto"), ("wide", "peer"),
+                                           ("wide_phantom", "peer")])
 def test_two_rank_slab(lifu_lib, tmp_path, case, exchange):
     import torch
     if torch.cuda.device_count() < 2:
