@@ -26,6 +26,10 @@
 #pragma once
 #include "fft_v2.cuh"
 
+// kx lanes of a strided tile when a line takes 32 threads (512 / 768 / 1024-point axes), template parameter L32 of the
+// strided kernels: 8 -> 256-thread CTAs, two per SM, 64-byte row segments (faster on one GPU); 16 -> 512-thread CTAs, one per
+// SM, 128-byte row segments -- what the NVLink stores of a slab decomposition want (profiles/r2_wide_summary.md).
+
 namespace lifu {
 
 __host__ __device__ constexpr float w24_re(int m) {
@@ -86,10 +90,11 @@ template <int N, bool INV> __device__ __forceinline__ void wdft(float2 (&x)[N]) 
 
 // ------------------------------------------------------------------------------------------------
 // geometry of a strided tile
-template <int A, int B> struct Wide {
+template <int A, int B, int L32 = 8> struct Wide {
   static constexpr int N = A * B;
-  static constexpr int LANES = B == 32 ? 8 : 16;
+  static constexpr int LANES = B == 32 ? L32 : 16;
   static constexpr int THREADS = LANES * B;
+  static constexpr int MINB = THREADS > 256 ? 1 : 2;             // CTAs per SM the register budget is set for
   static constexpr int PAD = LANES == 8 ? 8 : 0;                 // float2 per t row: keeps half-warp accesses conflict free
   static constexpr int PITCH = A * LANES + PAD;                  // float2 between consecutive t
   static constexpr int XCH = B * PITCH * 8;                      // bytes of the exchange buffer
@@ -105,9 +110,9 @@ template <int A, int B> struct Wide {
 
 // One strided line transform.  Forward: in v[0..A) = x[t + B i] on every thread, out v[0..B) = X[t + A kb] on threads
 // t < A.  Inverse: the reverse.  One barrier inside; the caller puts a barrier between two transforms that share `sm`.
-template <int A, int B, bool INV>
+template <int A, int B, bool INV, int L32 = 8>
 __device__ __forceinline__ void wfft_strided(float2 (&v)[B], const float4* __restrict__ tw, float2* sm, int l, int t) {
-  using W = Wide<A, B>;
+  using W = Wide<A, B, L32>;
   constexpr int N = A * B, L = W::LANES, PT = W::PITCH;
   const bool act = (A == B) || t < A;
   if constexpr (!INV) {
@@ -186,10 +191,10 @@ __device__ __forceinline__ void wmerge_store(float2* __restrict__ zp, const floa
 // ------------------------------------------------------------------------------------------------
 // y forward: packed row pairs -> half spectrum.  grid (tiles + 1, planes | plane blocks, ncomp)
 // MODE 0 pressure; 1 velocity (comp 0: x multiplier, comp 1: y multiplier); 2 source slab; 3 absorption operands
-template <int A, int B, int MODE>
-__global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_fwd(StepParams P, V2Params Q) {
+template <int A, int B, int MODE, int L32 = 8>
+__global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_y_fwd(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  using W = Wide<A, B>;
+  using W = Wide<A, B, L32>;
   constexpr int L = W::LANES;
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   const int comp = blockIdx.z;
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_fwd(StepParams P,
 #pragma unroll
     for (int i = 0; i < A; ++i) v[i] = cmul4(v[i], mx);
   }
-  wfft_strided<A, B, false>(v, tw, xa, l, t);
+  wfft_strided<A, B, false, L32>(v, tw, xa, l, t);
   if (live && (A == B || t < A)) {
     if (Q.G == 0) {
       float2* hp = Hout + (long long)z * Q.zsH + (long long)t * Q.PH + kx;   // ky = t + A kb
@@ -253,10 +258,10 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_fwd(StepParams P,
 // GRAD: the three pressure-gradient components from the two z-pass outputs:
 //   Z4[0] <- i kx e^{+i kx dx/2} IFFT_y[H4[2]];  Z4[1] <- IFFT_y[i ky e^{+i ky dy/2} H4[2]];  Z4[2] <- IFFT_y[H4[1]]
 // otherwise Z4[comp0 + c] <- IFFT_y[H4[comp0 + c]]
-template <int A, int B, bool GRAD>
-__global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_inv(StepParams P, V2Params Q) {
+template <int A, int B, bool GRAD, int L32 = 8>
+__global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_y_inv(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  using W = Wide<A, B>;
+  using W = Wide<A, B, L32>;
   constexpr int L = W::LANES;
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   const int comp = (int)blockIdx.z + (GRAD ? 0 : Q.comp0);
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_inv(StepParams P,
 #pragma unroll
     for (int kb = 0; kb < B; ++kb) a[kb] = cmul4(a[kb], Q.dpy4[t + A * kb]);
   }
-  wfft_strided<A, B, true>(a, tw, xa, l, t);
+  wfft_strided<A, B, true, L32>(a, tw, xa, l, t);
   if (GRAD && comp == 0) {
     const float4 mx = with_i(P.dpx[kx]);
 #pragma unroll
@@ -291,10 +296,10 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_y_inv(StepParams P,
 // OP 0 pressure gradient: chain 0: H4[2] <- IFFT_z[kappa FFT_z H4[0]]; chain 1: H4[1] <- IFFT_z[i kz e^{+i kz dz/2} kappa FFT_z H4[0]]
 // OP 1 divergence, in place: comps comp0 .. : kappa (0, 1), i kz e^{-i kz dz/2} kappa (2), source slab x cos(c_ref k dt/2) (3)
 // OP 2 absorption operands, in place: k^(y-2) (0), k^(y-1) (1)
-template <int A, int B, int OP>
-__global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2Params Q) {
+template <int A, int B, int OP, int L32 = 8>
+__global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_z(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  using W = Wide<A, B>;
+  using W = Wide<A, B, L32>;
   constexpr int L = W::LANES;
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   const int chain = (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
     for (int i = 0; i < A; ++i) v[i] = in[(long long)(t + B * i) * zs];
   }
   const float4* tw = W::load_tw(smraw, Q.tw4z);
-  wfft_strided<A, B, false>(v, tw, xa, l, t);
+  wfft_strided<A, B, false, L32>(v, tw, xa, l, t);
   if (A == B || t < A) {
     if (OP == 2) {
       const float kxy = P.kx2[kx] + P.ky2[kyg];
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(Wide<A, B>::THREADS, 2) kw_z(StepParams P, V2P
     }
   }
   __syncthreads();                               // the exchange buffer is read out before the inverse reuses it
-  wfft_strided<A, B, true>(v, tw, xa, l, t);
+  wfft_strided<A, B, true, L32>(v, tw, xa, l, t);
   if (live) {
     if (Q.G == 0) {
       float2* out = Q.H4 + fout * Q.HS + col;

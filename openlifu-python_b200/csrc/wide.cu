@@ -58,8 +58,15 @@ static void wlaunch(K kernel, dim3 grid, int threads, size_t sm, cudaStream_t st
     }                                                                       \
   } while (0)
 
-template <int A, int B> static dim3 wgrid(const V2Params& Q, int n_other, int nz) {
-  return dim3((unsigned)(Q.Nx / (2 * Wide<A, B>::LANES) + 1), (unsigned)n_other, (unsigned)nz);
+// ... and constexpr int WL = lanes parameter of the strided kernels: 16-lane tiles on 32-thread lines when W16 is set
+#define WIDE_ABL(NAX, W16, EXPR)                                                         \
+  do {                                                                                   \
+    if (W16) WIDE_AB(NAX, { constexpr int WL = WB == 32 ? 16 : 8; EXPR; });              \
+    else WIDE_AB(NAX, { constexpr int WL = 8; EXPR; });                                  \
+  } while (0)
+
+template <int A, int B, int L32> static dim3 wgrid(const V2Params& Q, int n_other, int nz) {
+  return dim3((unsigned)(Q.Nx / (2 * Wide<A, B, L32>::LANES) + 1), (unsigned)n_other, (unsigned)nz);
 }
 
 // kind: 0 no source, 1 source active (filtered additive source).
@@ -77,20 +84,24 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   const int nky = slab ? Q.Nyl : Q.Ny;                          // ky rows of the z passes
   const double srcf = (double)(slab ? Q.gnzs : Q.nzs) / Nz;
   int nk = 0;
+  // exchange-bearing kernels of a slab decomposition: 128-byte row segments for the NVLink stores (measured at 2 GPUs:
+  // y-forward + exchange stages 30 % shorter); one GPU: 64-byte segments, two CTAs per SM (LIFU_WIDE_LANES=8|16 overrides)
+  bool x16 = slab;
+  if (const char* e = getenv("LIFU_WIDE_LANES")) x16 = atoi(e) == 16;
   auto sync_ranks = [&]() -> int { if (slab && barrier) { ++nk; return barrier(); } return LIFU_OK; };
   // (1) pressure gradient
-  WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 0>, wgrid<WA, WB>(Q, Q.Nz, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_y_fwd_p+xchg" : "kw_y_fwd_p", 8);
-  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 0>, wgrid<WA, WB>(Q, nky, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, nky, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
-  WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, true>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, true, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
   wide_x(s, 0, 0);
   ++nk; mark("kw_x_u", s->homogeneous ? 48 : 60);
-  WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 1>, wgrid<WA, WB>(Q, Q.Nz, 3), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   ++nk; if (!slab) mark("kw_y_fwd_u", 24);
   // (3) source field on its slab (slab decomposition: on this rank's planes of it, if any)
   if (src) {
@@ -99,7 +110,7 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
       if (!slab) mark("k2_source_scatter", 0);
       wide_x(s, 3, 0);
       ++nk; if (!slab) mark("kw_x_src", 8 * srcf);
-      WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 2>, wgrid<WA, WB>(Q, Q.nzs, 1), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+      WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 2, WL>, wgrid<WA, WB, WL>(Q, Q.nzs, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
       ++nk; if (!slab) mark("kw_y_fwd_src", 8 * srcf);
     }
   }
@@ -108,10 +119,10 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 1>, wgrid<WA, WB>(Q, nky, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
-  WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, ncomp), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
   wide_x(s, 1, src);
@@ -122,13 +133,13 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   } else {
     // (6) absorbing medium: the two fractional Laplacians, then the equation of state
     mark("kw_x_rho_abs", 12 + 24 + 4 + 8 + (s->homogeneous ? 0 : 8) + (src ? 4 : 0));
-    WIDE_AB(Ny, (wlaunch(kw_y_fwd<WA, WB, 3>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 3, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     LIFU_CHECK(sync_ranks());
     ++nk; mark(slab ? "kw_y_fwd_abs+xchg" : "kw_y_fwd_abs", 16);
-    WIDE_AB(Nz, (wlaunch(kw_z<WA, WB, 2>, wgrid<WA, WB>(Q, nky, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 2, WL>, wgrid<WA, WB, WL>(Q, nky, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     LIFU_CHECK(sync_ranks());
     ++nk; mark(slab ? "kw_z_absorb+xchg" : "kw_z_absorb", 16);
-    WIDE_AB(Ny, (wlaunch(kw_y_inv<WA, WB, false>, wgrid<WA, WB>(Q, Q.Nz, 2), Wide<WA, WB>::THREADS, Wide<WA, WB>::SMEM, st, s->P, Q)));
+    WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     ++nk; mark("kw_y_inv_abs", 16);
     wide_x(s, 2, 0);
     ++nk; mark("kw_x_p", 8 + 4 + 16 * sens + 4 + (s->homogeneous ? 0 : 12));
