@@ -449,13 +449,21 @@ struct WStage {
     return s;
   }
 };
-template <int A, int B, int TPB, bool HOMOG> using WStageU = WStage<A, B, TPB, HOMOG ? 16 : 24, 0>;
-template <int A, int B, int TPB, bool HOMOG, bool ABS, int SRC>
-using WStageRho = WStage<A, B, TPB, 16, (HOMOG ? 0 : 16) + (ABS ? 8 : 0) + ((ABS && SRC == 1) ? 8 : 0)>;
+// SM ("stage the medium"): heterogeneous media append the rows of the medium maps an item needs to its stage, as in
+// fft_v2.cuh.  On long lines (N >= 512) that costs more in residency than it saves in latency -- a 768-point item with medium
+// rows is 18 KB, four groups per SM -- so there the rows are prefetched into L2 with the item and loaded where they are used.
+template <int A, int B, int TPB, bool HOMOG, bool SM> using WStageU = WStage<A, B, TPB, (HOMOG || !SM) ? 16 : 24, 0>;
+template <int A, int B, int TPB, bool HOMOG, bool SM, bool ABS, int SRC>
+using WStageRho = WStage<A, B, TPB, 16, ((HOMOG || !SM) ? 0 : 16) + (ABS ? 8 : 0) + ((ABS && SRC == 1) ? 8 : 0)>;
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// the B lanes of a group prefetch `bytes` (a row of N floats) into L2, one 128-byte line per lane and step
+template <int B> __device__ __forceinline__ void prefetch_row(const float* row, int bytes, int t) {
+  for (int o = 128 * t; o < bytes; o += 128 * B) prefetch_l2(reinterpret_cast<const char*>(row) + o);
+}
 
-template <int A, int B, int TPB, bool HOMOG>
+template <int A, int B, int TPB, bool HOMOG, bool SM>
 __global__ void __launch_bounds__(TPB) kw_x_u(StepParams P, V2Params Q) {
-  using XS = WStageU<A, B, TPB, HOMOG>;
+  using XS = WStageU<A, B, TPB, HOMOG, SM>;
   constexpr int N = A * B, G = XS::GROUPS;
   extern __shared__ __align__(16) unsigned char smraw[];
   const float4* tw = XS::load_tw(smraw, Q.tw4x);
@@ -477,9 +485,13 @@ __global__ void __launch_bounds__(TPB) kw_x_u(StepParams P, V2Params Q) {
       XS::copy(st, reinterpret_cast<const char*>(Q.Z4 + c * Q.ZS + (long long)pair * N), 8 * N, t);
       XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0), 4 * N, t);
       XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.u + c * P.RS + r0 + hi), 4 * N, t);
-      if constexpr (!HOMOG) {
+      if constexpr (!HOMOG && SM) {
         XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.dt_rho0_sg + c * P.RS + r0), 4 * N, t);
         XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.dt_rho0_sg + c * P.RS + r0 + hi), 4 * N, t);
+      }
+      if constexpr (!HOMOG && !SM) {
+        prefetch_row<B>(P.dt_rho0_sg + c * P.RS + r0, 4 * N, t);
+        prefetch_row<B>(P.dt_rho0_sg + c * P.RS + r0 + hi, 4 * N, t);
       }
     }
     cp_async_commit();
@@ -508,6 +520,7 @@ __global__ void __launch_bounds__(TPB) kw_x_u(StepParams P, V2Params Q) {
       __syncwarp();
       wline_fft<A, B, true>(v, tw, zb, t);
       float* u = P.u + c * P.RS + r0;
+      const float* mr = P.dt_rho0_sg + c * P.RS + r0;
       float2 s;
       if (c == 1) s = make_float2(P.sgy[ylo], P.sgy[ylo + Q.Ry]);
       else if (c == 2) s.x = s.y = P.sgz[z];
@@ -517,7 +530,8 @@ __global__ void __launch_bounds__(TPB) kw_x_u(StepParams P, V2Params Q) {
         if (c == 0) s.x = s.y = P.sgx[x];
         float2 d;
         if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_sg_s; }
-        else { d.x = -rb[2 * N + x]; d.y = -rb[3 * N + x]; }
+        else if constexpr (SM) { d.x = -rb[2 * N + x]; d.y = -rb[3 * N + x]; }
+        else { d.x = -mr[x]; d.y = -mr[hi + x]; }
         const float2 un = __fmul2_rn(s, __ffma2_rn(d, v[i], __fmul2_rn(s, make_float2(rb[x], rb[N + x]))));
         u[x] = un.x;
         u[hi + x] = un.y;
@@ -539,9 +553,9 @@ __global__ void __launch_bounds__(TPB) kw_x_u(StepParams P, V2Params Q) {
 
 // SRC: 0 none, 1 filtered source in Z4[3].  ABS: absorbing medium (operands of the fractional Laplacians go to Z4[0], Z4[1],
 // sum rho waits in r1; kw_x_p finishes the step).
-template <int A, int B, int TPB, bool HOMOG, int SRC, bool ABS>
+template <int A, int B, int TPB, bool HOMOG, bool SM, int SRC, bool ABS>
 __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
-  using XS = WStageRho<A, B, TPB, HOMOG, ABS, SRC>;
+  using XS = WStageRho<A, B, TPB, HOMOG, SM, ABS, SRC>;
   constexpr int N = A * B, G = XS::GROUPS;
   constexpr int NI = (SRC == 1 ? 5 : 4) - (ABS ? 1 : 0);
   constexpr int C0 = SRC == 1 ? 1 : 0;
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
   char* gbase = reinterpret_cast<char*>(smraw) + g * XS::GBYTES;
   char* mbase = gbase + 2 * XS::BYTES;
   // absorbing medium: the running sum of the velocity gradients lives in thread-private shared-memory slots (x = t + B i)
-  float2* dsl = reinterpret_cast<float2*>(mbase + (HOMOG ? 0 : 16 * N));
+  float2* dsl = reinterpret_cast<float2*>(mbase + ((HOMOG || !SM) ? 0 : 16 * N));
   float2* srl = dsl + N;                               // ... and with it the source rows (register budget)
   constexpr bool SRC_SM = ABS && SRC == 1;
   const long long hi = (long long)Q.Ry * N;
@@ -573,11 +587,15 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.rho + c * P.RS + r0 + hi), 4 * N, t);
         }
-        if constexpr (!HOMOG) {
+        if constexpr (!HOMOG && SM) {
           if (c == 0) {
             XS::copy(mbase + slot * 8 * N, reinterpret_cast<const char*>(P.dt_rho0 + r0), 4 * N, t);
             XS::copy(mbase + slot * 8 * N + 4 * N, reinterpret_cast<const char*>(P.dt_rho0 + r0 + hi), 4 * N, t);
           }
+        }
+        if constexpr (!HOMOG && !SM) {
+          if (c == 0) { prefetch_row<B>(P.dt_rho0 + r0, 4 * N, t); prefetch_row<B>(P.dt_rho0 + r0 + hi, 4 * N, t); }
+          if (c == 2 && !ABS) { prefetch_row<B>(P.c2 + r0, 4 * N, t); prefetch_row<B>(P.c2 + r0 + hi, 4 * N, t); }
         }
       } else {
         const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
@@ -608,7 +626,8 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
       const int stage = (par + ci) & 1;
       float2* zb = reinterpret_cast<float2*>(gbase + stage * XS::BYTES);
       const float* rb = reinterpret_cast<const float*>(gbase + stage * XS::BYTES + 8 * N);
-      const float* mb = reinterpret_cast<const float*>(mbase + (it & 1) * 8 * N);
+      const float* mb = SM ? reinterpret_cast<const float*>(mbase + (it & 1) * 8 * N) : P.dt_rho0 + r0;   // rows lo / hi
+      const long long mhi = SM ? (long long)N : hi;
       if (c < 3) {
         float2 v[B];
         if (act) {
@@ -635,7 +654,7 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
             if (c == 0) a.x = a.y = P.pmlx[x];
             float2 d;
             if constexpr (HOMOG) { d.x = d.y = -P.dt_rho0_s; }
-            else { d.x = -mb[x]; d.y = -mb[N + x]; }
+            else { d.x = -mb[x]; d.y = -mb[mhi + x]; }
             float2 rn = __fmul2_rn(a, __ffma2_rn(d, v[i], __fmul2_rn(a, make_float2(rb[x], rb[N + x]))));
             if constexpr (SRC == 1) rn = cadd(rn, SRC_SM ? srl[x] : src[SRC_SM ? 0 : i]);
             rho[x] = rn.x;
@@ -649,7 +668,7 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
               for (int i = 0; i < A; ++i) {
                 const int x = t + B * i;
                 float2 r0v;
-                if constexpr (HOMOG) { r0v.x = r0v.y = P.rho0_s; } else { r0v.x = mb[x] * P.inv_dt; r0v.y = mb[N + x] * P.inv_dt; }
+                if constexpr (HOMOG) { r0v.x = r0v.y = P.rho0_s; } else { r0v.x = mb[x] * P.inv_dt; r0v.y = mb[mhi + x] * P.inv_dt; }
                 v[i] = __fmul2_rn(r0v, dsl[x]);
                 P.r1[r0 + x] = sum[i].x;
                 P.r1[r0 + hi + x] = sum[i].y;
@@ -722,9 +741,9 @@ __global__ void __launch_bounds__(TPB) kw_x_rho_p(StepParams P, V2Params Q) {
 }
 
 // Absorbing medium, last pass of the step: p = c0^2 (sum rho + tau L1 - eta L2), running max/min, FFT_x of p -> ZP.
-template <int A, int B, int TPB, bool HOMOG>
+template <int A, int B, int TPB, bool HOMOG, bool SM>
 __global__ void __launch_bounds__(TPB) kw_x_p(StepParams P, V2Params Q, int use_tau, int use_eta) {
-  using XS = WStageU<A, B, TPB, HOMOG>;
+  using XS = WStageU<A, B, TPB, HOMOG, SM>;
   constexpr int N = A * B, G = XS::GROUPS;
   constexpr int NI = 3;
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -748,15 +767,21 @@ __global__ void __launch_bounds__(TPB) kw_x_p(StepParams P, V2Params Q, int use_
         if (c == 0) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.r1 + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.r1 + r0 + hi), 4 * N, t);
-          if constexpr (!HOMOG) {
+          if constexpr (!HOMOG && SM) {
             XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.tau + r0), 4 * N, t);
             XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.tau + r0 + hi), 4 * N, t);
           }
+          if constexpr (!HOMOG && !SM) { prefetch_row<B>(P.tau + r0, 4 * N, t); prefetch_row<B>(P.tau + r0 + hi, 4 * N, t); }
         } else if constexpr (!HOMOG) {
           XS::copy(st + 8 * N, reinterpret_cast<const char*>(P.eta + r0), 4 * N, t);
           XS::copy(st + 12 * N, reinterpret_cast<const char*>(P.eta + r0 + hi), 4 * N, t);
-          XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.c2 + r0), 4 * N, t);
-          XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.c2 + r0 + hi), 4 * N, t);
+          if constexpr (SM) {
+            XS::copy(st + 16 * N, reinterpret_cast<const char*>(P.c2 + r0), 4 * N, t);
+            XS::copy(st + 20 * N, reinterpret_cast<const char*>(P.c2 + r0 + hi), 4 * N, t);
+          } else {
+            prefetch_row<B>(P.c2 + r0, 4 * N, t);
+            prefetch_row<B>(P.c2 + r0 + hi, 4 * N, t);
+          }
         }
       } else {
         const bool zin = (unsigned)(z + P.z0 - P.pz) < (unsigned)P.nz;
@@ -798,13 +823,16 @@ __global__ void __launch_bounds__(TPB) kw_x_p(StepParams P, V2Params Q, int use_
           const int x = t + B * i;
           if (c == 0) {
             float2 ta;
-            if constexpr (HOMOG) { ta.x = ta.y = P.tau_s; } else { ta.x = rb[2 * N + x]; ta.y = rb[3 * N + x]; }
+            if constexpr (HOMOG) { ta.x = ta.y = P.tau_s; }
+            else if constexpr (SM) { ta.x = rb[2 * N + x]; ta.y = rb[3 * N + x]; }
+            else { ta.x = P.tau[r0 + x]; ta.y = P.tau[r0 + hi + x]; }
             const float2 s0 = make_float2(rb[x], rb[N + x]);
             acc[i] = use_tau ? __ffma2_rn(ta, v[i], s0) : s0;
           } else {
             float2 et, c2;
             if constexpr (HOMOG) { et.x = et.y = -P.eta_s; c2.x = c2.y = P.c2_s; }
-            else { et.x = -rb[x]; et.y = -rb[N + x]; c2.x = rb[2 * N + x]; c2.y = rb[3 * N + x]; }
+            else if constexpr (SM) { et.x = -rb[x]; et.y = -rb[N + x]; c2.x = rb[2 * N + x]; c2.y = rb[3 * N + x]; }
+            else { et.x = -rb[x]; et.y = -rb[N + x]; c2.x = P.c2[r0 + x]; c2.y = P.c2[r0 + hi + x]; }
             if (use_eta) acc[i] = __ffma2_rn(et, v[i], acc[i]);
             acc[i] = __fmul2_rn(c2, acc[i]);
             if (Q.store_p) { P.p[r0 + x] = acc[i].x; P.p[r0 + hi + x] = acc[i].y; }

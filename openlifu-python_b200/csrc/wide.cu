@@ -86,8 +86,8 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   int nk = 0;
   // exchange-bearing kernels of a slab decomposition: 128-byte row segments for the NVLink stores (measured at 2 GPUs:
   // y-forward + exchange stages 30 % shorter); one GPU: 64-byte segments, two CTAs per SM (LIFU_WIDE_LANES=8|16 overrides)
-  bool x16 = slab;
-  if (const char* e = getenv("LIFU_WIDE_LANES")) x16 = atoi(e) == 16;
+  bool x16 = slab, zdiv16 = true;            // the divergence z pass is the one strided kernel that is faster on 16-lane tiles
+  if (const char* e = getenv("LIFU_WIDE_LANES")) x16 = zdiv16 = atoi(e) == 16;
   auto sync_ranks = [&]() -> int { if (slab && barrier) { ++nk; return barrier(); } return LIFU_OK; };
   // (1) pressure gradient
   WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
@@ -119,7 +119,7 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));

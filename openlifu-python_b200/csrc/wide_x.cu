@@ -21,26 +21,27 @@ static void wlaunch_persistent(lifu_sim* s, K kernel, int tpb, size_t sm, int nb
   kernel<<<grid, tpb, sm, s->stream>>>(args...);
 }
 
-template <int A, int B, int TPB, bool HOMOG>
+// TPB: threads per CTA of the kernels without / with the absorption operands (the latter keep a running sum in shared memory)
+template <int A, int B, int TPB, int TPB_ABS, bool HOMOG, bool SM>
 static void wide_x_run(lifu_sim* s, int op, int src) {
-  constexpr int G = TPB / B;
   const V2Params& Q = s->Q;
-  const int nbatch = (int)((long long)Q.Nz * (Q.Ny / 2) / G);
+  const long long pairs = (long long)Q.Nz * (Q.Ny / 2);
+  const int nbatch = (int)(pairs / (TPB / B)), nbatch_abs = (int)(pairs / (TPB_ABS / B));
   if (op == 0) {
-    wlaunch_persistent(s, kw_x_u<A, B, TPB, HOMOG>, TPB, WStageU<A, B, TPB, HOMOG>::SMEM, nbatch, s->P, s->Q);
+    wlaunch_persistent(s, kw_x_u<A, B, TPB, HOMOG, SM>, TPB, WStageU<A, B, TPB, HOMOG, SM>::SMEM, nbatch, s->P, s->Q);
   } else if (op == 1) {
-    constexpr size_t sma1 = WStageRho<A, B, TPB, HOMOG, true, 1>::SMEM, sma = WStageRho<A, B, TPB, HOMOG, true, 0>::SMEM;
-    constexpr size_t sm = WStageRho<A, B, TPB, HOMOG, false, 0>::SMEM;
     if (s->absorbing) {
-      if (src) wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, 1, true>, TPB, sma1, nbatch, s->P, s->Q);
-      else wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, 0, true>, TPB, sma, nbatch, s->P, s->Q);
+      constexpr size_t sma1 = WStageRho<A, B, TPB_ABS, HOMOG, SM, true, 1>::SMEM, sma = WStageRho<A, B, TPB_ABS, HOMOG, SM, true, 0>::SMEM;
+      if (src) wlaunch_persistent(s, kw_x_rho_p<A, B, TPB_ABS, HOMOG, SM, 1, true>, TPB_ABS, sma1, nbatch_abs, s->P, s->Q);
+      else wlaunch_persistent(s, kw_x_rho_p<A, B, TPB_ABS, HOMOG, SM, 0, true>, TPB_ABS, sma, nbatch_abs, s->P, s->Q);
     } else {
-      if (src) wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, 1, false>, TPB, sm, nbatch, s->P, s->Q);
-      else wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, 0, false>, TPB, sm, nbatch, s->P, s->Q);
+      constexpr size_t sm = WStageRho<A, B, TPB, HOMOG, SM, false, 0>::SMEM;
+      if (src) wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, SM, 1, false>, TPB, sm, nbatch, s->P, s->Q);
+      else wlaunch_persistent(s, kw_x_rho_p<A, B, TPB, HOMOG, SM, 0, false>, TPB, sm, nbatch, s->P, s->Q);
     }
   } else if (op == 2) {
     const int use_tau = s->alpha_mode != LIFU_ALPHA_NO_ABSORPTION, use_eta = s->alpha_mode != LIFU_ALPHA_NO_DISPERSION;
-    wlaunch_persistent(s, kw_x_p<A, B, TPB, HOMOG>, TPB, WStageU<A, B, TPB, HOMOG>::SMEM, nbatch, s->P, s->Q, use_tau, use_eta);
+    wlaunch_persistent(s, kw_x_p<A, B, TPB, HOMOG, SM>, TPB, WStageU<A, B, TPB, HOMOG, SM>::SMEM, nbatch, s->P, s->Q, use_tau, use_eta);
   }
 }
 
@@ -60,9 +61,13 @@ void WX_NAME(WX_A, WX_B)(lifu_sim* s, int op, int src) {
     kw_x_src<A, B><<<gs, 256, sm, s->stream>>>(s->P, s->Q);
     return;
   }
-  constexpr int TPB_HET = N >= 512 ? 64 : 128;     // heterogeneous media stage 24 bytes per point: keep >= 2 CTAs per SM
-  if (s->homogeneous) wide_x_run<A, B, 128, true>(s, op, src);
-  else wide_x_run<A, B, TPB_HET, false>(s, op, src);
+  // long lines: 64-thread CTAs where a group's staging is large (medium rows, running sum of the absorbing kernel), so that
+  // at least two CTAs stay resident per SM.  Not staging the medium rows (SM = false: prefetch into L2, load where used)
+  // would fit six to eight groups per SM but measured slower -- 768^3: kw_x_u 8.4 -> 9.9 ms, kw_x_rho_abs 10.6 -> 18.7 ms
+  // (profiles/r2_wide_summary.md) -- so the rows stay in the stages.
+  constexpr bool LONG = N >= 512;
+  if (s->homogeneous) wide_x_run<A, B, 128, LONG ? 64 : 128, true, true>(s, op, src);
+  else wide_x_run<A, B, LONG ? 64 : 128, LONG ? 64 : 128, false, true>(s, op, src);
 }
 
 }  // namespace lifu

@@ -45,6 +45,19 @@ def v2_small_case(steps=80):
                      dt=3e-7, t_end=steps * 3e-7, name="v2_small")
 
 
+WIDE_PML = (10, 10, 10)
+
+
+def wide_case(n_exp, steps=60, name="wide"):
+    """Water, 1 mm grid whose PML-expanded size (PML 10 per side) is n_exp; 2 x 2 array at z = 0 focused at 18 mm.
+    The grids of pipeline "wide" (csrc/fft_wide.cuh): 128 / 512 / 768 / 1024-point axes next to 64 and 256."""
+    n = [e - 2 * p for e, p in zip(n_exp, WIDE_PML)]
+    ext = [(-(n[0] // 2), n[0] - 1 - n[0] // 2), (-(n[1] // 2), n[1] - 1 - n[1] // 2), (-3, n[2] - 4)]
+    case = make_case(ext, 1.0, 2, 2, 3.0, 0.5, (0, 0, 18), 400e3, 2, dt=3e-7, t_end=steps * 3e-7, name=name)
+    assert case["N"] == n, (case["N"], n)
+    return case
+
+
 def c1_case():
     """8x8 array, 4 mm pitch, focus 50 mm, water, 1 mm grid."""
     return make_case([(-30, 30), (-30, 30), (-4, 70)], 1.0, 8, 8, 4.0, 0.5, (0, 0, 50), 400e3, 10, name="C1")

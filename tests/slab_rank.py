@@ -26,8 +26,7 @@ def build_case(name, steps):
     from tests import cases
     if name.startswith("wide"):
         # 128 x 64 x 128 expanded (8 x 16 factorisations on x and z): the fused passes with routed stores on > 1 rank
-        from tests.test_gpu_wide import wide_case
-        case = wide_case((128, 64, 128), steps=steps)
+        case = cases.wide_case((128, 64, 128), steps=steps)
         if name == "wide_phantom":
             case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))
             case["dt"], case["t_end"] = 1.5e-7, steps * 1.5e-7

@@ -57,8 +57,7 @@ def test_single_rank_slab_peer_library_transforms(lifu_lib, monkeypatch):
 def test_single_rank_slab_fused_passes_on_a_wide_grid(lifu_lib, medium):
     """128 x 64 x 128 expanded grid (8 x 16 factorisations on x and z) through the slab code path of the fused passes:
     routed stores into the (own) transposed buffer, source planes through T4[3], sensor crop of the local planes."""
-    from tests.test_gpu_wide import wide_case
-    case = wide_case((128, 64, 128), steps=60)
+    case = cases.wide_case((128, 64, 128), steps=60)
     if medium == "phantom":
         case["c0"], case["rho0"], case["alpha"] = cases.layered_phantom(tuple(case["N"]))
         case["dt"], case["t_end"] = 1.5e-7, 60 * 1.5e-7

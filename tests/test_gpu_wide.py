@@ -12,16 +12,8 @@ from tests import cases
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
-PML = (10, 10, 10)
-
-
-def wide_case(n_exp, steps=60, name="wide"):
-    """Water, 1 mm grid whose PML-expanded size (PML 10 per side) is n_exp; 2 x 2 array at z = 0 focused at 18 mm."""
-    n = [e - 2 * p for e, p in zip(n_exp, PML)]
-    ext = [(-(n[0] // 2), n[0] - 1 - n[0] // 2), (-(n[1] // 2), n[1] - 1 - n[1] // 2), (-3, n[2] - 4)]
-    case = cases.make_case(ext, 1.0, 2, 2, 3.0, 0.5, (0, 0, 18), 400e3, 2, dt=3e-7, t_end=steps * 3e-7, name=name)
-    assert case["N"] == n, (case["N"], n)
-    return case
+PML = cases.WIDE_PML
+wide_case = cases.wide_case
 
 
 def _oracle(case, **kw):
