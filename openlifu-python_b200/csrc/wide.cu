@@ -69,6 +69,11 @@ template <int A, int B, int L32> static dim3 wgrid(const V2Params& Q, int n_othe
   return dim3((unsigned)(Q.Nx / (2 * Wide<A, B, L32>::LANES) + 1), (unsigned)n_other, (unsigned)nz);
 }
 
+// pressure-gradient z pass: two chains per tile, interleaved along grid.x
+template <int A, int B, int L32> static dim3 wgrid2(const V2Params& Q, int n_other) {
+  return dim3((unsigned)(2 * (Q.Nx / (2 * Wide<A, B, L32>::LANES) + 1)), (unsigned)n_other, 1u);
+}
+
 // kind: 0 no source, 1 source active (filtered additive source).
 // Slab decomposition (Q.G > 0, `barrier` given): the y-forward kernels store straight into the owners' transposed buffers
 // and the z kernels straight back into the owners' plane buffers over NVLink, so an exchange is the store phase of a
@@ -93,7 +98,7 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_y_fwd_p+xchg" : "kw_y_fwd_p", 8);
-  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, nky, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 0, WL>, wgrid2<WA, WB, WL>(Q, nky), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, true, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
