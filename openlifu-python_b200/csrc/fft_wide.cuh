@@ -291,10 +291,18 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   wmerge_store<A, B>(Q.Z4 + comp * Q.ZS + ((long long)zc * (Q.Ny / 2) + t) * Q.Nx, a, kx, Q.Nx, live);
 }
 
+// exact kappa / source filter (sinf / cosf with their argument-reduction slow paths) out of line: inlined at the 32 unrolled
+// sites of kw_z they made the kernel 10.8 K instructions long, a quarter of its stall samples sat in that region with
+// instruction-fetch stalls although the polynomial branch is the one that runs (profiles/r2_wide512_zdiv_stalls.txt)
+static __device__ __noinline__ float wkappa_exact(float a2) { return kappa_of(a2); }
+static __device__ __noinline__ float wcos_exact(float a2) { return cosf(sqrtf(a2)); }
+
 // z passes, one transform chain per CTA.  grid (tiles + 1, Ny | Ny blocks, chains)
 // OP 0 pressure gradient: chain 0: H4[2] <- IFFT_z[kappa FFT_z H4[0]]; chain 1: H4[1] <- IFFT_z[i kz e^{+i kz dz/2} kappa FFT_z H4[0]]
-// OP 1 divergence, in place: comps comp0 .. : kappa (0, 1), i kz e^{-i kz dz/2} kappa (2), source slab x cos(c_ref k dt/2) (3)
+// OP 1 divergence, in place: comps comp0 .. : kappa (0, 1), i kz e^{-i kz dz/2} kappa (2)
 // OP 2 absorption operands, in place: k^(y-2) (0), k^(y-1) (1)
+// OP 3 source field: source slab (or T4[3] of a slab decomposition) x cos(c_ref k dt/2) -> H4[3]; its own instantiation so
+//      that the divergence chains do not carry the unrolled cosine code
 template <int A, int B, int OP, int L32 = 8>
 __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_z(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -303,7 +311,7 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   // OP 0: the two chains of a tile sit in neighbouring CTAs (grid.x = 2 x tiles), so the second read of the column tile
   // finds it in L2 (with the chain in grid.z it came from DRAM again: 2.2 GB per launch instead of 1.6 GB at 512^3)
-  const int chain = OP == 0 ? ((int)blockIdx.x & 1) : (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0);
+  const int chain = OP == 0 ? ((int)blockIdx.x & 1) : (OP == 3 ? 3 : (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0));
   int kx, ky;
   const int nky = Q.G ? Q.Nyl : Q.Ny;                 // ky rows held here (all of them without a slab decomposition)
   if (!wlane_map<L>(Q, nky, l, kx, ky, (int)blockIdx.y, OP == 0 ? (int)blockIdx.x >> 1 : (int)blockIdx.x)) return;
@@ -317,7 +325,7 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   const float2* in = OP == 0 ? base + col : base + chain * Q.HS + col;
   const int fout = OP == 0 ? (chain == 0 ? 2 : 1) : chain;
   float2 v[B];
-  if (OP == 1 && chain == 3) {
+  if (OP == 3) {
     if (Q.G) {
       // the owners of the source planes stored their rows into T4[3]; the other planes of that field are not defined
 #pragma unroll
@@ -355,8 +363,8 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
         const int kz = t + A * kb;
         const float a2 = axy + P.az2[kz];
         float m;
-        if (OP == 1 && chain == 3) m = P.poly_ok == 2 ? cos_sqrt_poly8(a2) : (P.poly_ok == 1 ? cos_sqrt_poly(a2) : cosf(sqrtf(a2)));
-        else m = P.poly_ok == 2 ? sinc_sqrt_poly8(a2) : (P.poly_ok == 1 ? sinc_sqrt_poly(a2) : kappa_of(a2));
+        if (OP == 3) m = P.poly_ok == 2 ? cos_sqrt_poly8(a2) : (P.poly_ok == 1 ? cos_sqrt_poly(a2) : wcos_exact(a2));
+        else m = P.poly_ok == 2 ? sinc_sqrt_poly8(a2) : (P.poly_ok == 1 ? sinc_sqrt_poly(a2) : wkappa_exact(a2));
         v[kb] = cscale(v[kb], m * Q.norm);
         if (OP == 0 && chain == 1) v[kb] = cmul4(v[kb], Q.dpz4[kz]);
         if (OP == 1 && chain == 2) v[kb] = cmul4(v[kb], Q.dnz4[kz]);

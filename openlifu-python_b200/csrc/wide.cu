@@ -124,7 +124,11 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  if (src) {
+    WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 3, WL>, wgrid<WA, WB, WL>(Q, nky, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+    ++nk;
+  }
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
