@@ -394,6 +394,133 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   }
 }
 
+// EXPERIMENT (instantiated only with -DLIFU_WIDE_ZP, measured slower than kw_z: profiles/r2_wide_summary.md).
+// The same z chains as kw_z in PERSISTENT CTAs that keep the column tile of their next item in flight.  A chain is
+// load -> DFT -> exchange -> DFT -> operator -> DFT -> exchange -> DFT -> store; with two short-lived CTAs per SM the loads of
+// one CTA overlap only whatever the other happens to compute (kw_z: 1.3 TB/s of DRAM traffic against 4.3 TB/s for the
+// one-transform y kernels of the same tile shape, profiles/r2_wide_summary.md).  Here every thread copies ITS OWN A values of
+// the next item into thread-private shared-memory slots with cp.async (no barrier: a thread reads back only what it copied
+// itself) as soon as the forward transform of the current item is through, so a tile is on its way during the rest of the chain.
+// Items = (tile, chain) with the chain fastest: the two gradient chains of a tile run in neighbouring CTAs at the same time
+// (second read from L2).  grid = resident CTAs (wide.cu), `nchain` = chains per tile.
+__device__ __forceinline__ void cp_async8w(void* sdst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+template <int A, int B, int L32 = 8> struct WideZP {
+  using W = Wide<A, B, L32>;
+  static constexpr int STAGE = A * W::THREADS * 8;               // bytes: A complex values per thread
+  static constexpr int SMEM = W::XCH + W::TW + STAGE;
+};
+
+template <int A, int B, int OP, int L32 = 8>
+__global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_zp(StepParams P, V2Params Q, int nchain) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  using W = Wide<A, B, L32>;
+  constexpr int L = W::LANES, TH = W::THREADS;
+  const int tid = threadIdx.x, l = tid % L, t = tid / L;
+  float2* xa = reinterpret_cast<float2*>(smraw);
+  float2* stage = reinterpret_cast<float2*>(smraw + W::XCH + W::TW) + tid;      // this thread's slots: stage[i * TH]
+  const int nky = Q.G ? Q.Nyl : Q.Ny;
+  const int nxt = Q.Nx / (2 * L);
+  const int nreg = nxt * nky;                                                   // regular tiles, then the Nyquist column
+  const int nitem = (nreg + (nky + L - 1) / L) * nchain;
+  const long long zs = Q.G ? (long long)Q.Nyl * Q.PH : Q.zsH;
+  const float2* base = Q.G ? Q.T4 : Q.H4;
+  auto decode = [&](int it, int& chain, int& kx, int& ky) {
+    const int tile = it / nchain;
+    chain = OP == 3 ? 3 : (it - tile * nchain) + (OP == 1 ? Q.comp0 : 0);
+    if (tile < nreg) { const int by = tile / nxt; kx = (tile - by * nxt) * L + l; ky = by; }
+    else { kx = Q.Nx >> 1; ky = (tile - nreg) * L + l; }
+  };
+  auto issue = [&](int it) {
+    if (it < nitem) {
+      int chain, kx, ky;
+      decode(it, chain, kx, ky);
+      const int kyc = ky < nky ? ky : nky - 1;
+      const long long col = (long long)kyc * Q.PH + kx;
+      if (OP == 3) {
+        const float2* in = Q.G ? base + 3 * Q.HS + col : Q.HSslab + col;
+        const int z0 = Q.G ? Q.gz0s : Q.z0s, nz = Q.G ? Q.gnzs : Q.nzs;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+          const int z = t + B * i, zr = z - z0;
+          if (zr >= 0 && zr < nz) cp_async8w(stage + i * TH, in + (long long)(Q.G ? z : zr) * zs);
+          else stage[i * TH] = make_float2(0.f, 0.f);
+        }
+      } else {
+        const float2* in = (OP == 0 ? base : base + chain * Q.HS) + col;
+#pragma unroll
+        for (int i = 0; i < A; ++i) cp_async8w(stage + i * TH, in + (long long)(t + B * i) * zs);
+      }
+    }
+    cp_async_commit();
+  };
+  int it = blockIdx.x;
+  issue(it);
+  const float4* tw = W::load_tw(smraw, Q.tw4z);
+  for (; it < nitem; it += gridDim.x) {
+    int chain, kx, ky;
+    decode(it, chain, kx, ky);
+    const bool live = ky < nky;
+    const int kyc = live ? ky : nky - 1;
+    const int kyg = kyc + (Q.G ? Q.ky0 : 0);
+    const long long col = (long long)kyc * Q.PH + kx;
+    const int fout = OP == 0 ? (chain == 0 ? 2 : 1) : chain;
+    cp_async_wait<0>();
+    float2 v[B];
+#pragma unroll
+    for (int i = 0; i < A; ++i) v[i] = stage[i * TH];
+    wfft_strided<A, B, false, L32>(v, tw, xa, l, t);
+    issue(it + gridDim.x);                          // the slots were consumed by the first DFT: next tile on its way
+    if (A == B || t < A) {
+      if (OP == 2) {
+        const float kxy = P.kx2[kx] + P.ky2[kyg];
+        const float e = chain == 0 ? P.y_minus2_half : P.y_minus1_half;
+#pragma unroll
+        for (int kb = 0; kb < B; ++kb) {
+          const float k2 = kxy + P.kz2[t + A * kb];
+          v[kb] = cscale(v[kb], k2 > 0.f ? __powf(k2, e) * Q.norm : 0.f);
+        }
+      } else {
+        const float axy = P.ax2[kx] + P.ay2[kyg];
+#pragma unroll
+        for (int kb = 0; kb < B; ++kb) {
+          const int kz = t + A * kb;
+          const float a2 = axy + P.az2[kz];
+          float m;
+          if (OP == 3) m = P.poly_ok == 2 ? cos_sqrt_poly8(a2) : (P.poly_ok == 1 ? cos_sqrt_poly(a2) : wcos_exact(a2));
+          else m = P.poly_ok == 2 ? sinc_sqrt_poly8(a2) : (P.poly_ok == 1 ? sinc_sqrt_poly(a2) : wkappa_exact(a2));
+          v[kb] = cscale(v[kb], m * Q.norm);
+          if (OP == 0 && chain == 1) v[kb] = cmul4(v[kb], Q.dpz4[kz]);
+          if (OP == 1 && chain == 2) v[kb] = cmul4(v[kb], Q.dnz4[kz]);
+        }
+      }
+    }
+    __syncthreads();                               // the exchange buffer is read out before the inverse reuses it
+    wfft_strided<A, B, true, L32>(v, tw, xa, l, t);
+    if (live) {
+      if (Q.G == 0) {
+        float2* out = Q.H4 + fout * Q.HS + col;
+#pragma unroll
+        for (int i = 0; i < A; ++i) out[(long long)(t + B * i) * zs] = v[i];
+      } else {
+        const long long rowg = (long long)kyg * Q.PH + kx;
+        const int ag = A / Q.G;
+        int q = 0, rem = 0;
+        float2* dst = Q.peer[0] + fout * Q.HS + (long long)t * Q.zsH + rowg;
+#pragma unroll
+        for (int i = 0; i < A; ++i) {
+          dst[(long long)rem * B * Q.zsH] = v[i];
+          if (++rem == ag) { rem = 0; ++q; if (q < Q.G) dst = Q.peer[q] + fout * Q.HS + (long long)t * Q.zsH + rowg; }
+        }
+      }
+    }
+    __syncthreads();                               // ... and before the next item's forward transform writes it
+  }
+  cp_async_wait<0>();
+}
+
 // ------------------------------------------------------------------------------------------------
 // x passes
 // Line transform of a group of B lanes inside one warp; exchange in `sm` (N float2) with a rotation swizzle.

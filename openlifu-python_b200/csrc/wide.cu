@@ -74,6 +74,35 @@ template <int A, int B, int L32> static dim3 wgrid2(const V2Params& Q, int n_oth
   return dim3((unsigned)(2 * (Q.Nx / (2 * Wide<A, B, L32>::LANES) + 1)), (unsigned)n_other, 1u);
 }
 
+// z chains: one chain per CTA (kw_z).  The persistent prefetching variant (kw_zp, fft_wide.cuh) is built only with
+// -DLIFU_WIDE_ZP and taken with LIFU_WIDE_ZPERSIST=1: parity-green but measured SLOWER (768^3: z_grad 4.8 -> 6.6 ms, z_div
+// 9.4 -> 10.9 ms, z_absorb 3.3 -> 4.4 ms; profiles/r2_wide_summary.md) -- like the TMA-fed z passes of round 1, keeping the
+// next tile in flight does not help a chain that is bound by its own dependent DFT / exchange / barrier sequence.
+template <int A, int B, int OP, int L32>
+static void wlaunch_z(lifu_sim* s, const V2Params& Q, int nky, int nchain, bool persist) {
+  using W = Wide<A, B, L32>;
+  cudaStream_t st = s->stream;
+#ifndef LIFU_WIDE_ZP
+  persist = false;
+#endif
+  if (!persist) {
+    if (OP == 0) wlaunch(kw_z<A, B, OP, L32>, wgrid2<A, B, L32>(Q, nky), W::THREADS, W::SMEM, st, s->P, Q);
+    else wlaunch(kw_z<A, B, OP, L32>, wgrid<A, B, L32>(Q, nky, nchain), W::THREADS, W::SMEM, st, s->P, Q);
+    return;
+  }
+#ifdef LIFU_WIDE_ZP
+  constexpr size_t sm = WideZP<A, B, L32>::SMEM;
+  auto kern = kw_zp<A, B, OP, L32>;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W::THREADS, sm) != cudaSuccess || occ < 1) { occ = 1; cudaGetLastError(); }
+  const int nxt = Q.Nx / (2 * W::LANES);
+  const long long nitem = ((long long)nxt * nky + (nky + W::LANES - 1) / W::LANES) * nchain;
+  const int grid = (int)std::min<long long>(nitem, (long long)s->n_sm * occ);
+  kern<<<grid, W::THREADS, sm, st>>>(s->P, Q, nchain);
+#endif
+}
+
 // kind: 0 no source, 1 source active (filtered additive source).
 // Slab decomposition (Q.G > 0, `barrier` given): the y-forward kernels store straight into the owners' transposed buffers
 // and the z kernels straight back into the owners' plane buffers over NVLink, so an exchange is the store phase of a
@@ -93,12 +122,14 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // y-forward + exchange stages 30 % shorter); one GPU: 64-byte segments, two CTAs per SM (LIFU_WIDE_LANES=8|16 overrides)
   bool x16 = slab, zdiv16 = true;            // the divergence z pass is the one strided kernel that is faster on 16-lane tiles
   if (const char* e = getenv("LIFU_WIDE_LANES")) x16 = zdiv16 = atoi(e) == 16;
+  bool zpersist = false;                       // experiment switch, see wlaunch_z
+  if (const char* e = getenv("LIFU_WIDE_ZPERSIST")) zpersist = e[0] == '1';
   auto sync_ranks = [&]() -> int { if (slab && barrier) { ++nk; return barrier(); } return LIFU_OK; };
   // (1) pressure gradient
   WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_y_fwd_p+xchg" : "kw_y_fwd_p", 8);
-  WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 0, WL>, wgrid2<WA, WB, WL>(Q, nky), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, x16, (wlaunch_z<WA, WB, 0, WL>(s, Q, nky, 2, zpersist)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, true, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
@@ -124,9 +155,9 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 1, WL>, wgrid<WA, WB, WL>(Q, nky, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+  WIDE_ABL(Nz, zdiv16, (wlaunch_z<WA, WB, 1, WL>(s, Q, nky, 3, zpersist)));
   if (src) {
-    WIDE_ABL(Nz, zdiv16, (wlaunch(kw_z<WA, WB, 3, WL>, wgrid<WA, WB, WL>(Q, nky, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+    WIDE_ABL(Nz, zdiv16, (wlaunch_z<WA, WB, 3, WL>(s, Q, nky, 1, zpersist)));
     ++nk;
   }
   LIFU_CHECK(sync_ranks());
@@ -145,7 +176,7 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
     WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 3, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     LIFU_CHECK(sync_ranks());
     ++nk; mark(slab ? "kw_y_fwd_abs+xchg" : "kw_y_fwd_abs", 16);
-    WIDE_ABL(Nz, x16, (wlaunch(kw_z<WA, WB, 2, WL>, wgrid<WA, WB, WL>(Q, nky, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
+    WIDE_ABL(Nz, x16, (wlaunch_z<WA, WB, 2, WL>(s, Q, nky, 2, zpersist)));
     LIFU_CHECK(sync_ranks());
     ++nk; mark(slab ? "kw_z_absorb+xchg" : "kw_z_absorb", 16);
     WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
