@@ -303,7 +303,10 @@ static __device__ __noinline__ float wcos_exact(float a2) { return cosf(sqrtf(a2
 // OP 2 absorption operands, in place: k^(y-2) (0), k^(y-1) (1)
 // OP 3 source field: source slab (or T4[3] of a slab decomposition) x cos(c_ref k dt/2) -> H4[3]; its own instantiation so
 //      that the divergence chains do not carry the unrolled cosine code
-template <int A, int B, int OP, int L32 = 8>
+// PART 0: the whole chain.  PART 1 / 2 (experiment, LIFU_WIDE_ZSPLIT=1): the chain as two kernels -- forward transform +
+// operator, spectrum stored in natural kz order (gradient: into field 3, otherwise in place); then spectrum -> inverse
+// transform -> result.  Twice the traffic of the z pass for half the chain length per CTA.
+template <int A, int B, int OP, int L32 = 8, int PART = 0>
 __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MINB) kw_z(StepParams P, V2Params Q) {
   extern __shared__ __align__(16) unsigned char smraw[];
   using W = Wide<A, B, L32>;
@@ -311,10 +314,10 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   const int l = threadIdx.x % L, t = threadIdx.x / L;
   // OP 0: the two chains of a tile sit in neighbouring CTAs (grid.x = 2 x tiles), so the second read of the column tile
   // finds it in L2 (with the chain in grid.z it came from DRAM again: 2.2 GB per launch instead of 1.6 GB at 512^3)
-  const int chain = OP == 0 ? ((int)blockIdx.x & 1) : (OP == 3 ? 3 : (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0));
+  const int chain = OP == 0 ? (PART == 1 ? 0 : ((int)blockIdx.x & 1)) : (OP == 3 ? 3 : (int)blockIdx.z + (OP == 1 ? Q.comp0 : 0));
   int kx, ky;
   const int nky = Q.G ? Q.Nyl : Q.Ny;                 // ky rows held here (all of them without a slab decomposition)
-  if (!wlane_map<L>(Q, nky, l, kx, ky, (int)blockIdx.y, OP == 0 ? (int)blockIdx.x >> 1 : (int)blockIdx.x)) return;
+  if (!wlane_map<L>(Q, nky, l, kx, ky, (int)blockIdx.y, (OP == 0 && PART != 1) ? (int)blockIdx.x >> 1 : (int)blockIdx.x)) return;
   const bool live = ky < nky;
   const int kyc = live ? ky : nky - 1;
   const int kyg = kyc + (Q.G ? Q.ky0 : 0);           // global ky: index of the 1-D tables
@@ -325,7 +328,17 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
   const float2* in = OP == 0 ? base + col : base + chain * Q.HS + col;
   const int fout = OP == 0 ? (chain == 0 ? 2 : 1) : chain;
   float2 v[B];
-  if (OP == 3) {
+  // spectrum of a split chain: natural kz order, gradient in field 3, otherwise the chain's own field
+  float2* spec = const_cast<float2*>(base) + (OP == 0 ? 3 : chain) * Q.HS + col;
+  if (PART == 2) {
+    if (A == B || t < A) {
+#pragma unroll
+      for (int kb = 0; kb < B; ++kb) {
+        v[kb] = spec[(long long)(t + A * kb) * zs];
+        if (OP == 0 && chain == 1) v[kb] = cmul4(v[kb], Q.dpz4[t + A * kb]);
+      }
+    }
+  } else if (OP == 3) {
     if (Q.G) {
       // the owners of the source planes stored their rows into T4[3]; the other planes of that field are not defined
 #pragma unroll
@@ -346,8 +359,8 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
     for (int i = 0; i < A; ++i) v[i] = in[(long long)(t + B * i) * zs];
   }
   const float4* tw = W::load_tw(smraw, Q.tw4z);
-  wfft_strided<A, B, false, L32>(v, tw, xa, l, t);
-  if (A == B || t < A) {
+  if (PART != 2) wfft_strided<A, B, false, L32>(v, tw, xa, l, t);
+  if (PART != 2 && (A == B || t < A)) {
     if (OP == 2) {
       const float kxy = P.kx2[kx] + P.ky2[kyg];
       const float e = chain == 0 ? P.y_minus2_half : P.y_minus1_half;
@@ -366,12 +379,19 @@ __global__ void __launch_bounds__(Wide<A, B, L32>::THREADS, Wide<A, B, L32>::MIN
         if (OP == 3) m = P.poly_ok == 2 ? cos_sqrt_poly8(a2) : (P.poly_ok == 1 ? cos_sqrt_poly(a2) : wcos_exact(a2));
         else m = P.poly_ok == 2 ? sinc_sqrt_poly8(a2) : (P.poly_ok == 1 ? sinc_sqrt_poly(a2) : wkappa_exact(a2));
         v[kb] = cscale(v[kb], m * Q.norm);
-        if (OP == 0 && chain == 1) v[kb] = cmul4(v[kb], Q.dpz4[kz]);
+        if (PART == 0 && OP == 0 && chain == 1) v[kb] = cmul4(v[kb], Q.dpz4[kz]);
         if (OP == 1 && chain == 2) v[kb] = cmul4(v[kb], Q.dnz4[kz]);
       }
     }
   }
-  __syncthreads();                               // the exchange buffer is read out before the inverse reuses it
+  if (PART == 1) {
+    if (live && (A == B || t < A)) {
+#pragma unroll
+      for (int kb = 0; kb < B; ++kb) spec[(long long)(t + A * kb) * zs] = v[kb];
+    }
+    return;
+  }
+  if (PART == 0) __syncthreads();                // the exchange buffer is read out before the inverse reuses it
   wfft_strided<A, B, true, L32>(v, tw, xa, l, t);
   if (live) {
     if (Q.G == 0) {

@@ -78,17 +78,30 @@ template <int A, int B, int L32> static dim3 wgrid2(const V2Params& Q, int n_oth
 // -DLIFU_WIDE_ZP and taken with LIFU_WIDE_ZPERSIST=1: parity-green but measured SLOWER (768^3: z_grad 4.8 -> 6.6 ms, z_div
 // 9.4 -> 10.9 ms, z_absorb 3.3 -> 4.4 ms; profiles/r2_wide_summary.md) -- like the TMA-fed z passes of round 1, keeping the
 // next tile in flight does not help a chain that is bound by its own dependent DFT / exchange / barrier sequence.
+// returns the number of kernels launched
 template <int A, int B, int OP, int L32>
-static void wlaunch_z(lifu_sim* s, const V2Params& Q, int nky, int nchain, bool persist) {
+static int wlaunch_z(lifu_sim* s, const V2Params& Q, int nky, int nchain, bool persist) {
   using W = Wide<A, B, L32>;
   cudaStream_t st = s->stream;
 #ifndef LIFU_WIDE_ZP
   persist = false;
 #endif
   if (!persist) {
+    // Split chains (fft_wide.cuh, PART 1 / 2): forward transform + operator and the inverse transforms as two kernels.
+    // Measured (profiles/r2_wide_summary.md): the pressure gradient gains (one forward transform instead of one per chain:
+    // 768^3 4.84 -> 3.76 ms), divergence and absorption lose (twice the traffic: 9.4 -> 10.4, 3.3 -> 4.7 ms).  Default: the
+    // gradient on one GPU only; LIFU_WIDE_ZSPLIT=0 none, =1 every z pass.
+    static const int split_env = [] { const char* e = getenv("LIFU_WIDE_ZSPLIT"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+    const bool split = split_env == 1 || (split_env < 0 && OP == 0 && Q.G == 0);
+    if (split) {
+      wlaunch(kw_z<A, B, OP, L32, 1>, wgrid<A, B, L32>(Q, nky, OP == 0 ? 1 : nchain), W::THREADS, W::SMEM, st, s->P, Q);
+      if (OP == 0) wlaunch(kw_z<A, B, OP, L32, 2>, wgrid2<A, B, L32>(Q, nky), W::THREADS, W::SMEM, st, s->P, Q);
+      else wlaunch(kw_z<A, B, OP, L32, 2>, wgrid<A, B, L32>(Q, nky, nchain), W::THREADS, W::SMEM, st, s->P, Q);
+      return 2;
+    }
     if (OP == 0) wlaunch(kw_z<A, B, OP, L32>, wgrid2<A, B, L32>(Q, nky), W::THREADS, W::SMEM, st, s->P, Q);
     else wlaunch(kw_z<A, B, OP, L32>, wgrid<A, B, L32>(Q, nky, nchain), W::THREADS, W::SMEM, st, s->P, Q);
-    return;
+    return 1;
   }
 #ifdef LIFU_WIDE_ZP
   constexpr size_t sm = WideZP<A, B, L32>::SMEM;
@@ -101,6 +114,7 @@ static void wlaunch_z(lifu_sim* s, const V2Params& Q, int nky, int nchain, bool 
   const int grid = (int)std::min<long long>(nitem, (long long)s->n_sm * occ);
   kern<<<grid, W::THREADS, sm, st>>>(s->P, Q, nchain);
 #endif
+  return 1;
 }
 
 // kind: 0 no source, 1 source active (filtered additive source).
@@ -129,9 +143,9 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 0, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 1), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   LIFU_CHECK(sync_ranks());
   ++nk; mark(slab ? "kw_y_fwd_p+xchg" : "kw_y_fwd_p", 8);
-  WIDE_ABL(Nz, x16, (wlaunch_z<WA, WB, 0, WL>(s, Q, nky, 2, zpersist)));
+  WIDE_ABL(Nz, x16, (nk += wlaunch_z<WA, WB, 0, WL>(s, Q, nky, 2, zpersist)));
   LIFU_CHECK(sync_ranks());
-  ++nk; mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
+  mark(slab ? "kw_z_grad+xchg" : "kw_z_grad", 12);
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, true, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 3), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv_grad", 20);
   // (2) velocity update + forward x transform of the new velocity
@@ -155,13 +169,10 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
   // (4) divergence (+ filtered source) through z and back through y
   const int ncomp = src ? 4 : 3;
   Q.comp0 = 0;
-  WIDE_ABL(Nz, zdiv16, (wlaunch_z<WA, WB, 1, WL>(s, Q, nky, 3, zpersist)));
-  if (src) {
-    WIDE_ABL(Nz, zdiv16, (wlaunch_z<WA, WB, 3, WL>(s, Q, nky, 1, zpersist)));
-    ++nk;
-  }
+  WIDE_ABL(Nz, zdiv16, (nk += wlaunch_z<WA, WB, 1, WL>(s, Q, nky, 3, zpersist)));
+  if (src) WIDE_ABL(Nz, zdiv16, (nk += wlaunch_z<WA, WB, 3, WL>(s, Q, nky, 1, zpersist)));
   LIFU_CHECK(sync_ranks());
-  ++nk; mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
+  mark(slab ? "kw_z_div+xchg" : "kw_z_div", 24 + (src ? 4 + 4 * srcf : 0));
   WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, ncomp), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
   ++nk; mark("kw_y_inv", 8 * ncomp);
   // (5) density update, source, equation of state, sensor, forward x transform of p
@@ -176,9 +187,9 @@ int wide_enqueue_step(lifu_sim* s, int kind, int* n_kernels, const std::function
     WIDE_ABL(Ny, x16, (wlaunch(kw_y_fwd<WA, WB, 3, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     LIFU_CHECK(sync_ranks());
     ++nk; mark(slab ? "kw_y_fwd_abs+xchg" : "kw_y_fwd_abs", 16);
-    WIDE_ABL(Nz, x16, (wlaunch_z<WA, WB, 2, WL>(s, Q, nky, 2, zpersist)));
+    WIDE_ABL(Nz, x16, (nk += wlaunch_z<WA, WB, 2, WL>(s, Q, nky, 2, zpersist)));
     LIFU_CHECK(sync_ranks());
-    ++nk; mark(slab ? "kw_z_absorb+xchg" : "kw_z_absorb", 16);
+    mark(slab ? "kw_z_absorb+xchg" : "kw_z_absorb", 16);
     WIDE_ABL(Ny, false, (wlaunch(kw_y_inv<WA, WB, false, WL>, wgrid<WA, WB, WL>(Q, Q.Nz, 2), Wide<WA, WB, WL>::THREADS, Wide<WA, WB, WL>::SMEM, st, s->P, Q)));
     ++nk; mark("kw_y_inv_abs", 16);
     wide_x(s, 2, 0);
