@@ -9,16 +9,17 @@
 // Line transform.  A line of N = A * B points is transformed by B threads.  Real ("A") side: thread t < B holds
 // x[t + B i], i < A.  A register DFT of size A over i, the twiddle w_N^(t ka), ONE exchange through shared memory, then
 // threads u < A hold Y[t'][u] (t' < B) and do a register DFT of size B: X[u + A kb] sits in (thread u, register kb) --
-// the spectral ("B") side.  With A < B the threads u >= A idle through the second DFT (768: 8 of 32 lanes), which costs
-// no instruction issue (a warp runs the DFT once whatever its mask) and keeps everything in registers with one exchange --
-// the property that makes v2 fast.  The inverse runs the same steps backwards, so forward -> point-wise operator ->
-// inverse chains need no reordering.
+// the spectral ("B") side.  With A < B the threads u >= A idle through the second DFT (768: 8 of 32; whole warps in the
+// strided kernels, masked lanes in the x kernels, where a warp runs the DFT once whatever its mask) -- the price for keeping
+// everything in registers with one exchange, the property that makes v2 fast.  The inverse runs the same steps backwards,
+// so forward -> point-wise operator -> inverse chains need no reordering.
 //
 // Tiles of the strided (y, z) passes: CTA = LANES kx lanes x B threads (LANES = 8 when B = 32: 256 threads, 64-byte row
 // segments; 16 otherwise).  Every strided kernel here is ONE transform chain per CTA (component / pass = blockIdx.z):
 // with up to 32 complex registers per thread there is no room for the multi-component register pipelines of
 // k2_z_grad / k2_z_div / k2_y_inv_grad.  The pressure-gradient z pass is therefore out of place: H4[0] -> H4[2] (plain)
-// and H4[1] (z derivative).
+// and H4[1] (z derivative) -- on one GPU as a split chain (forward + kappa once into field 3, then the two inverse chains),
+// in a slab decomposition as two full chains whose stores are routed to the owning ranks.
 //
 // x passes: persistent CTAs, a group of B lanes owns one row pair at a time and prefetches its items two deep with
 // cp.async into private stages exactly as in fft_v2.cuh; the exchange runs inside the consumed spectrum stage with a
