@@ -435,6 +435,16 @@ def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
 
 
+def slab_barriers_per_time_step(st, ffts):
+    """Rank barriers of one time step of the slab path: the fused passes need one per exchange-bearing phase (gradient out /
+    back, divergence out / back, absorption operands out / back); the library-FFT path one per exchanged field."""
+    absorbing = bool(st.get("absorbing", 0))
+    if not ffts:
+        return 6 if absorbing else 4
+    src = 2 if st.get("source_steps", 0) >= st.get("steps", 1) else 0          # the filtered source field rides along
+    return 9 + (4 if absorbing else 0) + src
+
+
 def slab_leg(args, rank, local_rank, world):
     """Appended to the N > 1 line: a short C5-style run (one 512^3 phantom grid decomposed over all ranks) next to the
     same grid on one GPU -- strong-scaling efficiency and slab-vs-single-GPU parity where the driver sees them."""
@@ -452,6 +462,7 @@ def slab_leg(args, rank, local_rank, world):
                "speedup_vs_n1": r["value"] / one["value"],
                "rel_l2_vs_single": {"p_max": rel_l2(r["fields"][0], one["p_max"]), "p_min": rel_l2(r["fields"][1], one["p_min"])},
                "exchange": r["exchange"], "exchange_stage_ms_per_time_step": xchg_ms,
+               "barriers_per_time_step": slab_barriers_per_time_step(r["st"], r["ffts"]),
                "fft_launches": r["ffts"], "single_gpu_fft_launches": one["fft_launches"],
                "stages": [{"stage": nm, "ms": round(ms, 4)} for nm, ms, _ in r["prof"]]}
     if world > 1:
@@ -484,6 +495,7 @@ def run_slab(args, rank, local_rank, world):
                                    f"z-slab decomposed over {world} GPU(s), {Nt} of {r['nt_full']} time steps per bench step",
                        "voxels": V, "time_steps": Nt},
             "detail": {"n_src": r["n_src"], "exchange": r["exchange"],
+                       "barriers_per_time_step": slab_barriers_per_time_step(st, r["ffts"]),
                        "l2": "per-rank working set exceeds the 126 MB L2; no flush needed",
                        "fft": "library FFTs" if r["ffts"] else "hand-written fused FFT passes", "checksum_p_max": r["checksum"]},
             "e2e": None, "gpu_launches": int(r["launches"]), "fft_launches": int(r["ffts"]), "clocks": r["clocks"],
