@@ -61,3 +61,43 @@ def inverse(T: np.ndarray, world: int, Nx: int) -> np.ndarray:
     """T[z][kyl][kx] -> real slab (normalised like numpy's irfftn)."""
     H = exchange_backward(np.fft.ifft(T, axis=0), world)
     return np.fft.irfft2(H, s=(H.shape[1], Nx), axes=(1, 2))
+
+
+# ------------------------------------------------------------------------------------------------
+# The same decomposition with the exchange done the way the fused passes do it (csrc/fft_wide.cuh, wide.cu): there is no
+# pack kernel -- the thread that holds a spectrum value after its line transform stores it straight into the owning rank's
+# buffer.  A line of N = A x B points is held by B threads; after the transform thread u < A has X[u + A kb] in register kb.
+# With G | B that value's row ky = u + A kb belongs to rank kb // (B / G) at local row u + A (kb % (B / G)); with G | A the
+# plane z = t + B i (thread t < B, register i < A, real side) belongs to rank i // (A / G) at local plane t + B (i % (A / G)).
+# The functions below route element by element with exactly that arithmetic (no ky // nyl division) and move the blocks with
+# gloo instead of NVLink stores.
+
+def routed_forward(H: np.ndarray, world: int, ab_y) -> np.ndarray:
+    """H[zl][ky][kx] -> T[z][kyl][kx] through the per-thread routing of kw_y_fwd (Q.G > 0)."""
+    A, B = ab_y
+    nzl, Ny, Nxh = H.shape
+    assert Ny == A * B and B % world == 0
+    bg, nyl = B // world, Ny // world
+    send = np.zeros((world, nzl, nyl, Nxh), dtype=H.dtype)
+    for u in range(A):                       # thread
+        for kb in range(B):                  # register
+            q, rem = divmod(kb, bg)
+            send[q, :, u + A * rem, :] = H[:, u + A * kb, :]
+    recv = _all_to_all(send)                 # [src][zl][kyl][kx]: rank src's planes
+    return recv.reshape(world * nzl, nyl, Nxh)
+
+
+def routed_backward(T: np.ndarray, world: int, ab_z, rank: int) -> np.ndarray:
+    """T[z][kyl][kx] -> H[zl][ky][kx] through the per-thread routing of kw_z (Q.G > 0): plane blocks by register index,
+    this rank's rows land at ky0 + kyl in the owner's buffer."""
+    A, B = ab_z
+    Nz, nyl, Nxh = T.shape
+    assert Nz == A * B and A % world == 0
+    ag, nzl = A // world, Nz // world
+    send = np.zeros((world, nzl, nyl, Nxh), dtype=T.dtype)
+    for t in range(B):                       # thread (real side)
+        for i in range(A):                   # register
+            q, rem = divmod(i, ag)
+            send[q, t + B * rem, :, :] = T[t + B * i, :, :]
+    recv = _all_to_all(send)                 # [src][zl][kyl][kx]: rank src's ky rows
+    return np.concatenate([recv[q] for q in range(world)], axis=1)

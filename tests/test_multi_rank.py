@@ -148,6 +148,30 @@ def test_slab_fft_two_ranks_matches_fftn(shape):
         assert out[r][0] < 1e-10 and out[r][1] < 1e-12, out
 
 
+def _slab_fft_routed(rank, world, shape, ab_y, ab_z, seed):
+    """The exchange of the fused passes (csrc/fft_wide.cuh with Q.G > 0): every spectrum value goes from the thread /
+    register that holds it after the line transform straight into the owner's buffer, by block arithmetic."""
+    from oracle import slab as oslab
+    rng = np.random.default_rng(seed)
+    Nx, Ny, Nz = shape
+    full = rng.standard_normal((Nz, Ny, Nx)).astype(np.float64)
+    nzl, nyl = Nz // world, Ny // world
+    mine = full[rank * nzl:(rank + 1) * nzl]
+    T = np.fft.fft(oslab.routed_forward(np.fft.rfft2(mine, axes=(1, 2)), world, ab_y), axis=0)
+    want = np.fft.fftn(full, axes=(0, 1, 2))[:, :, : Nx // 2 + 1]
+    err_f = float(np.abs(T - want[:, rank * nyl:(rank + 1) * nyl, :]).max())
+    H = oslab.routed_backward(np.fft.ifft(T, axis=0), world, ab_z, rank)
+    back = np.fft.irfft2(H, s=(Ny, Nx), axes=(1, 2))
+    return err_f, float(np.abs(back - mine).max())
+
+
+@pytest.mark.parametrize("shape,ab_y,ab_z", [((8, 64, 128), (8, 8), (8, 16)), ((6, 128, 64), (8, 16), (8, 8))])
+def test_slab_fft_routed_stores_two_ranks_matches_fftn(shape, ab_y, ab_z):
+    out = _spawn(_slab_fft_routed, 2, shape, ab_y, ab_z, 147)
+    for r in (0, 1):
+        assert out[r][0] < 1e-9 and out[r][1] < 1e-12, out
+
+
 # ------------------------------------------------------------------------------------------------
 def _candidates(rank, world, n_poses):
     """Protocol.simulate_candidates under torch.distributed: pose i runs on rank i mod world, every rank ends up with
